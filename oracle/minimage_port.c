@@ -1,0 +1,204 @@
+/*
+ * oracle/minimage_port.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, strict IEEE float32: build with
+ * -fno-fast-math -ffp-contract=off) of the three minimum-image pair loops of
+ * kpounot/NAMDAnalyzer's OpenMP build.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library;
+ * the product (namdanalyzer_b200) never does.
+ *
+ * Parity pin: checked bit-for-bit against the reference's own sources compiled
+ * where they lie (oracle/_ref/libref_strict.so, see oracle/Makefile and
+ * tests/test_oracle.py) and against the golden vectors those produced
+ * (tests/golden/).
+ *
+ * Each function cites the reference lines it follows; paths are relative to
+ * /root/reference/package/NAMDAnalyzer/lib/openmp/src/.
+ *
+ * Deliberate differences from the reference text:
+ *   B-3  getWithin.cpp:55 indexes outSel[atomId*nbrFrames + frame] (out of
+ *        bounds for nbrFrames > 1).  Both branches it guards write the same
+ *        value, so the result does not depend on it; the port drops the read
+ *        and therefore handles any number of frames.
+ *   B-4  getDistances.cpp:57 assigns (last frame / nF); the documented and
+ *        legacy-CUDA behaviour is the mean over frames.  The port returns the
+ *        float64 SUM over frames of the per-frame float32 distance so the
+ *        caller can form either.
+ *   B-8  getRadialNbrDensity.cpp:44 accumulates 1.0/nF in float32.  The port
+ *        counts in uint64 (exactly what the reference produces when driven one
+ *        frame per call, where the increment is 1.0).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* d - c*roundf(d/c): division, round-half-away, product and difference each
+ * rounded once to binary32 (getWithin.cpp:63, getDistances.cpp:52-54,
+ * getRadialNbrDensity.cpp:34-36). */
+static inline float wrap1(float d, float c)
+{
+    float q = d / c;
+    float n = roundf(q);
+    float p = c * n;
+    return d - p;
+}
+
+/* ((x*x + y*y) + z*z), every operation rounded (getWithin.cpp:73,
+ * getDistances.cpp:56, getRadialNbrDensity.cpp:38). */
+static inline float norm2(float x, float y, float z)
+{
+    float xx = x * x;
+    float yy = y * y;
+    float zz = z * z;
+    float s = xx + yy;
+    return s + zz;
+}
+
+/* getWithin.cpp:9-90.  allAtoms [nAtoms][nFrames][3], cellDims [nFrames][3],
+ * out int32 [nAtoms][nFrames] (only ever set to 1, never cleared).
+ * literal_early_out != 0 keeps the per-axis tests of lines 64-71, which compare
+ * a signed component against distance squared; 0 gives the
+ * pure predicate r2 <= distance^2. */
+void port_get_within(const float *allAtoms, int nAtoms, int nFrames,
+                     const int *refSel, int refSize,
+                     const int *outSel, int outSelSize,
+                     int *out, const float *cellDims, float distance,
+                     int literal_early_out)
+{
+    (void)nAtoms;
+    const float squaredDist = distance * distance;          /* :29 */
+    #pragma omp parallel for schedule(static)
+    for (int frame = 0; frame < nFrames; ++frame) {        /* :31 */
+        const float cx = cellDims[3 * frame];
+        const float cy = cellDims[3 * frame + 1];
+        const float cz = cellDims[3 * frame + 2];
+        for (int r = 0; r < refSize; ++r) {                 /* :37 */
+            const int refIdx = refSel[r];
+            const float *ref = allAtoms + 3 * ((size_t)nFrames * refIdx + frame);
+            const float sx = ref[0], sy = ref[1], sz = ref[2];
+            for (int a = 0; a < outSelSize; ++a) {          /* :46 */
+                const int atomIdx = outSel[a];
+                const float *at = allAtoms + 3 * ((size_t)nFrames * atomIdx + frame);
+                /* :55-86 -- with out==1 and refIdx==atomIdx the else-branch
+                 * rewrites the 1 that is already there; otherwise compute. */
+                float dx = at[0] - sx;                      /* :58-60 atom - ref */
+                float dy = at[1] - sy;
+                float dz = at[2] - sz;
+                dx = wrap1(dx, cx);                         /* :63 */
+                if (literal_early_out && dx > squaredDist) continue;   /* :64-65 */
+                dy = wrap1(dy, cy);
+                if (literal_early_out && dy > squaredDist) continue;   /* :67-68 */
+                dz = wrap1(dz, cz);
+                if (literal_early_out && dz > squaredDist) continue;   /* :70-71 */
+                if (norm2(dx, dy, dz) <= squaredDist)       /* :73-75 */
+                    out[(size_t)atomIdx * nFrames + frame] = 1;        /* :77 */
+            }
+        }
+    }
+}
+
+/* getDistances.cpp:9-63.  sel1 [n1][nF][3], sel2 [n2][nF][3].
+ * sum64[i*n2+j] += sqrtf(r2) for every frame; with sameSel only j > i is
+ * visited (:44) and the rest of sum64 is left untouched.
+ * If last32 != NULL it receives the per-frame float32 distance of the LAST
+ * frame (what the reference's assignment leaves behind, before its /nF). */
+void port_get_distances(const float *sel1, int n1, const float *sel2, int n2,
+                        double *sum64, float *last32,
+                        const float *cellDims, int nFrames, int sameSel)
+{
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < n1; ++i) {                          /* :35 */
+        for (int frame = 0; frame < nFrames; ++frame) {    /* :26 */
+            const float cx = cellDims[3 * frame];
+            const float cy = cellDims[3 * frame + 1];
+            const float cz = cellDims[3 * frame + 2];
+            const float *a = sel1 + 3 * ((size_t)i * nFrames + frame);
+            for (int j = (sameSel == 1 ? i + 1 : 0); j < n2; ++j) {   /* :44 */
+                const float *b = sel2 + 3 * ((size_t)j * nFrames + frame);
+                float dx = b[0] - a[0];                     /* :47-49 sel2 - sel1 */
+                float dy = b[1] - a[1];
+                float dz = b[2] - a[2];
+                dx = wrap1(dx, cx);                         /* :52-54 */
+                dy = wrap1(dy, cy);
+                dz = wrap1(dz, cz);
+                float dist = sqrtf(norm2(dx, dy, dz));      /* :56 float overload */
+                sum64[(size_t)i * n2 + j] += (double)dist;
+                if (last32) last32[(size_t)i * n2 + j] = dist;
+            }
+        }
+    }
+}
+
+/* getRadialNbrDensity.cpp:8-52.  counts[g*outSize + idx] += 1 for every
+ * (row, col, frame) with 0 <= idx < outSize, idx = (int)(sqrtf(r2)/dr) (:38-41).
+ * groupId == NULL means a single group (the reference call); otherwise
+ * groupId[col] in [0, nGroups) selects the histogram row (one reference call
+ * per residue, dataAnalysis/RadialDensity.py:84-103, batched).
+ * maxR is accepted and ignored exactly as the reference ignores it (B-9). */
+void port_get_rdf_counts(const float *sel1, int n1, const float *sel2, int n2,
+                         uint64_t *counts, int outSize, const int *groupId, int nGroups,
+                         const float *cellDims, int nFrames, int sameSel,
+                         float maxR, float dr)
+{
+    (void)maxR;
+    const size_t H = (size_t)outSize * (size_t)(groupId ? nGroups : 1);
+    #pragma omp parallel
+    {
+        uint64_t *local = (uint64_t *)calloc(H ? H : 1, sizeof(uint64_t));
+        #pragma omp for schedule(dynamic, 8) collapse(2)
+        for (int frame = 0; frame < nFrames; ++frame) {    /* :12 */
+            for (int row = 0; row < n1; ++row) {            /* :20 */
+                const float cx = cellDims[3 * frame];
+                const float cy = cellDims[3 * frame + 1];
+                const float cz = cellDims[3 * frame + 2];
+                const float *a = sel1 + 3 * ((size_t)row * nFrames + frame);
+                for (int col = (sameSel == 1 ? row + 1 : 0); col < n2; ++col) {  /* :27 */
+                    const float *b = sel2 + 3 * ((size_t)col * nFrames + frame);
+                    float dx = a[0] - b[0];                 /* :29-31 sel1 - sel2 */
+                    float dy = a[1] - b[1];
+                    float dz = a[2] - b[2];
+                    dx = wrap1(dx, cx);                     /* :34-36 */
+                    dy = wrap1(dy, cy);
+                    dz = wrap1(dz, cz);
+                    float dist = sqrtf(norm2(dx, dy, dz));  /* :38 */
+                    float t = dist / dr;                    /* :40 float / float */
+                    /* (int)t is undefined in C for NaN / out-of-range; x86
+                     * cvttss2si returns INT_MIN there, which fails idx >= 0. */
+                    if (!(t > -1.0f && t < 2147483648.0f)) continue;
+                    int idx = (int)t;
+                    if (idx >= 0 && idx < outSize) {        /* :41 */
+                        size_t g = groupId ? (size_t)groupId[col] : 0;
+                        local[g * outSize + idx] += 1;      /* :44 with nF = 1 */
+                    }
+                }
+            }
+        }
+        #pragma omp critical
+        for (size_t k = 0; k < H; ++k) counts[k] += local[k];
+        free(local);
+    }
+}
+
+/* Per-pair probe used by the tests to enumerate pairs near an edge: returns the
+ * strict float32 r2 for one pair in one frame with the sign convention of
+ * getRadialNbrDensity.cpp:29-31 (a - b). */
+float port_pair_r2(const float *a, const float *b, const float *cell)
+{
+    float dx = wrap1(a[0] - b[0], cell[0]);
+    float dy = wrap1(a[1] - b[1], cell[1]);
+    float dz = wrap1(a[2] - b[2], cell[2]);
+    return norm2(dx, dy, dz);
+}
+
+int port_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,114 @@
+"""oracle.port -- TEST INFRASTRUCTURE.  ctypes loader for ``minimage_port.c`` (our
+plain-C, strict-IEEE restatement of lib/openmp/src/{getWithin,getDistances,
+getRadialNbrDensity}.cpp).  Built by ``make -C oracle port`` /
+``__graft_entry__.build()`` into ``oracle/_build/libminimage_port.so``."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libminimage_port.so")
+_f32p = ctypes.POINTER(ctypes.c_float)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_i32p = ctypes.POINTER(ctypes.c_int)
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "minimage_port.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "port"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_SO)
+        L.port_get_within.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, _i32p, ctypes.c_int, _i32p,
+                                      ctypes.c_int, _i32p, _f32p, ctypes.c_float, ctypes.c_int]
+        L.port_get_within.restype = None
+        L.port_get_distances.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int, _f64p, _f32p, _f32p,
+                                         ctypes.c_int, ctypes.c_int]
+        L.port_get_distances.restype = None
+        L.port_get_rdf_counts.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int, _u64p, ctypes.c_int,
+                                          _i32p, ctypes.c_int, _f32p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_float, ctypes.c_float]
+        L.port_get_rdf_counts.restype = None
+        L.port_pair_r2.argtypes = [_f32p, _f32p, _f32p]
+        L.port_pair_r2.restype = ctypes.c_float
+        L.port_num_threads.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def num_threads():
+    return lib().port_num_threads()
+
+
+def within(allAtoms, refSel, outSel, cellDims, distance, literal_early_out=True, out=None):
+    """-> int32 [nAtoms][nFrames]; any number of frames."""
+    allAtoms = np.ascontiguousarray(allAtoms, np.float32)
+    cellDims = np.ascontiguousarray(cellDims, np.float32)
+    refSel = np.ascontiguousarray(refSel, np.int32)
+    outSel = np.ascontiguousarray(outSel, np.int32)
+    nA, nF = allAtoms.shape[:2]
+    if out is None:
+        out = np.zeros((nA, nF), np.int32)
+    lib().port_get_within(allAtoms.ctypes.data_as(_f32p), nA, nF,
+                          refSel.ctypes.data_as(_i32p), refSel.size,
+                          outSel.ctypes.data_as(_i32p), outSel.size,
+                          out.ctypes.data_as(_i32p), cellDims.ctypes.data_as(_f32p),
+                          ctypes.c_float(distance), int(bool(literal_early_out)))
+    return out
+
+
+def distances_sum(sel1, sel2, cellDims, sameSel, want_last=False):
+    """-> float64 [n1][n2] sum over frames of the per-frame float32 distance
+    (+ the last frame's float32 distances if want_last)."""
+    sel1 = np.ascontiguousarray(sel1, np.float32)
+    sel2 = np.ascontiguousarray(sel2, np.float32)
+    cellDims = np.ascontiguousarray(cellDims, np.float32)
+    n1, nF = sel1.shape[:2]
+    n2 = sel2.shape[0]
+    s = np.zeros((n1, n2), np.float64)
+    last = np.zeros((n1, n2), np.float32) if want_last else None
+    lib().port_get_distances(sel1.ctypes.data_as(_f32p), n1, sel2.ctypes.data_as(_f32p), n2,
+                             s.ctypes.data_as(_f64p),
+                             last.ctypes.data_as(_f32p) if want_last else None,
+                             cellDims.ctypes.data_as(_f32p), nF, int(sameSel))
+    return (s, last) if want_last else s
+
+
+def rdf_counts(sel1, sel2, cellDims, sameSel, outSize, dr, maxR=0.0, groupId=None, nGroups=1):
+    """-> uint64 [outSize] (or [nGroups][outSize]) exact pair counts over all frames."""
+    sel1 = np.ascontiguousarray(sel1, np.float32)
+    sel2 = np.ascontiguousarray(sel2, np.float32)
+    cellDims = np.ascontiguousarray(cellDims, np.float32)
+    n1, nF = sel1.shape[:2]
+    n2 = sel2.shape[0]
+    if groupId is None:
+        counts = np.zeros(outSize, np.uint64)
+        gp = None
+        nGroups = 1
+    else:
+        groupId = np.ascontiguousarray(groupId, np.int32)
+        assert groupId.size == n2 and groupId.min() >= 0 and groupId.max() < nGroups
+        counts = np.zeros((nGroups, outSize), np.uint64)
+        gp = groupId.ctypes.data_as(_i32p)
+    lib().port_get_rdf_counts(sel1.ctypes.data_as(_f32p), n1, sel2.ctypes.data_as(_f32p), n2,
+                              counts.ctypes.data_as(_u64p), outSize, gp, nGroups,
+                              cellDims.ctypes.data_as(_f32p), nF, int(sameSel),
+                              ctypes.c_float(maxR), ctypes.c_float(dr))
+    return counts
+
+
+def pair_r2(a, b, cell):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    cell = np.ascontiguousarray(cell, np.float32)
+    return float(lib().port_pair_r2(a.ctypes.data_as(_f32p), b.ctypes.data_as(_f32p),
+                                    cell.ctypes.data_as(_f32p)))

@@ -1,0 +1,165 @@
+"""oracle.ref -- TEST INFRASTRUCTURE.  ctypes driver for the reference's own OpenMP
+sources compiled by ``oracle/Makefile`` into ``oracle/_ref/libref_{strict,fast}.so``.
+
+The reference declares its functions without ``extern "C"``
+(package/NAMDAnalyzer/lib/libFunc.h:37-48,57), so they are bound by their mangled
+names.  Every call is made ONE FRAME AT A TIME:
+
+* multi-frame ``getWithin`` reads out of bounds and segfaults
+  (lib/openmp/src/getWithin.cpp:55);
+* multi-frame ``getDistances`` assigns instead of accumulating
+  (lib/openmp/src/getDistances.cpp:57);
+* with one frame ``getRadialNbrDensity`` adds exactly 1.0 per pair
+  (lib/openmp/src/getRadialNbrDensity.cpp:44), so float32 bins are exact integers
+  (below 2**24 per bin per frame).
+"""
+import ctypes
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int)
+
+_SYMS = {
+    "getWithin": ("_Z9getWithinPfiiPiiS0_iS0_S_f",
+                  [_f32p, ctypes.c_int, ctypes.c_int, _i32p, ctypes.c_int, _i32p, ctypes.c_int,
+                   _i32p, _f32p, ctypes.c_float]),
+    "getDistances": ("_Z12getDistancesPfiS_iS_S_ii",
+                     [_f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p, _f32p, ctypes.c_int, ctypes.c_int]),
+    "getRadialNbrDensity": ("_Z19getRadialNbrDensityPfiS_iS_iS_iiff",
+                            [_f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p,
+                             ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float]),
+    "getParallelBackend": ("_Z18getParallelBackendv", []),
+}
+
+
+def lib_path(kind="strict"):
+    return os.path.join(_HERE, "_ref", "libref_%s.so" % kind)
+
+
+def available(kind="strict"):
+    return os.path.exists(lib_path(kind))
+
+
+class RefLib:
+    """One compiled build of the reference ('strict' = parity, 'fast' = shipped flags)."""
+
+    def __init__(self, kind="strict"):
+        self.kind = kind
+        self.lib = ctypes.CDLL(lib_path(kind))
+        self.fn = {}
+        for name, (sym, argtypes) in _SYMS.items():
+            f = getattr(self.lib, sym)
+            f.argtypes = argtypes
+            f.restype = ctypes.c_int if name == "getParallelBackend" else None
+            self.fn[name] = f
+
+    @staticmethod
+    def _quiet():
+        """The reference printf()s a progress line per frame; silence fd 1 around calls."""
+        class _Q:
+            def __enter__(s):
+                import sys
+                sys.stdout.flush()
+                s.saved = os.dup(1)
+                s.null = os.open(os.devnull, os.O_WRONLY)
+                os.dup2(s.null, 1)
+            def __exit__(s, *a):
+                # the reference leaves text in the C stdio buffer; flush it into /dev/null
+                ctypes.CDLL(None).fflush(None)
+                os.dup2(s.saved, 1)
+                os.close(s.saved)
+                os.close(s.null)
+        return _Q()
+
+    def parallel_backend(self):
+        return self.fn["getParallelBackend"]()
+
+    # -- per-frame drivers ---------------------------------------------------------
+    def within(self, allAtoms, refSel, outSel, cellDims, distance):
+        """-> int32 [nAtoms][nFrames] mask, per-frame calls of the reference getWithin."""
+        allAtoms = np.ascontiguousarray(allAtoms, np.float32)
+        cellDims = np.ascontiguousarray(cellDims, np.float32)
+        refSel = np.ascontiguousarray(refSel, np.int32)
+        outSel = np.ascontiguousarray(outSel, np.int32)
+        nA, nF = allAtoms.shape[:2]
+        out = np.zeros((nA, nF), np.int32)
+        with self._quiet():
+            for f in range(nF):
+                xyz = np.ascontiguousarray(allAtoms[:, f:f + 1, :])
+                cell = np.ascontiguousarray(cellDims[f:f + 1])
+                o = np.zeros((nA, 1), np.int32)
+                self.fn["getWithin"](xyz.ctypes.data_as(_f32p), nA, 1,
+                                     refSel.ctypes.data_as(_i32p), refSel.size,
+                                     outSel.ctypes.data_as(_i32p), outSel.size,
+                                     o.ctypes.data_as(_i32p), cell.ctypes.data_as(_f32p),
+                                     ctypes.c_float(distance))
+                out[:, f] = o[:, 0]
+        return out
+
+    def distances_per_frame(self, sel1, sel2, cellDims, sameSel):
+        """-> float32 [nFrames][n1][n2], the reference getDistances called frame by frame
+        (entries the reference does not visit stay 0)."""
+        sel1 = np.ascontiguousarray(sel1, np.float32)
+        sel2 = np.ascontiguousarray(sel2, np.float32)
+        cellDims = np.ascontiguousarray(cellDims, np.float32)
+        n1, nF = sel1.shape[:2]
+        n2 = sel2.shape[0]
+        res = np.zeros((nF, n1, n2), np.float32)
+        with self._quiet():
+            for f in range(nF):
+                a = np.ascontiguousarray(sel1[:, f:f + 1, :])
+                b = np.ascontiguousarray(sel2[:, f:f + 1, :])
+                cell = np.ascontiguousarray(cellDims[f:f + 1])
+                o = np.zeros((n1, n2), np.float32)
+                self.fn["getDistances"](a.ctypes.data_as(_f32p), n1, b.ctypes.data_as(_f32p), n2,
+                                        o.ctypes.data_as(_f32p), cell.ctypes.data_as(_f32p), 1, int(sameSel))
+                res[f] = o
+        return res
+
+    def rdf_counts(self, sel1, sel2, cellDims, sameSel, outSize, dr, maxR=0.0, frames=None):
+        """-> int64 [outSize] exact pair counts, the reference getRadialNbrDensity per frame."""
+        same_obj = sel2 is sel1
+        sel1 = np.ascontiguousarray(sel1, np.float32)
+        sel2 = sel1 if same_obj else np.ascontiguousarray(sel2, np.float32)
+        cellDims = np.ascontiguousarray(cellDims, np.float32)
+        n1, nF = sel1.shape[:2]
+        n2 = sel2.shape[0]
+        tot = np.zeros(outSize, np.int64)
+        with self._quiet():
+            for f in (range(nF) if frames is None else frames):
+                a = np.ascontiguousarray(sel1[:, f:f + 1, :])
+                b = a if same_obj else np.ascontiguousarray(sel2[:, f:f + 1, :])
+                cell = np.ascontiguousarray(cellDims[f:f + 1])
+                o = np.zeros(outSize, np.float32)
+                self.fn["getRadialNbrDensity"](a.ctypes.data_as(_f32p), n1, b.ctypes.data_as(_f32p), n2,
+                                               o.ctypes.data_as(_f32p), outSize, cell.ctypes.data_as(_f32p),
+                                               1, int(sameSel), ctypes.c_float(maxR), ctypes.c_float(dr))
+                assert o.max(initial=0.0) < 2 ** 24, "per-frame bin count left float32's exact range"
+                tot += o.astype(np.int64)
+        return tot
+
+    # -- raw multi-frame calls, as the reference's callers make them (for timing) ---
+    def raw_rdf(self, sel1, sel2, out, cellDims, sameSel, maxR, dr):
+        with self._quiet():
+            self.fn["getRadialNbrDensity"](sel1.ctypes.data_as(_f32p), sel1.shape[0],
+                                           sel2.ctypes.data_as(_f32p), sel2.shape[0],
+                                           out.ctypes.data_as(_f32p), out.size,
+                                           cellDims.ctypes.data_as(_f32p), cellDims.shape[0],
+                                           int(sameSel), ctypes.c_float(maxR), ctypes.c_float(dr))
+
+    def raw_distances(self, sel1, sel2, out, cellDims, sameSel):
+        with self._quiet():
+            self.fn["getDistances"](sel1.ctypes.data_as(_f32p), sel1.shape[0],
+                                    sel2.ctypes.data_as(_f32p), sel2.shape[0],
+                                    out.ctypes.data_as(_f32p), cellDims.ctypes.data_as(_f32p),
+                                    cellDims.shape[0], int(sameSel))
+
+    def raw_within_frame(self, xyz1, refSel, outSel, out1, cell1, distance):
+        """one-frame call on prepared (nAtoms,1,3)/(1,3)/(nAtoms,1) arrays (timing loop)."""
+        self.fn["getWithin"](xyz1.ctypes.data_as(_f32p), xyz1.shape[0], 1,
+                             refSel.ctypes.data_as(_i32p), refSel.size,
+                             outSel.ctypes.data_as(_i32p), outSel.size,
+                             out1.ctypes.data_as(_i32p), cell1.ctypes.data_as(_f32p),
+                             ctypes.c_float(distance))
