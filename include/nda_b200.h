@@ -1,0 +1,155 @@
+/*
+ * nda_b200.h -- C ABI of libnda_b200.so: the minimum-image pair path of
+ * kpounot/NAMDAnalyzer (getWithin / getDistances / getRadialNbrDensity) as
+ * hand-written sm_100a CUDA.  Plain pointers and sizes only; no torch, no C++
+ * types.  Every function returns 0 on success and a non-zero code on failure;
+ * nda_last_error() then holds a message (thread-local).  Nothing here ever
+ * calls exit() (the reference's CUDA build does: lib/cuda/src/getWithin.cu:9-17).
+ *
+ * Reference interface replaced (paths relative to
+ * /root/reference/package/NAMDAnalyzer/):
+ *   lib/libFunc.h:37-38   getDistances          -> nda_get_distances
+ *   lib/libFunc.h:41-43   getRadialNbrDensity   -> nda_get_radial_nbr_density
+ *   lib/libFunc.h:46-48   getWithin             -> nda_get_within
+ *   lib/libFunc.h:57      getParallelBackend    -> nda_get_parallel_backend
+ * which the reference binds from Cython at lib/libFunc.pyx:118-127, 131-140,
+ * 176-186, 356-358.  Argument order and meaning are the reference's, so the two
+ * headers can be diffed.
+ *
+ * Layouts (all C-contiguous, the reference's own):
+ *   coordinates  float32 [nAtoms][nFrames][3]   (dataParsers/dcdReader.py:127,175)
+ *   cellDims     float32 [nFrames][3]           (dataParsers/dcdCell.py:113-114)
+ *
+ * "host" entry points take host pointers (pageable or pinned) and do the
+ * host<->device copies themselves.  "dev" entry points take device pointers in
+ * the same layouts, enqueue on the given CUDA stream (a cudaStream_t passed as
+ * void*, NULL = the library's own stream) and do not synchronise.
+ */
+#ifndef NDA_B200_H
+#define NDA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status ------------------------------------------------------------------- */
+#define NDA_OK              0
+#define NDA_ERR_ARG         1   /* bad argument (null pointer, negative size, ...)   */
+#define NDA_ERR_CUDA        2   /* a CUDA runtime call or kernel failed             */
+#define NDA_ERR_NO_DEVICE   3   /* no usable sm_100 device                          */
+
+const char *nda_last_error(void);
+/* lib/libFunc.h:57 -- 2 = "CUDA build" so NAMDDCD.getWithin always takes the native
+ * branch and never the scipy kd-tree (dataParsers/dcdParser.py:181). */
+int  nda_get_parallel_backend(void);
+int  nda_device_count(void);
+int  nda_set_device(int device);          /* device used by the calling thread's context */
+int  nda_get_device(void);
+/* kernels launched by this library in this process since the last reset */
+uint64_t nda_launch_count(void);
+void     nda_launch_count_reset(void);
+/* 0 (default): literal getWithin.cpp:64-71 per-axis early-outs; 1: pure r2 <= d^2 */
+int  nda_set_within_pure_predicate(int on);
+
+/* ---- drop-in host entry points (reference signatures) --------------------------- */
+
+/* lib/openmp/src/getWithin.cpp:9-90.  out int32 [nbrAtoms][nbrFrames]: entries of
+ * outSel atoms within `distance` of any refSel atom are set to 1; nothing is cleared. */
+int nda_get_within(const float *allAtoms, int nbrAtoms, int nbrFrames,
+                   const int *refSel, int refSize, const int *outSel, int outSelSize,
+                   int *out, const float *cellDims, float distance);
+
+/* lib/openmp/src/getDistances.cpp:9-63.  out float32 [sel1_size][sel2_size] = mean over
+ * frames of the minimum-image distance (the documented behaviour,
+ * dataParsers/dcdParser.py:103-105, and what lib/cuda/src/getDistances.cu:49 computes).
+ * sameSel != 0: sel2 is sel1; the matrix is filled symmetrically, diagonal 0. */
+int nda_get_distances(const float *sel1, int sel1_size, const float *sel2, int sel2_size,
+                      float *out, const float *cellDims, int nbrFrames, int sameSel);
+
+/* lib/openmp/src/getRadialNbrDensity.cpp:8-52.  out float32 [outSize] is OVERWRITTEN with
+ * count[idx] / nbrFrames, idx = (int)(dist/dr); sameSel != 0 counts each unordered pair
+ * once (col > row).  maxR is accepted and ignored, as in the reference. */
+int nda_get_radial_nbr_density(const float *sel1, int sel1_size, const float *sel2, int sel2_size,
+                               float *out, int outSize, const float *cellDims, int nbrFrames,
+                               int sameSel, float maxR, float dr);
+
+/* ---- extended host entry points -------------------------------------------------- */
+
+/* Exact integer pair counts and/or the batched per-group histogram that
+ * dataAnalysis/RadialDensity.py:84-103 obtains with one reference call per residue.
+ * groupId int32 [sel2_size] in [0, nGroups) (NULL: one group).  counts uint64
+ * [nGroups][outSize] and/or out float32 [nGroups][outSize] (either may be NULL) are
+ * OVERWRITTEN.  Only frames [frameBegin, frameEnd) of the nbrFrames-frame arrays are
+ * processed (the multi-GPU shard); out is still normalised by nbrFrames. */
+int nda_get_radial_nbr_counts(const float *sel1, int sel1_size, const float *sel2, int sel2_size,
+                              const int *groupId, int nGroups,
+                              uint64_t *counts, float *out, int outSize,
+                              const float *cellDims, int nbrFrames, int frameBegin, int frameEnd,
+                              int sameSel, float dr);
+
+/* Sum over frames [frameBegin, frameEnd) of the per-frame float32 distance, in float64
+ * [sel1_size][sel2_size] (OVERWRITTEN); sameSel fills both triangles. */
+int nda_get_distances_sum(const float *sel1, int sel1_size, const float *sel2, int sel2_size,
+                          double *sum, const float *cellDims, int nbrFrames,
+                          int frameBegin, int frameEnd, int sameSel);
+
+/* The within bitmask itself: bits uint32 [frameEnd-frameBegin][ceil(outSelSize/32)]
+ * (OVERWRITTEN), bit (a & 31) of word a >> 5 = outSel[a] is within.  out may be NULL. */
+int nda_get_within_bits(const float *allAtoms, int nbrAtoms, int nbrFrames,
+                        const int *refSel, int refSize, const int *outSel, int outSelSize,
+                        uint32_t *bits, int *out, const float *cellDims, float distance,
+                        int frameBegin, int frameEnd);
+
+/* ---- device-pointer entry points (inputs resident in HBM, stream-ordered) ---------- */
+
+/* d_counts uint64 [nGroups][outSize] is ACCUMULATED into (zero it first).
+ * d_sel2 == d_sel1 is required when sameSel != 0. */
+int nda_dev_radial_nbr_counts(const float *d_sel1, int sel1_size, const float *d_sel2, int sel2_size,
+                              const int *d_groupId, int nGroups,
+                              unsigned long long *d_counts, int outSize,
+                              const float *d_cellDims, int nbrFrames, int frameBegin, int frameEnd,
+                              int sameSel, float dr, void *stream);
+
+/* d_bits uint32 [frameEnd-frameBegin][ceil(outSelSize/32)] is overwritten.  If d_out
+ * (int32 [nbrAtoms][nbrFrames]) is not NULL, the rows of outSel atoms, columns
+ * [frameBegin, frameEnd), are overwritten with 0/1. */
+int nda_dev_within(const float *d_allAtoms, int nbrAtoms, int nbrFrames,
+                   const int *d_refSel, int refSize, const int *d_outSel, int outSelSize,
+                   uint32_t *d_bits, int *d_out, const float *d_cellDims, float distance,
+                   int frameBegin, int frameEnd, void *stream);
+
+/* d_sum float64 [sel1_size][sel2_size] is ACCUMULATED into (zero it first); with sameSel
+ * only j > i is accumulated (mirror on the host or with nda_dev_symmetrize). */
+int nda_dev_distances_sum(const float *d_sel1, int sel1_size, const float *d_sel2, int sel2_size,
+                          double *d_sum, const float *d_cellDims, int nbrFrames,
+                          int frameBegin, int frameEnd, int sameSel, void *stream);
+
+/* ---- measurement / test support ---------------------------------------------------- */
+
+/* Config-5 generator (namdanalyzer_b200/synth.py water_box_frame, bit-identical): writes
+ * frames [frameBegin, frameEnd) of an n_side^3-atom box into d_xyz float32
+ * [n_side^3][nbrFrames][3] and d_cellDims float32 [nbrFrames][3]. */
+int nda_dev_synth_water_box(float *d_xyz, float *d_cellDims, int n_side, int nbrFrames,
+                            int frameBegin, int frameEnd, float L, float sigma, uint32_t seed,
+                            void *stream);
+
+/* Dependent-free FFMA loop on every SM: returns the measured FP32 rate in TFLOP/s
+ * (FMA = 2 flop).  variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2. */
+int nda_measure_fp32_peak(int variant, double *tflops);
+
+/* Statistics of the last RDF / within launch on the calling thread's context:
+ * [0] pairs evaluated by the fast filter, [1] candidates re-evaluated exactly,
+ * [2] frames that ran in all-exact mode (cut-off >= half the box), [3] kernel ms. */
+int nda_last_stats(double stats[4]);
+
+/* Device time (CUDA events on the launching stream) spent in the pair kernel(s) -- rdf_kernel,
+ * within_kernel or distances_kernel, one launch per pass -- of the last entry-point call on this
+ * device; synchronises on the last of them. */
+int nda_last_kernel_ms(double *ms, int *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDA_B200_H */

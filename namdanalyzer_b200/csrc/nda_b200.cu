@@ -1,0 +1,712 @@
+// nda_b200.cu -- host side of libnda_b200.so: context, buffer cache, launch logic and the C ABI
+// declared in include/nda_b200.h.  Compiled for sm_100a only; there is no CPU path.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/nda_b200.h"
+#include "nda_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------
+// errors, launch accounting
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_within_pure{0};
+static std::mutex g_mutex;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(NDA_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,  \
+                        cudaGetErrorString(e_));                                              \
+    } while (0)
+
+#define LAUNCHED()                                                                            \
+    do {                                                                                      \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+        CK(cudaGetLastError());                                                               \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// per-device context: one stream, grow-only device buffers (the reference cudaMallocs and
+// frees on every call, lib/cuda/src/getWithin.cu:84-133)
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Ctx {
+    int dev = -1;
+    bool ready = false;
+    int numSMs = 0;
+    size_t smemOptin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf packA, packB, fp, maxAbs, ctl;        // ctl: [0..1] work counter (u32 x2), stats u64 at +16
+    DevBuf raw1, raw2, cell, idx1, idx2, gid, counts, bits, sum;
+    double stats[4] = {0, 0, 0, 0};
+    // CUDA-event brackets around the pair kernel of every pass of the last entry-point call
+    std::vector<cudaEvent_t> kev;
+    int kevUsed = 0;
+    cudaError_t kev_record(cudaStream_t st)
+    {
+        if (kevUsed >= 256) return cudaSuccess;
+        if ((int)kev.size() <= kevUsed) {
+            cudaEvent_t e;
+            cudaError_t r = cudaEventCreate(&e);
+            if (r != cudaSuccess) return r;
+            kev.push_back(e);
+        }
+        return cudaEventRecord(kev[kevUsed++], st);
+    }
+};
+
+static Ctx g_ctx[16];
+static thread_local int g_dev = -1;
+
+static int ctx_get(Ctx **out)
+{
+    if (g_dev < 0) {
+        int cur = 0;
+        cudaError_t e = cudaGetDevice(&cur);
+        if (e != cudaSuccess) return fail(NDA_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+        g_dev = cur;
+    }
+    if (g_dev >= 16) return fail(NDA_ERR_ARG, "device index %d not supported", g_dev);
+    Ctx &c = g_ctx[g_dev];
+    CK(cudaSetDevice(g_dev));
+    if (!c.ready) {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, g_dev));
+        if (prop.major != 10)
+            return fail(NDA_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                        g_dev, prop.major, prop.minor);
+        c.dev = g_dev;
+        c.numSMs = prop.multiProcessorCount;
+        c.smemOptin = prop.sharedMemPerBlockOptin;
+        CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&c.ev0));
+        CK(cudaEventCreate(&c.ev1));
+        CK(c.ctl.reserve(256));
+        c.ready = true;
+    }
+    *out = &c;
+    return NDA_OK;
+}
+
+static inline void begin_call(Ctx &c) { c.kevUsed = 0; }
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------
+// device-level drivers (inputs resident, stream-ordered)
+// ------------------------------------------------------------------------------------------
+static int launch_pack(Ctx &c, cudaStream_t st, const float *src, int nFtot, const int *gather, int n,
+                       int nPad, int f0, int nFc, const int *gid, float4 *dst, unsigned *maxAbs)
+{
+    dim3 grid(nPad / 32, (nFc + 31) / 32);
+    pack_kernel<<<grid, 256, 0, st>>>(src, nFtot, gather, n, nPad, f0, nFc, gid, dst, maxAbs);
+    LAUNCHED();
+    return NDA_OK;
+}
+
+// frames per pass so that the packed copies stay within a fixed HBM budget
+static int frames_per_pass(size_t bytesPerFrame, int nF)
+{
+    const size_t budget = (size_t)6 << 30;
+    size_t f = budget / (bytesPerFrame ? bytesPerFrame : 1);
+    if (f < 1) f = 1;
+    if (f > (size_t)nF) f = nF;
+    return (int)f;
+}
+
+static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const float *d_sel2, int n2,
+                   const int *d_gid, int nGroups, unsigned long long *d_counts, int nBins,
+                   const float *d_cell, int nF, int fb, int fe, int sameSel, float dr)
+{
+    if (n1 <= 0 || n2 <= 0 || fe <= fb || nBins <= 0) return NDA_OK;
+    if (nGroups < 1) nGroups = 1;
+    const bool grouped = d_gid != nullptr;
+    if (!grouped) nGroups = 1;
+    const size_t H = (size_t)nGroups * nBins;
+    // shared-memory budget: 2 CTAs per SM
+    const size_t perCta = (c.smemOptin * 2 + 2048 <= (size_t)228 * 1024) ? c.smemOptin : (size_t)113 * 1024;
+    size_t histBudget = (perCta > PAIR_SMEM_BASE) ? perCta - PAIR_SMEM_BASE : 0;
+    int copies = (int)std::min<size_t>(PAIR_WARPS, histBudget / (H * 4));
+    size_t smem = PAIR_SMEM_BASE + (size_t)std::max(copies, 1) * H * 4;
+    if (copies < 1) {
+        copies = 1;
+        if (smem > c.smemOptin)
+            return fail(NDA_ERR_ARG, "nGroups*outSize = %zu histogram cells do not fit in shared memory (max %zu)",
+                        H, (c.smemOptin - PAIR_SMEM_BASE) / 4);
+    }
+    const int n1Pad = sameSel ? round_up(n1, PAIR_BTILE) : round_up(n1, PAIR_ATILE);
+    const int n2Pad = sameSel ? n1Pad : round_up(n2, PAIR_BTILE);
+    const size_t bytesPerFrame = ((size_t)n1Pad + (sameSel ? 0 : (size_t)n2Pad)) * sizeof(float4);
+    const int pass = frames_per_pass(bytesPerFrame, fe - fb);
+
+    CK(c.packA.reserve((size_t)n1Pad * pass * sizeof(float4)));
+    if (!sameSel) CK(c.packB.reserve((size_t)n2Pad * pass * sizeof(float4)));
+    CK(c.fp.reserve((size_t)pass * sizeof(FrameParams)));
+    CK(c.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
+
+    const double drd = (double)dr;
+    const double lim = (double)nBins * fabs(drd);
+    const double T = lim * lim * (1.0 + 9.5367431640625e-07);       // (nBins*dr)^2 (1 + 2^-20)
+
+    unsigned *work = c.ctl.as<unsigned>();
+    unsigned long long *stats = reinterpret_cast<unsigned long long *>(c.ctl.as<unsigned char>() + 16);
+
+    RdfArgs a;
+    a.n1 = n1; a.n1Pad = n1Pad; a.n2 = n2; a.n2Pad = n2Pad;
+    a.nATiles = (n1 + PAIR_ATILE - 1) / PAIR_ATILE;
+    a.nBTiles = (n2 + PAIR_BTILE - 1) / PAIR_BTILE;
+    a.chunkTiles = std::min(a.nBTiles, 32);
+    a.nBChunks = (a.nBTiles + a.chunkTiles - 1) / a.chunkTiles;
+    a.counts = d_counts; a.nBins = nBins; a.nGroups = nGroups; a.histCopies = copies;
+    a.sameSel = sameSel ? 1 : 0; a.dr = dr;
+    a.workCounter = work; a.stats = stats;
+
+    if (grouped) CK(cudaFuncSetAttribute(rdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else         CK(cudaFuncSetAttribute(rdf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    for (int f0 = fb; f0 < fe; f0 += pass) {
+        const int nFc = std::min(pass, fe - f0);
+        CK(cudaMemsetAsync(c.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
+        CK(cudaMemsetAsync(work, 0, 8, st));
+        int rc = launch_pack(c, st, d_sel1, nF, nullptr, n1, n1Pad, f0, nFc, sameSel ? d_gid : nullptr,
+                             c.packA.as<float4>(), c.maxAbs.as<unsigned>());
+        if (rc) return rc;
+        if (!sameSel) {
+            rc = launch_pack(c, st, d_sel2, nF, nullptr, n2, n2Pad, f0, nFc, d_gid,
+                             c.packB.as<float4>(), c.maxAbs.as<unsigned>());
+            if (rc) return rc;
+        }
+        prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, c.maxAbs.as<unsigned>(), T,
+                                                             c.fp.as<FrameParams>(), stats);
+        LAUNCHED();
+        a.A = c.packA.as<float4>();
+        a.B = sameSel ? a.A : c.packB.as<float4>();
+        a.fp = c.fp.as<FrameParams>();
+        const unsigned long long items = (unsigned long long)nFc * a.nATiles * a.nBChunks;
+        if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
+        a.nItems = (unsigned)items;
+        const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)2 * c.numSMs);
+        CK(c.kev_record(st));
+        if (grouped) rdf_kernel<true><<<grid, PAIR_THREADS, smem, st>>>(a);
+        else         rdf_kernel<false><<<grid, PAIR_THREADS, smem, st>>>(a);
+        LAUNCHED();
+        CK(c.kev_record(st));
+    }
+    return NDA_OK;
+}
+
+static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, int nF,
+                      const int *d_refSel, int refSize, const int *d_outSel, int outSize,
+                      unsigned *d_bits, int *d_out, const float *d_cell, float distance, int fb, int fe)
+{
+    (void)nAtoms;
+    if (outSize <= 0 || fe <= fb) return NDA_OK;
+    const int words = (outSize + 31) / 32;
+    if (refSize <= 0) {
+        CK(cudaMemsetAsync(d_bits, 0, (size_t)(fe - fb) * words * sizeof(unsigned), st));
+    } else {
+        const int nAPad = round_up(outSize, PAIR_ATILE);
+        const int nBPad = round_up(refSize, PAIR_BTILE);
+        const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * sizeof(float4);
+        const int pass = frames_per_pass(bytesPerFrame, fe - fb);
+        CK(c.packA.reserve((size_t)nAPad * pass * sizeof(float4)));
+        CK(c.packB.reserve((size_t)nBPad * pass * sizeof(float4)));
+        CK(c.fp.reserve((size_t)pass * sizeof(FrameParams)));
+        CK(c.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
+        unsigned *work = c.ctl.as<unsigned>();
+        unsigned long long *stats = reinterpret_cast<unsigned long long *>(c.ctl.as<unsigned char>() + 16);
+
+        const float d2 = distance * distance;                  // one float32 rounding, getWithin.cpp:29
+        const double T = (double)d2 * (1.0 + 9.5367431640625e-07);
+
+        WithinArgs a;
+        a.nA = outSize; a.nAPad = nAPad; a.nB = refSize; a.nBPad = nBPad;
+        a.nATiles = nAPad / PAIR_ATILE;
+        a.nBTiles = (refSize + PAIR_BTILE - 1) / PAIR_BTILE;
+        a.wordsPerFrame = words;
+        a.d2 = d2;
+        a.literal = g_within_pure.load() ? 0 : 1;
+        a.workCounter = work; a.stats = stats;
+        const size_t smem = PAIR_SMEM_BASE;
+        CK(cudaFuncSetAttribute(within_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+        for (int f0 = fb; f0 < fe; f0 += pass) {
+            const int nFc = std::min(pass, fe - f0);
+            CK(cudaMemsetAsync(c.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
+            CK(cudaMemsetAsync(work, 0, 8, st));
+            int rc = launch_pack(c, st, d_all, nF, d_outSel, outSize, nAPad, f0, nFc, nullptr,
+                                 c.packA.as<float4>(), c.maxAbs.as<unsigned>());
+            if (rc) return rc;
+            rc = launch_pack(c, st, d_all, nF, d_refSel, refSize, nBPad, f0, nFc, nullptr,
+                             c.packB.as<float4>(), c.maxAbs.as<unsigned>());
+            if (rc) return rc;
+            prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, c.maxAbs.as<unsigned>(), T,
+                                                                 c.fp.as<FrameParams>(), stats);
+            LAUNCHED();
+            a.A = c.packA.as<float4>();
+            a.B = c.packB.as<float4>();
+            a.fp = c.fp.as<FrameParams>();
+            a.bits = d_bits + (size_t)(f0 - fb) * words;
+            const unsigned long long items = (unsigned long long)nFc * a.nATiles;
+            if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
+            a.nItems = (unsigned)items;
+            const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)2 * c.numSMs);
+            CK(c.kev_record(st));
+            within_kernel<<<grid, PAIR_THREADS, smem, st>>>(a);
+            LAUNCHED();
+            CK(c.kev_record(st));
+        }
+    }
+    if (d_out) {
+        dim3 grid((fe - fb + 255) / 256, outSize);
+        expand_mask_kernel<<<grid, 256, 0, st>>>(d_bits, words, d_outSel, outSize, nF, fb, fe - fb, d_out);
+        LAUNCHED();
+    }
+    return NDA_OK;
+}
+
+static int dev_distances(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const float *d_sel2, int n2,
+                         double *d_sum, const float *d_cell, int nF, int fb, int fe, int sameSel)
+{
+    if (n1 <= 0 || n2 <= 0 || fe <= fb) return NDA_OK;
+    const int chunks = (fe - fb + DIST_FCHUNK - 1) / DIST_FCHUNK;
+    const int zt = (n1 + DIST_NA - 1) / DIST_NA;
+    if (chunks > 65535 || zt > 65535) return fail(NDA_ERR_ARG, "selection or frame range too large for one launch");
+    dim3 grid((n2 + 7) / 8, chunks, zt);
+    CK(c.kev_record(st));
+    distances_kernel<<<grid, 256, 0, st>>>(d_sel1, n1, d_sel2, n2, d_cell, nF, fb, fe, sameSel ? 1 : 0, d_sum);
+    LAUNCHED();
+    CK(c.kev_record(st));
+    return NDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------
+// copy columns [fb, fe) of a host [n][nF][3] array into a compact device [n][fe-fb][3] array
+static int upload_columns(cudaStream_t st, float *dst, const float *src, int n, int nF, int fb, int fe)
+{
+    const size_t w = (size_t)(fe - fb) * 12;
+    if (fb == 0 && fe == nF) {
+        CK(cudaMemcpyAsync(dst, src, (size_t)n * w, cudaMemcpyHostToDevice, st));
+    } else {
+        CK(cudaMemcpy2DAsync(dst, w, src + (size_t)fb * 3, (size_t)nF * 12, w, (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    return NDA_OK;
+}
+
+static int read_stats(Ctx &c, double pairs, float ms)
+{
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpy(h, c.ctl.as<unsigned char>() + 16, sizeof h, cudaMemcpyDeviceToHost));
+    c.stats[0] = pairs;
+    c.stats[1] = (double)h[0];
+    c.stats[2] = (double)h[1];
+    c.stats[3] = (double)ms;
+    return NDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *nda_last_error(void) { return g_err.c_str(); }
+int nda_get_parallel_backend(void) { return 2; }
+
+int nda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int nda_set_device(int device)
+{
+    int n = nda_device_count();
+    if (device < 0 || device >= n) return fail(NDA_ERR_ARG, "device %d out of range (%d visible)", device, n);
+    g_dev = device;
+    CK(cudaSetDevice(device));
+    return NDA_OK;
+}
+
+int nda_get_device(void) { return g_dev; }
+uint64_t nda_launch_count(void) { return g_launches.load(); }
+void nda_launch_count_reset(void) { g_launches.store(0); }
+int nda_set_within_pure_predicate(int on) { g_within_pure.store(on ? 1 : 0); return NDA_OK; }
+
+int nda_last_stats(double stats[4])
+{
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    memcpy(stats, c->stats, sizeof c->stats);
+    return NDA_OK;
+}
+
+int nda_last_kernel_ms(double *ms, int *launches)
+{
+    if (!ms) return fail(NDA_ERR_ARG, "null pointer argument");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    double tot = 0.0;
+    int n = 0;
+    for (int i = 0; i + 1 < c->kevUsed; i += 2) {
+        float t = 0.f;
+        CK(cudaEventSynchronize(c->kev[i + 1]));
+        CK(cudaEventElapsedTime(&t, c->kev[i], c->kev[i + 1]));
+        tot += t;
+        ++n;
+    }
+    *ms = tot;
+    if (launches) *launches = n;
+    return NDA_OK;
+}
+
+// ---- device-pointer entry points -----------------------------------------------------------
+int nda_dev_radial_nbr_counts(const float *d_sel1, int n1, const float *d_sel2, int n2,
+                              const int *d_groupId, int nGroups, unsigned long long *d_counts, int outSize,
+                              const float *d_cellDims, int nF, int fb, int fe, int sameSel, float dr, void *stream)
+{
+    if (!d_sel1 || !d_sel2 || !d_counts || !d_cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (n1 < 0 || n2 < 0 || outSize < 0 || nF < 0 || fb < 0 || fe > nF) return fail(NDA_ERR_ARG, "bad size / frame range");
+    if (sameSel && (d_sel1 != d_sel2 || n1 != n2)) return fail(NDA_ERR_ARG, "sameSel requires sel2 == sel1");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    begin_call(*c);
+    CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
+    return dev_rdf(*c, st, d_sel1, n1, d_sel2, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr);
+}
+
+int nda_dev_within(const float *d_allAtoms, int nAtoms, int nF, const int *d_refSel, int refSize,
+                   const int *d_outSel, int outSelSize, uint32_t *d_bits, int *d_out,
+                   const float *d_cellDims, float distance, int fb, int fe, void *stream)
+{
+    if (!d_allAtoms || !d_bits || !d_cellDims || (refSize > 0 && !d_refSel) || (outSelSize > 0 && !d_outSel))
+        return fail(NDA_ERR_ARG, "null pointer argument");
+    if (nAtoms < 0 || nF < 0 || refSize < 0 || outSelSize < 0 || fb < 0 || fe > nF) return fail(NDA_ERR_ARG, "bad size / frame range");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    begin_call(*c);
+    CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
+    return dev_within(*c, st, d_allAtoms, nAtoms, nF, d_refSel, refSize, d_outSel, outSelSize, d_bits, d_out,
+                      d_cellDims, distance, fb, fe);
+}
+
+int nda_dev_distances_sum(const float *d_sel1, int n1, const float *d_sel2, int n2, double *d_sum,
+                          const float *d_cellDims, int nF, int fb, int fe, int sameSel, void *stream)
+{
+    if (!d_sel1 || !d_sel2 || !d_sum || !d_cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (n1 < 0 || n2 < 0 || nF < 0 || fb < 0 || fe > nF) return fail(NDA_ERR_ARG, "bad size / frame range");
+    if (sameSel && n1 != n2) return fail(NDA_ERR_ARG, "sameSel requires sel2 == sel1");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    begin_call(*c);
+    return dev_distances(*c, st, d_sel1, n1, d_sel2, n2, d_sum, d_cellDims, nF, fb, fe, sameSel);
+}
+
+// ---- host entry points ---------------------------------------------------------------------
+int nda_get_radial_nbr_counts(const float *sel1, int n1, const float *sel2, int n2,
+                              const int *groupId, int nGroups, uint64_t *counts, float *out, int outSize,
+                              const float *cellDims, int nF, int fb, int fe, int sameSel, float dr)
+{
+    if (!sel1 || !sel2 || !cellDims || (!counts && !out)) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (n1 < 0 || n2 < 0 || outSize < 0 || nF <= 0 || fb < 0 || fe > nF || fb > fe) return fail(NDA_ERR_ARG, "bad size / frame range");
+    if (!groupId) nGroups = 1;
+    if (nGroups < 1) return fail(NDA_ERR_ARG, "nGroups must be >= 1");
+    if (sameSel && n1 != n2) return fail(NDA_ERR_ARG, "sameSel requires sel2 to be sel1");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    begin_call(*c);
+    const size_t H = (size_t)nGroups * outSize;
+    std::vector<unsigned long long> h(H, 0ull);
+    float ms = 0.f;
+    if (H && n1 && n2 && fe > fb) {
+        const int nFc = fe - fb;
+        CK(c->counts.reserve(H * 8));
+        CK(c->cell.reserve((size_t)nF * 12));
+        CK(cudaMemsetAsync(c->counts.p, 0, H * 8, st));
+        CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
+        CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
+        if (groupId) {
+            for (int i = 0; i < n2; ++i)
+                if (groupId[i] < 0 || groupId[i] >= nGroups) return fail(NDA_ERR_ARG, "groupId[%d] = %d outside [0, %d)", i, groupId[i], nGroups);
+            CK(c->gid.reserve((size_t)n2 * 4));
+            CK(cudaMemcpyAsync(c->gid.p, groupId, (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
+        }
+        // upload in frame slabs so the raw copies stay bounded
+        const size_t rowBytes = ((size_t)n1 + (sameSel ? 0 : (size_t)n2)) * 12;
+        int slab = (int)std::min<size_t>((size_t)nFc, std::max<size_t>(1, ((size_t)4 << 30) / rowBytes));
+        CK(c->raw1.reserve((size_t)n1 * slab * 12));
+        if (!sameSel) CK(c->raw2.reserve((size_t)n2 * slab * 12));
+        CK(cudaEventRecord(c->ev0, st));
+        for (int f0 = fb; f0 < fe; f0 += slab) {
+            const int f1 = std::min(fe, f0 + slab);
+            rc = upload_columns(st, c->raw1.as<float>(), sel1, n1, nF, f0, f1);
+            if (rc) return rc;
+            if (!sameSel) { rc = upload_columns(st, c->raw2.as<float>(), sel2, n2, nF, f0, f1); if (rc) return rc; }
+            rc = dev_rdf(*c, st, c->raw1.as<float>(), n1, sameSel ? c->raw1.as<float>() : c->raw2.as<float>(), n2,
+                         groupId ? c->gid.as<int>() : nullptr, nGroups, c->counts.as<unsigned long long>(), outSize,
+                         c->cell.as<float>() + (size_t)f0 * 3, f1 - f0, 0, f1 - f0, sameSel, dr);
+            if (rc) return rc;
+            if (f1 < fe) CK(cudaStreamSynchronize(st));      // raw slabs are reused
+        }
+        CK(cudaEventRecord(c->ev1, st));
+        CK(cudaMemcpyAsync(h.data(), c->counts.p, H * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        const double perFrame = sameSel ? 0.5 * (double)n1 * ((double)n1 - 1.0) : (double)n1 * (double)n2;
+        rc = read_stats(*c, perFrame * nFc, ms);
+        if (rc) return rc;
+    }
+    if (counts) for (size_t i = 0; i < H; ++i) counts[i] = (uint64_t)h[i];
+    if (out)    for (size_t i = 0; i < H; ++i) out[i] = (float)((double)h[i] / (double)nF);
+    return NDA_OK;
+}
+
+int nda_get_radial_nbr_density(const float *sel1, int n1, const float *sel2, int n2, float *out, int outSize,
+                               const float *cellDims, int nF, int sameSel, float maxR, float dr)
+{
+    (void)maxR;                                             // unused by the reference as well (SURVEY B-9)
+    if (!out) return fail(NDA_ERR_ARG, "null pointer argument");
+    return nda_get_radial_nbr_counts(sel1, n1, sel2, n2, nullptr, 1, nullptr, out, outSize, cellDims, nF, 0, nF, sameSel, dr);
+}
+
+int nda_get_distances_sum(const float *sel1, int n1, const float *sel2, int n2, double *sum,
+                          const float *cellDims, int nF, int fb, int fe, int sameSel)
+{
+    if (!sel1 || !sel2 || !sum || !cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (n1 < 0 || n2 < 0 || nF <= 0 || fb < 0 || fe > nF || fb > fe) return fail(NDA_ERR_ARG, "bad size / frame range");
+    if (sameSel && n1 != n2) return fail(NDA_ERR_ARG, "sameSel requires sel2 to be sel1");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    begin_call(*c);
+    const size_t M = (size_t)n1 * n2;
+    if (M == 0) return NDA_OK;
+    if (fe == fb) { memset(sum, 0, M * 8); return NDA_OK; }
+    const int nFc = fe - fb;
+    CK(c->sum.reserve(M * 8));
+    CK(c->cell.reserve((size_t)nF * 12));
+    CK(cudaMemsetAsync(c->sum.p, 0, M * 8, st));
+    CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
+    const size_t rowBytes = ((size_t)n1 + (sameSel ? 0 : (size_t)n2)) * 12;
+    int slab = (int)std::min<size_t>((size_t)nFc, std::max<size_t>(1, ((size_t)4 << 30) / rowBytes));
+    CK(c->raw1.reserve((size_t)n1 * slab * 12));
+    if (!sameSel) CK(c->raw2.reserve((size_t)n2 * slab * 12));
+    for (int f0 = fb; f0 < fe; f0 += slab) {
+        const int f1 = std::min(fe, f0 + slab);
+        rc = upload_columns(st, c->raw1.as<float>(), sel1, n1, nF, f0, f1);
+        if (rc) return rc;
+        if (!sameSel) { rc = upload_columns(st, c->raw2.as<float>(), sel2, n2, nF, f0, f1); if (rc) return rc; }
+        rc = dev_distances(*c, st, c->raw1.as<float>(), n1, sameSel ? c->raw1.as<float>() : c->raw2.as<float>(), n2,
+                           c->sum.as<double>(), c->cell.as<float>() + (size_t)f0 * 3, f1 - f0, 0, f1 - f0, sameSel);
+        if (rc) return rc;
+        if (f1 < fe) CK(cudaStreamSynchronize(st));
+    }
+    if (sameSel) {
+        dim3 grid((n1 + 255) / 256, n1);
+        symmetrize_kernel<<<grid, 256, 0, st>>>(c->sum.as<double>(), n1);
+        LAUNCHED();
+    }
+    CK(cudaMemcpyAsync(sum, c->sum.p, M * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return NDA_OK;
+}
+
+int nda_get_distances(const float *sel1, int n1, const float *sel2, int n2, float *out,
+                      const float *cellDims, int nF, int sameSel)
+{
+    if (!out) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (n1 < 0 || n2 < 0) return fail(NDA_ERR_ARG, "bad size");
+    std::vector<double> s((size_t)n1 * n2, 0.0);
+    int rc = nda_get_distances_sum(sel1, n1, sel2, n2, s.data(), cellDims, nF, 0, nF, sameSel);
+    if (rc) return rc;
+    for (size_t i = 0; i < s.size(); ++i) out[i] = (float)(s[i] / (double)nF);
+    return NDA_OK;
+}
+
+int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *refSel, int refSize,
+                        const int *outSel, int outSelSize, uint32_t *bits, int *out,
+                        const float *cellDims, float distance, int fb, int fe)
+{
+    if (!allAtoms || !cellDims || (!bits && !out) || (refSize > 0 && !refSel) || (outSelSize > 0 && !outSel))
+        return fail(NDA_ERR_ARG, "null pointer argument");
+    if (nAtoms < 0 || nF <= 0 || refSize < 0 || outSelSize < 0 || fb < 0 || fe > nF || fb > fe)
+        return fail(NDA_ERR_ARG, "bad size / frame range");
+    for (int i = 0; i < refSize; ++i)
+        if (refSel[i] < 0 || refSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "refSel[%d] = %d outside [0, %d)", i, refSel[i], nAtoms);
+    for (int i = 0; i < outSelSize; ++i)
+        if (outSel[i] < 0 || outSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "outSel[%d] = %d outside [0, %d)", i, outSel[i], nAtoms);
+    if (outSelSize == 0 || fe == fb) return NDA_OK;
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    begin_call(*c);
+    const int nFc = fe - fb;
+    const int words = (outSelSize + 31) / 32;
+    std::vector<uint32_t> hb;
+    uint32_t *hbits = bits;
+    if (!hbits) { hb.resize((size_t)nFc * words); hbits = hb.data(); }
+
+    CK(c->cell.reserve((size_t)nF * 12));
+    CK(c->idx1.reserve((size_t)std::max(refSize, 1) * 4));
+    CK(c->idx2.reserve((size_t)outSelSize * 4));
+    CK(c->bits.reserve((size_t)nFc * words * 4));
+    CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
+    CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
+    if (refSize) CK(cudaMemcpyAsync(c->idx1.p, refSel, (size_t)refSize * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->idx2.p, outSel, (size_t)outSelSize * 4, cudaMemcpyHostToDevice, st));
+    const size_t rowBytes = (size_t)nAtoms * 12;
+    int slab = (int)std::min<size_t>((size_t)nFc, std::max<size_t>(1, ((size_t)4 << 30) / rowBytes));
+    CK(c->raw1.reserve((size_t)nAtoms * slab * 12));
+    float ms = 0.f;
+    CK(cudaEventRecord(c->ev0, st));
+    for (int f0 = fb; f0 < fe; f0 += slab) {
+        const int f1 = std::min(fe, f0 + slab);
+        rc = upload_columns(st, c->raw1.as<float>(), allAtoms, nAtoms, nF, f0, f1);
+        if (rc) return rc;
+        rc = dev_within(*c, st, c->raw1.as<float>(), nAtoms, f1 - f0, c->idx1.as<int>(), refSize,
+                        c->idx2.as<int>(), outSelSize, c->bits.as<unsigned>() + (size_t)(f0 - fb) * words, nullptr,
+                        c->cell.as<float>() + (size_t)f0 * 3, distance, 0, f1 - f0);
+        if (rc) return rc;
+        if (f1 < fe) CK(cudaStreamSynchronize(st));
+    }
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaMemcpyAsync(hbits, c->bits.p, (size_t)nFc * words * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    rc = read_stats(*c, (double)refSize * outSelSize * nFc, ms);
+    if (rc) return rc;
+    if (out) {
+        // the reference only ever stores 1 (getWithin.cpp:77,83): scatter the set bits
+        for (int f = 0; f < nFc; ++f) {
+            const uint32_t *row = hbits + (size_t)f * words;
+            for (int w = 0; w < words; ++w) {
+                uint32_t v = row[w];
+                while (v) {
+                    const int b = __builtin_ctz(v);
+                    v &= v - 1;
+                    out[(size_t)outSel[w * 32 + b] * nF + fb + f] = 1;
+                }
+            }
+        }
+    }
+    return NDA_OK;
+}
+
+int nda_get_within(const float *allAtoms, int nAtoms, int nF, const int *refSel, int refSize,
+                   const int *outSel, int outSelSize, int *out, const float *cellDims, float distance)
+{
+    if (!out) return fail(NDA_ERR_ARG, "null pointer argument");
+    return nda_get_within_bits(allAtoms, nAtoms, nF, refSel, refSize, outSel, outSelSize, nullptr, out,
+                               cellDims, distance, 0, nF);
+}
+
+// ---- measurement / test support --------------------------------------------------------------
+int nda_dev_synth_water_box(float *d_xyz, float *d_cellDims, int n_side, int nF, int fb, int fe,
+                            float L, float sigma, uint32_t seed, void *stream)
+{
+    if (!d_xyz || !d_cellDims || n_side <= 0 || n_side > 1024 || fb < 0 || fe > nF || fb > fe)
+        return fail(NDA_ERR_ARG, "bad argument");
+    if (fe == fb) return NDA_OK;
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const unsigned n = (unsigned)n_side * n_side * n_side;
+    for (int f0 = fb; f0 < fe; f0 += 32768) {
+        const int nFc = std::min(32768, fe - f0);
+        dim3 grid((n + 255) / 256, nFc);
+        synth_water_box_kernel<<<grid, 256, 0, st>>>(d_xyz, d_cellDims, n_side, nF, f0, nFc, L, sigma, seed);
+        LAUNCHED();
+    }
+    return NDA_OK;
+}
+
+int nda_measure_fp32_peak(int variant, double *tflops)
+{
+    if (!tflops) return fail(NDA_ERR_ARG, "null pointer argument");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    CK(c->bits.reserve(64));
+    const int iters = 4096, blocks = c->numSMs * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(c->ev0, st));
+        if (variant == 0) fp32_peak_kernel<0><<<blocks, 256, 0, st>>>(c->bits.as<float>(), iters, 0.999f, 0.001f);
+        else              fp32_peak_kernel<1><<<blocks, 256, 0, st>>>(c->bits.as<float>(), iters, 0.999f, 0.001f);
+        LAUNCHED();
+        CK(cudaEventRecord(c->ev1, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        const double flop = 2.0 * 16.0 * iters * 256.0 * blocks;
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    return NDA_OK;
+}
+
+} // extern "C"

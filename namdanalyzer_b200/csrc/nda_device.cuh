@@ -1,0 +1,140 @@
+// nda_device.cuh -- device-side building blocks shared by the pair kernels (sm_100a only).
+//
+//  * strict_*   : the reference's per-pair arithmetic with one IEEE rounding per operation
+//                 (lib/openmp/src/getRadialNbrDensity.cpp:29-45,
+//                 getWithin.cpp:58-77, getDistances.cpp:47-57).  Intrinsics (__fdiv_rn, __fmul_rn,
+//                 ...) are used so nvcc can neither contract to FMA nor reassociate.
+//  * fast_r2    : the FP32 filter applied to EVERY pair: rintf via the 1.5*2^23 magic constant,
+//                 reciprocal multiply, FMA-contracted wrap and norm (15 FMA-pipe instructions).
+//                 It only decides which pairs are CANDIDATES (r2' < thr, thr = in-range limit plus a
+//                 proven guard band, see prep_frames_kernel); candidates are re-evaluated with
+//                 strict_* so every count / mask bit equals the reference's bit for bit.
+//  * TMA        : 1-D bulk copies global -> shared (cp.async.bulk, SASS UBLKCP) completing on an
+//                 mbarrier.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define NDA_FULL_MASK 0xffffffffu
+#define NDA_MAGIC     12582912.0f          /* 1.5 * 2^23: x + MAGIC - MAGIC == rintf(x) for |x| < 2^22 */
+
+struct __align__(16) FrameParams {
+    float cx, cy, cz;        // cell edges of this frame
+    float thr;               // candidate threshold on the fast r2 (valid only if exact_all == 0)
+    float icx, icy, icz;     // fl(1/c)
+    int   exact_all;         // 1: cut-off too close to half the box (or odd cell): every pair strict
+};
+
+// ---------------------------------------------------------------- strict arithmetic
+__device__ __forceinline__ float strict_wrap(float d, float c)
+{
+    float q = __fdiv_rn(d, c);
+    float n = roundf(q);                    // half away from zero, as C roundf
+    float p = __fmul_rn(c, n);
+    return __fsub_rn(d, p);
+}
+
+__device__ __forceinline__ float strict_norm2(float x, float y, float z)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// a - b, wrapped, squared norm: bit-identical to the reference's float32 result
+__device__ __forceinline__ float strict_r2(float ax, float ay, float az,
+                                           float bx, float by, float bz,
+                                           float cx, float cy, float cz)
+{
+    float wx = strict_wrap(__fsub_rn(ax, bx), cx);
+    float wy = strict_wrap(__fsub_rn(ay, by), cy);
+    float wz = strict_wrap(__fsub_rn(az, bz), cz);
+    return strict_norm2(wx, wy, wz);
+}
+
+// (int)(sqrtf(r2)/dr) with the reference's range test 0 <= idx < outSize
+// (getRadialNbrDensity.cpp:38-41).  NaN / huge values fail the test exactly as x86's
+// cvttss2si result INT_MIN does.  Returns -1 when the pair is not counted.
+__device__ __forceinline__ int strict_bin(float r2, float dr, int outSize)
+{
+    float t = __fdiv_rn(__fsqrt_rn(r2), dr);
+    if (!(t > -1.0f && t < 2147483648.0f)) return -1;
+    int idx = (int)t;                       // truncation toward zero
+    return (idx >= 0 && idx < outSize) ? idx : -1;
+}
+
+// ---------------------------------------------------------------- fast filter
+struct FrameRegs {
+    float ncx, ncy, ncz;     // -c
+    float icx, icy, icz;
+    float thr;
+};
+
+__device__ __forceinline__ FrameRegs load_frame_regs(const FrameParams &p)
+{
+    FrameRegs r;
+    r.ncx = -p.cx; r.ncy = -p.cy; r.ncz = -p.cz;
+    r.icx = p.icx; r.icy = p.icy; r.icz = p.icz;
+    r.thr = p.thr;
+    return r;
+}
+
+__device__ __forceinline__ float fast_r2(float ax, float ay, float az, const float4 &b, const FrameRegs &f)
+{
+    float dx = ax - b.x;
+    float dy = ay - b.y;
+    float dz = az - b.z;
+    float nx = __fmaf_rn(dx, f.icx, NDA_MAGIC) - NDA_MAGIC;      // rintf(dx / cx)
+    float ny = __fmaf_rn(dy, f.icy, NDA_MAGIC) - NDA_MAGIC;
+    float nz = __fmaf_rn(dz, f.icz, NDA_MAGIC) - NDA_MAGIC;
+    float wx = __fmaf_rn(f.ncx, nx, dx);
+    float wy = __fmaf_rn(f.ncy, ny, dy);
+    float wz = __fmaf_rn(f.ncz, nz, dz);
+    return __fmaf_rn(wz, wz, __fmaf_rn(wy, wy, wx * wx));
+}
+
+// ---------------------------------------------------------------- mbarrier + TMA bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// global -> shared bulk copy (TMA, no tensor map needed for 1-D); bytes % 16 == 0, 16-B aligned
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}

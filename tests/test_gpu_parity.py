@@ -1,0 +1,341 @@
+"""GPU (B200): parity of the CUDA path, called through the reference-shaped Python operators and
+hence through the C ABI, against (a) the golden vectors produced by the reference's own OpenMP
+sources and (b) the C restatement (oracle/port) on fresh seeded inputs.
+
+Gates (BASELINE.json north_star):
+  * within masks and histogram counts: BIT-EXACT.  The kernels re-evaluate every candidate pair
+    with the reference's strict float32 arithmetic, so the "pairs within 1 ulp of an edge" list the
+    north_star allows for is expected to be EMPTY against the strict oracle; the tests assert that.
+  * distances: relative error <= 1e-6 (float32) against per-frame oracle distances averaged in
+    float64.
+"""
+import numpy as np
+import pytest
+
+from conftest import crc, unpack_mask
+from namdanalyzer_b200 import synth
+from namdanalyzer_b200.lib import pylibFuncs as plf
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+NB = 149
+REL_TOL = 1e-6          # north_star: distances within 1e-6 relative in float32
+
+
+def rdf_counts(a, b, cell, same, nb, dr, **kw):
+    return plf.py_getRadialNbrCounts(a, b, cell, same, nb, dr, **kw).astype(np.int64)
+
+
+def within_mask(xyz, refSel, outSel, cell, dist):
+    out = np.zeros(xyz.shape[:2], np.int32)
+    plf.py_getWithin(xyz, refSel, outSel, out, cell, dist)
+    return out
+
+
+# ------------------------------------------------------------------ golden vectors (reference output)
+
+def test_rdf_config1_full_golden(golden):
+    c = synth.config1()
+    assert crc(c["sel1"], c["cellDims"]) == golden["c1_crc"]
+    got = rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, NB, 0.1)
+    mism = np.flatnonzero(got != golden["c1_counts"])
+    assert mism.size == 0, "edge-pair list not empty: bins %s" % mism
+    # the reference-shaped call: float32 density = count / nFrames, written in place
+    out = np.full(NB, 7.0, np.float32)
+    plf.py_getRadialNbrDensity(c["sel1"], c["sel1"], out, c["cellDims"], 1, 15.0, 0.1)
+    assert np.array_equal(out, (golden["c1_counts"] / 100.0).astype(np.float32))
+
+
+def test_rdf_two_selections_and_odd_bin_width_golden(golden):
+    c = synth.config1()
+    a, b, cell = c["sel1"][:300, :10], c["sel1"][300:, :10], c["cellDims"][:10]
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    assert np.array_equal(rdf_counts(a, b, cell, 0, NB, 0.1), golden["c1ab_counts"])
+    s5 = np.ascontiguousarray(c["sel1"][:, :5])
+    assert np.array_equal(rdf_counts(s5, s5, c["cellDims"][:5], 1, 17, 0.37), golden["c1_dr037_counts"])
+
+
+@pytest.mark.parametrize("tag,dist", [("d08", 0.8), ("d35", 3.5)])
+def test_within_config1_golden(golden, tag, dist):
+    c = synth.config1()
+    xyz, cell = np.ascontiguousarray(c["sel1"][:, :5]), c["cellDims"][:5]
+    refSel = np.arange(0, 500, dtype=np.int32)
+    outSel = np.arange(0, 1000, dtype=np.int32)
+    want = unpack_mask(golden["c1_within_%s" % tag], (1000, 5))
+    assert np.array_equal(within_mask(xyz, refSel, outSel, cell, dist), want)
+
+
+def test_within_config2_golden(golden):
+    c = synth.config2(n_frames=20)
+    assert crc(c["allAtoms"], c["cellDims"]) == golden["c2_crc"]
+    want = unpack_mask(golden["c2_mask_bits"], (25000, 20))
+    got = within_mask(c["allAtoms"], c["refSel"], c["outSel"], c["cellDims"], c["distance"])
+    assert np.array_equal(got, want)
+    assert np.array_equal(got.sum(0), golden["c2_hits_per_frame"])
+    # raw bitmask agrees with the int32 mask
+    bits = plf.py_getWithinBits(c["allAtoms"], c["refSel"], c["outSel"], c["cellDims"], c["distance"])
+    exp = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :c["outSel"].size]
+    assert np.array_equal(exp.T.astype(np.int32), want[c["outSel"]])
+
+
+def test_grouped_rdf_config3_golden(golden):
+    c = synth.config3(n_frames=3)
+    got = rdf_counts(c["waters"], c["protein"], c["cellDims"], 0, NB, 0.1,
+                     groupId=c["groupId"], nGroups=c["nGroups"])
+    assert np.array_equal(got, golden["c3_group_counts"])
+    # call-by-call, the way dataAnalysis/RadialDensity.py:84-103 does it, gives the same rows
+    for r in (0, 37, 75):
+        sel = np.ascontiguousarray(c["protein"][c["groupId"] == r])
+        assert np.array_equal(rdf_counts(c["waters"], sel, c["cellDims"], 0, NB, 0.1), golden["c3_group_counts"][r])
+    out = np.zeros((c["nGroups"], NB), np.float32)
+    plf.py_getRadialNbrDensityGrouped(c["waters"], c["protein"], c["groupId"], out, c["cellDims"], 0, 15.0, 0.1)
+    assert np.array_equal(out, (golden["c3_group_counts"] / 3.0).astype(np.float32))
+
+
+def test_distances_config4_golden(golden):
+    c = synth.config4(n_frames=50)
+    out = np.zeros((7, 1231), np.float32)
+    plf.py_getDistances(c["sel1"], c["sel2"], out, c["cellDims"], 0)
+    want = golden["c4_mean64"]
+    assert np.max(np.abs(out - want) / want.clip(1e-30)) <= REL_TOL
+    # the float64 sums are exact sums of the reference's float32 per-frame distances
+    s = plf.py_getDistancesSum(c["sel1"], c["sel2"], c["cellDims"], 0)
+    assert np.max(np.abs(s / 50 - want) / want.clip(1e-30)) <= 1e-12
+    # sameSel: upper triangle equals the reference, matrix symmetric, diagonal zero (SURVEY B-6)
+    out = np.zeros((7, 7), np.float32)
+    plf.py_getDistances(c["sel1"], c["sel1"], out, c["cellDims"], 1)
+    want = golden["c4_same_mean64"]
+    iu = np.triu_indices(7, 1)
+    assert np.max(np.abs(out[iu] - want[iu]) / want[iu]) <= REL_TOL
+    assert np.array_equal(out, out.T) and np.all(np.diag(out) == 0)
+
+
+def test_rdf_config5_reduced_golden(golden):
+    c = synth.config5(n_side=27, n_frames=2)
+    assert np.array_equal(rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, NB, 0.1), golden["c5_counts"])
+
+
+def test_real_geometry_no_unit_cell_golden(golden):
+    fx = synth.fixture()
+    xyz, cell = fx["all_xyz"], fx["all_cell"]
+    want = unpack_mask(golden["ubq_mask_bits"], (6682, 3))
+    assert np.array_equal(within_mask(xyz, fx["protein_idx"], fx["water_o_idx"], cell, 3.0), want)
+    wo = np.ascontiguousarray(xyz[fx["water_o_idx"]])
+    assert np.array_equal(rdf_counts(wo, wo, cell, 1, NB, 0.1), golden["ubq_oo_counts"])
+    pr = np.ascontiguousarray(xyz[fx["protein_idx"]])
+    r53 = np.ascontiguousarray(pr[fx["protein_resid"] == 53])
+    out = np.zeros((7, 1231), np.float32)
+    plf.py_getDistances(r53, pr, out, cell, 0)
+    want = golden["ubq_dist_mean64"]
+    ok = want > 0
+    assert np.max(np.abs(out[ok] - want[ok]) / want[ok]) <= REL_TOL
+    assert np.all(out[~ok] == 0)
+
+
+# ------------------------------------------------------------------ fresh inputs vs the C restatement
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_random_shapes_against_port(seed):
+    rng = np.random.default_rng(seed)
+    n1, n2, nF = int(rng.integers(1, 1500)), int(rng.integers(1, 2500)), int(rng.integers(1, 7))
+    cell = rng.uniform(25, 60, (nF, 3)).astype(np.float32)          # orthorhombic, per frame
+    a = rng.uniform(-80, 140, (n1, nF, 3)).astype(np.float32)        # unwrapped: |q| up to ~5
+    b = rng.uniform(-80, 140, (n2, nF, 3)).astype(np.float32)
+    dr = float(rng.uniform(0.03, 0.4))
+    nb = int(rng.integers(1, 120))
+    if nb * dr > 12:
+        nb = int(12 / dr)
+    assert np.array_equal(rdf_counts(a, b, cell, 0, nb, dr), port.rdf_counts(a, b, cell, 0, nb, dr).astype(np.int64))
+    assert np.array_equal(rdf_counts(a, a, cell, 1, nb, dr), port.rdf_counts(a, a, cell, 1, nb, dr).astype(np.int64))
+    allA = np.concatenate([a, b])
+    refSel = rng.permutation(n1 + n2)[: max(1, (n1 + n2) // 3)].astype(np.int32)
+    outSel = rng.permutation(n1 + n2)[: max(1, (n1 + n2) // 2)].astype(np.int32)
+    for dist in (0.6, float(rng.uniform(1.0, 9.0))):
+        assert np.array_equal(within_mask(allA, refSel, outSel, cell, dist),
+                              port.within(allA, refSel, outSel, cell, dist))
+    s = plf.py_getDistancesSum(a[:40], b[:300], cell, 0)
+    w = port.distances_sum(a[:40], b[:300], cell, 0)
+    assert np.max(np.abs(s - w) / np.maximum(w, 1e-30)) <= 1e-12
+
+
+def test_cutoff_beyond_half_box_runs_exact_path():
+    """range >= half the cell: the rintf/roundf tie argument no longer holds, every pair must take
+    the strict path (FrameParams.exact_all) and still match bit for bit"""
+    rng = np.random.default_rng(21)
+    nF = 2
+    cell = np.array([[20.0, 22.0, 19.0], [18.5, 30.0, 21.0]], np.float32)
+    a = rng.uniform(-30, 50, (700, nF, 3)).astype(np.float32)
+    b = rng.uniform(-30, 50, (900, nF, 3)).astype(np.float32)
+    assert np.array_equal(rdf_counts(a, b, cell, 0, 140, 0.1), port.rdf_counts(a, b, cell, 0, 140, 0.1).astype(np.int64))
+    assert np.array_equal(rdf_counts(a, a, cell, 1, 200, 0.1), port.rdf_counts(a, a, cell, 1, 200, 0.1).astype(np.int64))
+    allA = np.concatenate([a, b])
+    r = np.arange(0, 700, dtype=np.int32)
+    o = np.arange(700, 1600, dtype=np.int32)
+    assert np.array_equal(within_mask(allA, r, o, cell, 11.0), port.within(allA, r, o, cell, 11.0))
+
+
+def test_half_integer_ties_and_lattice_points():
+    """coordinates on an exact lattice of the cell: d/c hits +-0.5 exactly (roundf vs rintf differ
+    there) and many pairs sit exactly on bin edges"""
+    g = np.arange(0, 16, dtype=np.float32) * 2.0                     # cell 32 -> half-integers at 16
+    pts = np.stack(np.meshgrid(g, g, g[:4], indexing="ij"), -1).reshape(-1, 1, 3).astype(np.float32)
+    cell = np.array([[32.0, 32.0, 32.0]], np.float32)
+    for nb, dr in ((149, 0.1), (64, 0.25), (40, 0.5)):
+        assert np.array_equal(rdf_counts(pts, pts, cell, 1, nb, dr), port.rdf_counts(pts, pts, cell, 1, nb, dr).astype(np.int64))
+    idx = np.arange(pts.shape[0], dtype=np.int32)
+    for dist in (2.0, 4.0, 6.0):
+        assert np.array_equal(within_mask(pts, idx[:100], idx, cell, dist), port.within(pts, idx[:100], idx, cell, dist))
+
+
+def test_within_small_distance_literal_early_out():
+    """getWithin.cpp:64-71 quirk (SURVEY B-2) reproduced by default, pure predicate on request"""
+    from namdanalyzer_b200 import _capi
+    rng = np.random.default_rng(5)
+    xyz = rng.uniform(0, 12, (3000, 2, 3)).astype(np.float32)
+    cell = np.full((2, 3), 12.0, np.float32)
+    r = np.arange(0, 1500, dtype=np.int32)
+    o = np.arange(1500, 3000, dtype=np.int32)
+    lit = port.within(xyz, r, o, cell, 0.7, literal_early_out=True)
+    pure = port.within(xyz, r, o, cell, 0.7, literal_early_out=False)
+    assert (lit != pure).any()                                      # the quirk is exercised
+    assert np.array_equal(within_mask(xyz, r, o, cell, 0.7), lit)
+    _capi.load().nda_set_within_pure_predicate(1)
+    try:
+        assert np.array_equal(within_mask(xyz, r, o, cell, 0.7), pure)
+    finally:
+        _capi.load().nda_set_within_pure_predicate(0)
+
+
+def test_edge_cases_empty_single_nan_and_preset_output():
+    cell = np.full((2, 3), 30.0, np.float32)
+    xyz = np.random.default_rng(3).uniform(0, 30, (50, 2, 3)).astype(np.float32)
+    e = np.zeros((0, 2, 3), np.float32)
+    assert rdf_counts(e, xyz, cell, 0, 10, 0.5).sum() == 0
+    assert rdf_counts(xyz, e, cell, 0, 10, 0.5).sum() == 0
+    one = np.ascontiguousarray(xyz[:1])
+    assert rdf_counts(one, one, cell, 1, 10, 0.5).sum() == 0         # a single atom has no pair
+    assert np.array_equal(rdf_counts(one, xyz, cell, 0, 40, 0.5), port.rdf_counts(one, xyz, cell, 0, 40, 0.5).astype(np.int64))
+    # NaN coordinates never count and never match
+    bad = xyz.copy()
+    bad[7, 0, 1] = np.nan
+    bad[9, 1, :] = np.inf
+    assert np.array_equal(rdf_counts(bad, bad, cell, 1, 40, 0.5), port.rdf_counts(bad, bad, cell, 1, 40, 0.5).astype(np.int64))
+    idx = np.arange(50, dtype=np.int32)
+    assert np.array_equal(within_mask(bad, idx[:20], idx, cell, 5.0), port.within(bad, idx[:20], idx, cell, 5.0))
+    # empty selections; out is only ever set, never cleared (getWithin.cpp:77)
+    out = np.zeros((50, 2), np.int32)
+    out[3, 1] = 1
+    plf.py_getWithin(xyz, np.zeros(0, np.int32), idx, out, cell, 5.0)
+    assert out.sum() == 1 and out[3, 1] == 1
+    plf.py_getWithin(xyz, idx, np.zeros(0, np.int32), out, cell, 5.0)
+    assert out.sum() == 1
+    # F-ordered cellDims, as dcdCell.__getitem__ returns for several frames (SURVEY B-5)
+    cellF = np.asfortranarray(cell)
+    assert not cellF.flags.c_contiguous
+    assert np.array_equal(within_mask(xyz, idx[:10], idx, cellF, 4.0), port.within(xyz, idx[:10], idx, cell, 4.0))
+    # duplicates in the selections
+    dup = np.array([1, 1, 2, 5, 5, 5], np.int32)
+    assert np.array_equal(within_mask(xyz, dup, dup, cell, 4.0), port.within(xyz, dup, dup, cell, 4.0))
+
+
+def test_frame_range_shards_add_up():
+    """the multi-GPU decomposition: disjoint frame ranges sum to the whole"""
+    c = synth.config1(n_frames=12)
+    whole = rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, NB, 0.1)
+    parts = sum(rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, NB, 0.1, frameBegin=b, frameEnd=e)
+                for b, e in ((0, 5), (5, 6), (6, 12)))
+    assert np.array_equal(whole, parts)
+    c4 = synth.config4(n_frames=37)
+    s = plf.py_getDistancesSum(c4["sel1"], c4["sel2"], c4["cellDims"], 0)
+    s2 = plf.py_getDistancesSum(c4["sel1"], c4["sel2"], c4["cellDims"], 0, 0, 20) + \
+        plf.py_getDistancesSum(c4["sel1"], c4["sel2"], c4["cellDims"], 0, 20, 37)
+    assert np.max(np.abs(s - s2) / np.maximum(s, 1e-30)) < 1e-13
+    c2 = synth.config2(n_frames=6, n_water=900)
+    full = plf.py_getWithinBits(c2["allAtoms"], c2["refSel"], c2["outSel"], c2["cellDims"], 3.0)
+    lo = plf.py_getWithinBits(c2["allAtoms"], c2["refSel"], c2["outSel"], c2["cellDims"], 3.0, 0, 2)
+    hi = plf.py_getWithinBits(c2["allAtoms"], c2["refSel"], c2["outSel"], c2["cellDims"], 3.0, 2, 6)
+    assert np.array_equal(full, np.concatenate([lo, hi]))
+
+
+# ------------------------------------------------------------------ full-size properties
+
+def test_full_size_config2_properties(golden):
+    """BASELINE config 2 at full size (25 000 atoms, 1000 frames): the first 20 frames share the
+    generator prefix?  No -- the generator draws per array, so instead check size-independent
+    properties: monotonicity in the cut-off, agreement of the int32 mask with the bitmask, and an
+    oracle check on a random sample of frames."""
+    c = synth.config2(n_frames=1000)
+    xyz, cell, r, o = c["allAtoms"], c["cellDims"], c["refSel"], c["outSel"]
+    b3 = plf.py_getWithinBits(xyz, r, o, cell, 3.0)
+    b4 = plf.py_getWithinBits(xyz, r, o, cell, 4.0)
+    assert b3.shape == (1000, (o.size + 31) // 32)
+    assert np.all((b3 & ~b4) == 0)                                   # within 3 => within 4
+    assert 0 < np.unpackbits(b3.view(np.uint8)).sum() < np.unpackbits(b4.view(np.uint8)).sum()
+    frames = [0, 1, 499, 998, 999]
+    sub = np.ascontiguousarray(xyz[:, frames])
+    want = port.within(sub, r, o, cell[frames], 3.0)
+    got = np.unpackbits(b3[frames].view(np.uint8), axis=1, bitorder="little")[:, :o.size]
+    assert np.array_equal(got.T.astype(np.int32), want[o])
+
+
+def test_full_matrix_vs_unique_pair_identity_large():
+    """size-independent identity: counts(A, A, sameSel=0) = 2*counts(A, A, sameSel=1) + self pairs in
+    bin 0 (what the legacy CUDA build computes, SURVEY B-6), on a 27k-atom box"""
+    c = synth.config5(n_side=30, n_frames=2)
+    a, cell = c["sel1"], c["cellDims"]
+    uniq = rdf_counts(a, a, cell, 1, NB, 0.1)
+    b = a.copy()
+    full = rdf_counts(a, b, cell, 0, NB, 0.1)
+    selfp = np.zeros(NB, np.int64)
+    selfp[0] = a.shape[0] * a.shape[1]
+    assert np.array_equal(full, 2 * uniq + selfp)
+    # linearity in the first selection
+    h = a.shape[0] // 3
+    a1, a2 = np.ascontiguousarray(a[:h]), np.ascontiguousarray(a[h:])
+    assert np.array_equal(full, rdf_counts(a1, b, cell, 0, NB, 0.1) + rdf_counts(a2, b, cell, 0, NB, 0.1))
+
+
+# ------------------------------------------------------------------ device-pointer entry points
+
+def test_device_pointer_api_and_synth_generator():
+    import ctypes
+    import torch
+    from namdanalyzer_b200 import _capi
+    L = _capi.load()
+    n_side, nF = 12, 3
+    n = n_side ** 3
+    host = synth.config5(n_side=n_side, n_frames=nF)
+    xyz = torch.empty((n, nF, 3), dtype=torch.float32, device="cuda")
+    cell = torch.empty((nF, 3), dtype=torch.float32, device="cuda")
+    Lbox = float(host["cellDims"][0, 0])
+    st = torch.cuda.current_stream().cuda_stream
+    _capi.check(L.nda_dev_synth_water_box(xyz.data_ptr(), cell.data_ptr(), n_side, nF, 0, nF, Lbox, 0.6, 1005, st))
+    torch.cuda.synchronize()
+    assert np.array_equal(xyz.cpu().numpy(), host["sel1"])            # generator is bit-identical
+    assert np.array_equal(cell.cpu().numpy(), host["cellDims"])
+    counts = torch.zeros(NB, dtype=torch.int64, device="cuda")
+    _capi.check(L.nda_dev_radial_nbr_counts(xyz.data_ptr(), n, xyz.data_ptr(), n, None, 1, counts.data_ptr(), NB,
+                                            cell.data_ptr(), nF, 0, nF, 1, 0.1, st))
+    torch.cuda.synchronize()
+    want = port.rdf_counts(host["sel1"], host["sel1"], host["cellDims"], 1, NB, 0.1).astype(np.int64)
+    assert np.array_equal(counts.cpu().numpy(), want)
+    # within on device, with the expanded int32 mask
+    refSel = torch.arange(0, 200, dtype=torch.int32, device="cuda")
+    outSel = torch.arange(100, n, dtype=torch.int32, device="cuda")
+    words = (outSel.numel() + 31) // 32
+    bits = torch.zeros((nF, words), dtype=torch.int32, device="cuda")
+    out = torch.zeros((n, nF), dtype=torch.int32, device="cuda")
+    _capi.check(L.nda_dev_within(xyz.data_ptr(), n, nF, refSel.data_ptr(), 200, outSel.data_ptr(), outSel.numel(),
+                                 bits.data_ptr(), out.data_ptr(), cell.data_ptr(), 3.2, 0, nF, st))
+    torch.cuda.synchronize()
+    wantm = port.within(host["sel1"], refSel.cpu().numpy(), outSel.cpu().numpy(), host["cellDims"], 3.2)
+    assert np.array_equal(out.cpu().numpy(), wantm)
+    # distances on device
+    s = torch.zeros((20, n), dtype=torch.float64, device="cuda")
+    sub = xyz[:20].contiguous()
+    _capi.check(L.nda_dev_distances_sum(sub.data_ptr(), 20, xyz.data_ptr(), n, s.data_ptr(), cell.data_ptr(),
+                                        nF, 0, nF, 0, st))
+    torch.cuda.synchronize()
+    w = port.distances_sum(host["sel1"][:20], host["sel1"], host["cellDims"], 0)
+    assert np.max(np.abs(s.cpu().numpy() - w) / np.maximum(w, 1e-30)) <= 1e-12
+    assert L.nda_launch_count() > 0

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Short, deterministic run of the three pair kernels for ncu (one launch each after a warm-up).
+
+    python tools/profile_run.py [within|rdf|dist|all]
+"""
+import ctypes
+import sys
+import numpy as np
+import torch
+
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+from namdanalyzer_b200 import synth, _capi  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+lib = _capi.load()
+dev = torch.device("cuda", 0)
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ms():
+    v = ctypes.c_double(0)
+    _capi.check(lib.nda_last_kernel_ms(ctypes.byref(v), None))
+    return v.value
+
+
+if what in ("within", "all"):
+    nF = 200
+    c = synth.config2(n_frames=nF)
+    xyz = torch.from_numpy(c["allAtoms"]).to(dev)
+    cell = torch.from_numpy(c["cellDims"]).to(dev)
+    rs, os_ = torch.from_numpy(c["refSel"]).to(dev), torch.from_numpy(c["outSel"]).to(dev)
+    bits = torch.zeros((nF, (os_.numel() + 31) // 32), dtype=torch.int32, device=dev)
+    for _ in range(2):
+        _capi.check(lib.nda_dev_within(xyz.data_ptr(), xyz.shape[0], nF, rs.data_ptr(), rs.numel(), os_.data_ptr(),
+                                       os_.numel(), bits.data_ptr(), None, cell.data_ptr(), 3.0, 0, nF, st))
+        t = ms()
+    pairs = 1231.0 * 7923.0 * nF
+    print("within: %.3f ms, %.3e pairs/s" % (t, pairs / t * 1e3))
+
+if what in ("rdf", "all"):
+    n_side, nF = 48, 2
+    n = n_side ** 3
+    L = float(np.float32((n / 0.0334) ** (1.0 / 3.0)))
+    xyz = torch.empty((n, nF, 3), dtype=torch.float32, device=dev)
+    cell = torch.empty((nF, 3), dtype=torch.float32, device=dev)
+    _capi.check(lib.nda_dev_synth_water_box(xyz.data_ptr(), cell.data_ptr(), n_side, nF, 0, nF, L, 0.6, 1005, st))
+    counts = torch.zeros(149, dtype=torch.int64, device=dev)
+    for _ in range(2):
+        counts.zero_()
+        _capi.check(lib.nda_dev_radial_nbr_counts(xyz.data_ptr(), n, xyz.data_ptr(), n, None, 1, counts.data_ptr(), 149,
+                                                  cell.data_ptr(), nF, 0, nF, 1, 0.1, st))
+        t = ms()
+    pairs = 0.5 * n * (n - 1.0) * nF
+    st4 = (ctypes.c_double * 4)()
+    print("rdf: %.3f ms, %.3e pairs/s, in-range %d" % (t, pairs / t * 1e3, int(counts.sum().item())))
+
+if what in ("dist", "all"):
+    nF = 2000
+    c = synth.config4(n_frames=nF)
+    a, b = torch.from_numpy(c["sel1"]).to(dev), torch.from_numpy(c["sel2"]).to(dev)
+    cell = torch.from_numpy(c["cellDims"]).to(dev)
+    s = torch.zeros((7, 1231), dtype=torch.float64, device=dev)
+    for _ in range(2):
+        s.zero_()
+        _capi.check(lib.nda_dev_distances_sum(a.data_ptr(), 7, b.data_ptr(), 1231, s.data_ptr(), cell.data_ptr(),
+                                              nF, 0, nF, 0, st))
+        t = ms()
+    print("dist: %.3f ms, %.3e pairs/s, %.1f GB/s" % (t, 7 * 1231.0 * nF / t * 1e3, (7 + 1231) * nF * 12 / t / 1e6))
+torch.cuda.synchronize()
