@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <atomic>
@@ -129,6 +130,14 @@ static int ctx_get(Ctx **out)
 
 static inline void begin_call(Ctx &c) { c.kevUsed = 0; }
 
+// tuning override for experiments: NDA_CTAS_PER_SM=<n> caps the persistent grid at n CTAs per SM
+static int tuned_ctas(int occ)
+{
+    const char *e = getenv("NDA_CTAS_PER_SM");
+    if (e && *e) { int v = atoi(e); if (v >= 1 && v < occ) return v; }
+    return occ < 1 ? 1 : occ;
+}
+
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // ------------------------------------------------------------------------------------------
@@ -162,17 +171,15 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
     const bool grouped = d_gid != nullptr;
     if (!grouped) nGroups = 1;
     const size_t H = (size_t)nGroups * nBins;
-    // shared-memory budget: 2 CTAs per SM
-    const size_t perCta = (c.smemOptin * 2 + 2048 <= (size_t)228 * 1024) ? c.smemOptin : (size_t)113 * 1024;
+    // shared memory: as many warp-private histogram copies as still allow PAIR_MIN_CTAS CTAs per SM
+    const size_t perCta = ((size_t)227 * 1024) / PAIR_MIN_CTAS - 1024;
     size_t histBudget = (perCta > PAIR_SMEM_BASE) ? perCta - PAIR_SMEM_BASE : 0;
     int copies = (int)std::min<size_t>(PAIR_WARPS, histBudget / (H * 4));
-    size_t smem = PAIR_SMEM_BASE + (size_t)std::max(copies, 1) * H * 4;
-    if (copies < 1) {
-        copies = 1;
-        if (smem > c.smemOptin)
-            return fail(NDA_ERR_ARG, "nGroups*outSize = %zu histogram cells do not fit in shared memory (max %zu)",
-                        H, (c.smemOptin - PAIR_SMEM_BASE) / 4);
-    }
+    if (copies < 1) copies = 1;
+    const size_t smem = PAIR_SMEM_BASE + (size_t)copies * H * 4;
+    if (smem > c.smemOptin)
+        return fail(NDA_ERR_ARG, "nGroups*outSize = %zu histogram cells do not fit in shared memory (max %zu)",
+                    H, (c.smemOptin - PAIR_SMEM_BASE) / 4);
     const int n1Pad = sameSel ? round_up(n1, PAIR_BTILE) : round_up(n1, PAIR_ATILE);
     const int n2Pad = sameSel ? n1Pad : round_up(n2, PAIR_BTILE);
     const size_t bytesPerFrame = ((size_t)n1Pad + (sameSel ? 0 : (size_t)n2Pad)) * sizeof(float4);
@@ -194,14 +201,30 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
     a.n1 = n1; a.n1Pad = n1Pad; a.n2 = n2; a.n2Pad = n2Pad;
     a.nATiles = (n1 + PAIR_ATILE - 1) / PAIR_ATILE;
     a.nBTiles = (n2 + PAIR_BTILE - 1) / PAIR_BTILE;
-    a.chunkTiles = std::min(a.nBTiles, 32);
-    a.nBChunks = (a.nBTiles + a.chunkTiles - 1) / a.chunkTiles;
     a.counts = d_counts; a.nBins = nBins; a.nGroups = nGroups; a.histCopies = copies;
     a.sameSel = sameSel ? 1 : 0; a.dr = dr;
     a.workCounter = work; a.stats = stats;
 
-    if (grouped) CK(cudaFuncSetAttribute(rdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else         CK(cudaFuncSetAttribute(rdf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctasPerSM = 0;
+    if (grouped) {
+        CK(cudaFuncSetAttribute(rdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, rdf_kernel<true>, PAIR_THREADS, smem));
+    } else {
+        CK(cudaFuncSetAttribute(rdf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, rdf_kernel<false>, PAIR_THREADS, smem));
+    }
+    ctasPerSM = tuned_ctas(ctasPerSM);
+    // B chunk per work item: aim at >= 16 items per resident CTA so the dynamic scheduler can
+    // balance the triangular (sameSel) workload, but keep an item >= 2 tiles (~1e6 pairs)
+    {
+        const long long target = 16LL * ctasPerSM * c.numSMs;
+        const long long rows = (long long)pass * a.nATiles;
+        const long long chunksWanted = std::max<long long>(1, (target + rows - 1) / rows);
+        long long ct = (a.nBTiles + chunksWanted - 1) / chunksWanted;
+        ct = std::max<long long>(2, std::min<long long>(32, ct));
+        a.chunkTiles = (int)std::min<long long>(ct, a.nBTiles);
+        a.nBChunks = (a.nBTiles + a.chunkTiles - 1) / a.chunkTiles;
+    }
 
     for (int f0 = fb; f0 < fe; f0 += pass) {
         const int nFc = std::min(pass, fe - f0);
@@ -224,7 +247,7 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
         const unsigned long long items = (unsigned long long)nFc * a.nATiles * a.nBChunks;
         if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
         a.nItems = (unsigned)items;
-        const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)2 * c.numSMs);
+        const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)ctasPerSM * c.numSMs);
         CK(c.kev_record(st));
         if (grouped) rdf_kernel<true><<<grid, PAIR_THREADS, smem, st>>>(a);
         else         rdf_kernel<false><<<grid, PAIR_THREADS, smem, st>>>(a);
@@ -268,6 +291,9 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
         a.workCounter = work; a.stats = stats;
         const size_t smem = PAIR_SMEM_BASE;
         CK(cudaFuncSetAttribute(within_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int ctasPerSM = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, within_kernel, PAIR_THREADS, smem));
+        ctasPerSM = tuned_ctas(ctasPerSM);
 
         for (int f0 = fb; f0 < fe; f0 += pass) {
             const int nFc = std::min(pass, fe - f0);
@@ -289,7 +315,7 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
             const unsigned long long items = (unsigned long long)nFc * a.nATiles;
             if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
             a.nItems = (unsigned)items;
-            const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)2 * c.numSMs);
+            const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)ctasPerSM * c.numSMs);
             CK(c.kev_record(st));
             within_kernel<<<grid, PAIR_THREADS, smem, st>>>(a);
             LAUNCHED();

@@ -117,7 +117,7 @@ def water_box_frame(n_side, frame, L=None, seed=1005, sigma=0.6, rho=0.0334):
     iy = ((a // np.uint32(n_side)) % np.uint32(n_side)).astype(np.uint32)
     iz = (a % np.uint32(n_side)).astype(np.uint32)
     h = F(L / F(n_side))
-    amp = F(sigma * np.sqrt(3.0))
+    amp = F(np.float64(F(sigma)) * np.sqrt(3.0))        # float32 sigma, as the C ABI receives it
     out = np.empty((n, 3), F)
     with np.errstate(over="ignore"):
         key = _mix32(np.uint32(seed) ^ _mix32(np.full(1, frame, np.uint32) + np.uint32(0x9E3779B9)))

@@ -1,0 +1,140 @@
+"""GPU: the host-side mirror of the reference interface (Dataset.selection('... within ...'),
+Dataset.getWithin / getDistances, RadialNumberDensity, ResidueWiseWaterDensity) on the reference's
+own test geometry (ubq_ws, no unit cell) and on periodic synthetic boxes, checked against the
+oracle assembled the way the reference's Python glue assembles it."""
+import numpy as np
+import pytest
+
+from namdanalyzer_b200 import synth
+from namdanalyzer_b200.Dataset import ArrayDataset
+from namdanalyzer_b200.dataAnalysis.RadialDensity import RadialNumberDensity, ResidueWiseWaterDensity
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def ubq_dataset():
+    fx = synth.fixture()
+    n = fx["all_xyz"].shape[0]
+    names = np.array(["X"] * n, dtype=object)
+    names[fx["water_o_idx"]] = "OH2"
+    resn = np.array(["TIP3"] * n, dtype=object)
+    resn[fx["protein_idx"]] = "ALA"
+    resid = np.zeros(n, int)
+    resid[fx["protein_idx"]] = fx["protein_resid"]
+    resid[~np.isin(np.arange(n), fx["protein_idx"])] = 1000
+    return ArrayDataset(fx["all_xyz"], fx["all_cell"], names, resn, resid), fx
+
+
+def test_selection_within_single_and_multi_frame():
+    d, fx = ubq_dataset()
+    assert d.selection("name OH2").size == 1817                      # the reference's own asserted count
+    assert d.parallelBackend == 2
+    want = port.within(fx["all_xyz"], fx["protein_idx"], fx["water_o_idx"], fx["all_cell"], 3.0)
+    s0 = d.selection("name OH2 and within 3 of protein")             # default frame 0
+    assert np.array_equal(s0.getIndices(), np.flatnonzero(want[:, 0]))
+    s2 = d.selection("name OH2 and within 3 of protein frame 2")
+    assert np.array_equal(s2.getIndices(), np.flatnonzero(want[:, 2]))
+    sm = d.selection("name OH2 and within 3 of protein frame 0:3")   # list of per-frame index arrays
+    assert len(sm.getIndices()) == 3
+    for k in range(3):
+        assert np.array_equal(sm.getIndices()[k], np.flatnonzero(want[:, k]))
+    # Dataset.getWithin: index vector for one frame, 0/1 matrix for several (dcdParser.py:190-194)
+    k1 = d.getWithin(3.0, "protein", "name OH2", frame=1)
+    assert np.array_equal(k1, np.flatnonzero(want[:, 1]))
+    km = d.getWithin(3.0, "protein", "name OH2", frame=np.arange(3))
+    assert km.shape == (6682, 3) and np.array_equal(km, want)
+
+
+def test_get_distances_host_method():
+    d, fx = ubq_dataset()
+    out = d.getDistances("protein and resid 53", "protein", frame=np.arange(3))
+    pr = np.ascontiguousarray(fx["all_xyz"][fx["protein_idx"]])
+    r53 = np.ascontiguousarray(pr[fx["protein_resid"] == 53])
+    w = port.distances_sum(r53, pr, fx["all_cell"], 0) / 3
+    assert out.shape == (7, 1231) and out.dtype == np.float32
+    assert np.max(np.abs(out - w) / np.maximum(w, 1e-30)) <= 1e-6
+    same = d.getDistances("protein and resid 53", frame=0)            # sel2 None -> sameSel
+    assert same.shape == (7, 7) and np.array_equal(same, same.T) and np.all(np.diag(same) == 0)
+
+
+def test_radial_number_density_class():
+    c = synth.config1(n_frames=6)
+    d = ArrayDataset(c["sel1"], c["cellDims"], names=["OH2"] * 1000, resnames=["TIP3"] * 1000)
+    rdf = RadialNumberDensity(d, "name OH2", "name OH2", dr=0.1, maxR=15)
+    assert rdf.sameSel == 1
+    rdf.compDensity()
+    counts = port.rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, 149, 0.1).astype(np.float64)
+    dens = (counts / 6).astype(np.float32)
+    dens[0] -= dens[0]                                               # RadialDensity.py:222-223
+    radii = np.arange(0.1, 15, 0.1)
+    dens /= (4 * np.pi * radii ** 2 * 0.1)
+    assert rdf.radii.size == 149 and np.array_equal(rdf.density, dens)
+
+
+def test_residue_wise_water_density_class():
+    c = synth.config3(n_frames=2, n_water=3000)
+    nP, nW = c["protein"].shape[0], c["waters"].shape[0]
+    fx = synth.fixture()
+    xyz = np.concatenate([c["protein"], c["waters"]])
+    d = ArrayDataset(xyz, c["cellDims"], names=["CA"] * nP + ["OH2"] * nW,
+                     resnames=["ALA"] * nP + ["TIP3"] * nW,
+                     resids=np.concatenate([fx["protein_resid"], np.full(nW, 5000)]))
+    rw = ResidueWiseWaterDensity(d, "protein", maxR=15, dr=0.1)
+    rw.compDensity()
+    assert rw.density.shape == (76, 149)
+    radii = np.arange(0.1, 15, 0.1)
+    # the reference's loop (RadialDensity.py:84-103): one call per residue, string-sorted residues
+    for k in (0, 17, 75):
+        res = int(rw.residues[k])
+        sel = np.ascontiguousarray(c["protein"][fx["protein_resid"] == res])
+        cnt = port.rdf_counts(c["waters"], sel, c["cellDims"], 0, 149, 0.1).astype(np.float64)
+        dens = (cnt / 2).astype(np.float32)
+        dens[0] -= dens[0]
+        dens = (dens / (4 * np.pi * radii ** 2 * 0.1)).astype(np.float32)
+        assert np.array_equal(rw.density[k].astype(np.float32), dens)
+
+
+def test_nccl_frame_sharding_if_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os, socket, sys
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port_no = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    c = synth.config1(n_frames=9)
+    want = port.rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, 149, 0.1).astype(np.int64)
+    assert np.array_equal(res, want)
+
+
+def _nccl_worker(rank, world, port_no, q):
+    import os, sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from namdanalyzer_b200 import synth, distributed as nd, _capi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    torch.cuda.set_device(rank)
+    _capi.check(_capi.load().nda_set_device(rank))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        c = synth.config1(n_frames=9)
+        counts = nd.radial_nbr_counts(c["sel1"], c["sel1"], c["cellDims"], 1, 149, 0.1)
+        if rank == 0:
+            q.put(counts)
+    finally:
+        dist.destroy_process_group()
