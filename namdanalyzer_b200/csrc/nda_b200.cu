@@ -76,7 +76,7 @@ struct Ctx {
     size_t smemOptin = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf packA, packB, fp, maxAbs, ctl;        // ctl: [0..1] work counter (u32 x2), stats u64 at +16
+    DevBuf packA, packB, packAw, packBw, fp, maxAbs, ctl;        // ctl: [0..1] work counter (u32 x2), stats u64 at +16
     DevBuf raw1, raw2, cell, idx1, idx2, gid, counts, bits, sum;
     double stats[4] = {0, 0, 0, 0};
     // CUDA-event brackets around the pair kernel of every pass of the last entry-point call
@@ -144,12 +144,22 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // device-level drivers (inputs resident, stream-ordered)
 // ------------------------------------------------------------------------------------------
 static int launch_pack(Ctx &c, cudaStream_t st, const float *src, int nFtot, const int *gather, int n,
-                       int nPad, int f0, int nFc, const int *gid, float4 *dst, unsigned *maxAbs)
+                       int nPad, int f0, int nFc, const int *gid, float4 *dst, unsigned *maxAbs,
+                       const float *cell, float4 *dstW)
 {
+    (void)c;
     dim3 grid(nPad / 32, (nFc + 31) / 32);
-    pack_kernel<<<grid, 256, 0, st>>>(src, nFtot, gather, n, nPad, f0, nFc, gid, dst, maxAbs);
+    pack_kernel<<<grid, 256, 0, st>>>(src, nFtot, gather, n, nPad, f0, nFc, gid, dst, maxAbs, cell, dstW);
     LAUNCHED();
     return NDA_OK;
+}
+
+// which FP32 filter the pair kernels run (NDA_FILTER=rint|fold, default fold)
+static int filter_kind()
+{
+    const char *e = getenv("NDA_FILTER");
+    if (e && !strcmp(e, "rint")) return kFilterRint;
+    return kFilterFold;
 }
 
 // frames per pass so that the packed copies stay within a fixed HBM budget
@@ -182,11 +192,17 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
                     H, (c.smemOptin - PAIR_SMEM_BASE) / 4);
     const int n1Pad = sameSel ? round_up(n1, PAIR_BTILE) : round_up(n1, PAIR_ATILE);
     const int n2Pad = sameSel ? n1Pad : round_up(n2, PAIR_BTILE);
-    const size_t bytesPerFrame = ((size_t)n1Pad + (sameSel ? 0 : (size_t)n2Pad)) * sizeof(float4);
+    const int filter = filter_kind();
+    const bool fold = filter == kFilterFold;
+    const size_t bytesPerFrame = ((size_t)n1Pad + (sameSel ? 0 : (size_t)n2Pad)) * sizeof(float4) * (fold ? 2 : 1);
     const int pass = frames_per_pass(bytesPerFrame, fe - fb);
 
     CK(c.packA.reserve((size_t)n1Pad * pass * sizeof(float4)));
     if (!sameSel) CK(c.packB.reserve((size_t)n2Pad * pass * sizeof(float4)));
+    if (fold) {
+        CK(c.packAw.reserve((size_t)n1Pad * pass * sizeof(float4)));
+        if (!sameSel) CK(c.packBw.reserve((size_t)n2Pad * pass * sizeof(float4)));
+    }
     CK(c.fp.reserve((size_t)pass * sizeof(FrameParams)));
     CK(c.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
 
@@ -206,13 +222,10 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
     a.workCounter = work; a.stats = stats;
 
     int ctasPerSM = 0;
-    if (grouped) {
-        CK(cudaFuncSetAttribute(rdf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, rdf_kernel<true>, PAIR_THREADS, smem));
-    } else {
-        CK(cudaFuncSetAttribute(rdf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, rdf_kernel<false>, PAIR_THREADS, smem));
-    }
+    const void *kfn = grouped ? (fold ? (const void *)rdf_kernel<true, kFilterFold> : (const void *)rdf_kernel<true, kFilterRint>)
+                              : (fold ? (const void *)rdf_kernel<false, kFilterFold> : (const void *)rdf_kernel<false, kFilterRint>);
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kfn, PAIR_THREADS, smem));
     ctasPerSM = tuned_ctas(ctasPerSM);
     // B chunk per work item: aim at >= 16 items per resident CTA so the dynamic scheduler can
     // balance the triangular (sameSel) workload, but keep an item >= 2 tiles (~1e6 pairs)
@@ -231,11 +244,11 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
         CK(cudaMemsetAsync(c.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
         CK(cudaMemsetAsync(work, 0, 8, st));
         int rc = launch_pack(c, st, d_sel1, nF, nullptr, n1, n1Pad, f0, nFc, sameSel ? d_gid : nullptr,
-                             c.packA.as<float4>(), c.maxAbs.as<unsigned>());
+                             c.packA.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packAw.as<float4>() : nullptr);
         if (rc) return rc;
         if (!sameSel) {
             rc = launch_pack(c, st, d_sel2, nF, nullptr, n2, n2Pad, f0, nFc, d_gid,
-                             c.packB.as<float4>(), c.maxAbs.as<unsigned>());
+                             c.packB.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packBw.as<float4>() : nullptr);
             if (rc) return rc;
         }
         prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, c.maxAbs.as<unsigned>(), T,
@@ -243,14 +256,21 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
         LAUNCHED();
         a.A = c.packA.as<float4>();
         a.B = sameSel ? a.A : c.packB.as<float4>();
+        a.Aw = fold ? c.packAw.as<float4>() : a.A;
+        a.Bw = fold ? (sameSel ? a.Aw : c.packBw.as<float4>()) : a.B;
         a.fp = c.fp.as<FrameParams>();
         const unsigned long long items = (unsigned long long)nFc * a.nATiles * a.nBChunks;
         if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
         a.nItems = (unsigned)items;
         const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)ctasPerSM * c.numSMs);
         CK(c.kev_record(st));
-        if (grouped) rdf_kernel<true><<<grid, PAIR_THREADS, smem, st>>>(a);
-        else         rdf_kernel<false><<<grid, PAIR_THREADS, smem, st>>>(a);
+        if (grouped) {
+            if (fold) rdf_kernel<true, kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
+            else      rdf_kernel<true, kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
+        } else {
+            if (fold) rdf_kernel<false, kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
+            else      rdf_kernel<false, kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
+        }
         LAUNCHED();
         CK(c.kev_record(st));
     }
@@ -269,10 +289,16 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
     } else {
         const int nAPad = round_up(outSize, PAIR_ATILE);
         const int nBPad = round_up(refSize, PAIR_BTILE);
-        const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * sizeof(float4);
+        const int filter = filter_kind();
+        const bool fold = filter == kFilterFold;
+        const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * sizeof(float4) * (fold ? 2 : 1);
         const int pass = frames_per_pass(bytesPerFrame, fe - fb);
         CK(c.packA.reserve((size_t)nAPad * pass * sizeof(float4)));
         CK(c.packB.reserve((size_t)nBPad * pass * sizeof(float4)));
+        if (fold) {
+            CK(c.packAw.reserve((size_t)nAPad * pass * sizeof(float4)));
+            CK(c.packBw.reserve((size_t)nBPad * pass * sizeof(float4)));
+        }
         CK(c.fp.reserve((size_t)pass * sizeof(FrameParams)));
         CK(c.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
         unsigned *work = c.ctl.as<unsigned>();
@@ -290,9 +316,10 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
         a.literal = g_within_pure.load() ? 0 : 1;
         a.workCounter = work; a.stats = stats;
         const size_t smem = PAIR_SMEM_BASE;
-        CK(cudaFuncSetAttribute(within_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const void *kfn = fold ? (const void *)within_kernel<kFilterFold> : (const void *)within_kernel<kFilterRint>;
+        CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int ctasPerSM = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, within_kernel, PAIR_THREADS, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kfn, PAIR_THREADS, smem));
         ctasPerSM = tuned_ctas(ctasPerSM);
 
         for (int f0 = fb; f0 < fe; f0 += pass) {
@@ -300,16 +327,18 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
             CK(cudaMemsetAsync(c.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
             CK(cudaMemsetAsync(work, 0, 8, st));
             int rc = launch_pack(c, st, d_all, nF, d_outSel, outSize, nAPad, f0, nFc, nullptr,
-                                 c.packA.as<float4>(), c.maxAbs.as<unsigned>());
+                                 c.packA.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packAw.as<float4>() : nullptr);
             if (rc) return rc;
             rc = launch_pack(c, st, d_all, nF, d_refSel, refSize, nBPad, f0, nFc, nullptr,
-                             c.packB.as<float4>(), c.maxAbs.as<unsigned>());
+                             c.packB.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packBw.as<float4>() : nullptr);
             if (rc) return rc;
             prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, c.maxAbs.as<unsigned>(), T,
                                                                  c.fp.as<FrameParams>(), stats);
             LAUNCHED();
             a.A = c.packA.as<float4>();
             a.B = c.packB.as<float4>();
+            a.Aw = fold ? c.packAw.as<float4>() : a.A;
+            a.Bw = fold ? c.packBw.as<float4>() : a.B;
             a.fp = c.fp.as<FrameParams>();
             a.bits = d_bits + (size_t)(f0 - fb) * words;
             const unsigned long long items = (unsigned long long)nFc * a.nATiles;
@@ -317,7 +346,8 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
             a.nItems = (unsigned)items;
             const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)ctasPerSM * c.numSMs);
             CK(c.kev_record(st));
-            within_kernel<<<grid, PAIR_THREADS, smem, st>>>(a);
+            if (fold) within_kernel<kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
+            else      within_kernel<kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
             LAUNCHED();
             CK(c.kev_record(st));
         }

@@ -4,11 +4,10 @@
 //                 (lib/openmp/src/getRadialNbrDensity.cpp:29-45,
 //                 getWithin.cpp:58-77, getDistances.cpp:47-57).  Intrinsics (__fdiv_rn, __fmul_rn,
 //                 ...) are used so nvcc can neither contract to FMA nor reassociate.
-//  * fast_r2    : the FP32 filter applied to EVERY pair: rintf via the 1.5*2^23 magic constant,
-//                 reciprocal multiply, FMA-contracted wrap and norm (15 FMA-pipe instructions).
-//                 It only decides which pairs are CANDIDATES (r2' < thr, thr = in-range limit plus a
-//                 proven guard band, see prep_frames_kernel); candidates are re-evaluated with
-//                 strict_* so every count / mask bit equals the reference's bit for bit.
+//  * fast_r2    : the FP32 filter applied to EVERY pair (two variants, see below).  It only decides
+//                 which pairs are CANDIDATES (r2' < thr, thr = in-range limit plus a proven guard
+//                 band, see prep_frames_kernel); candidates are re-evaluated with strict_* on the
+//                 ORIGINAL coordinates, so every count / mask bit equals the reference's bit for bit.
 //  * TMA        : 1-D bulk copies global -> shared (cp.async.bulk, SASS UBLKCP) completing on an
 //                 mbarrier.
 #pragma once
@@ -61,33 +60,53 @@ __device__ __forceinline__ int strict_bin(float r2, float dr, int outSize)
     return (idx >= 0 && idx < outSize) ? idx : -1;
 }
 
-// ---------------------------------------------------------------- fast filter
+// ---------------------------------------------------------------- fast filters
+// Two interchangeable FP32 filters, both applied to EVERY pair, both only deciding which pairs
+// become candidates for the strict re-evaluation:
+//   kFilterRint : original coordinates; n = rintf(d * (1/c)) via the magic constant, w = fma(-c, n, d)
+//                 -> 15 FMA-pipe instructions per pair.
+//   kFilterFold : coordinates pre-wrapped into [0, c) by pack_kernel, so d in (-c, c) and the
+//                 minimum image is |w| = min(|d|, c - |d|): FADD, FADD, FMNMX per axis
+//                 -> 9 FMA-pipe + 3 ALU-pipe instructions per pair (the two pipes run side by side).
+constexpr int kFilterRint = 0;
+constexpr int kFilterFold = 1;
+
 struct FrameRegs {
-    float ncx, ncy, ncz;     // -c
-    float icx, icy, icz;
+    float px, py, pz;        // rint: -c        fold: |c|
+    float icx, icy, icz;     // rint: fl(1/c)   fold: unused
     float thr;
 };
 
+template <int kFilter>
 __device__ __forceinline__ FrameRegs load_frame_regs(const FrameParams &p)
 {
     FrameRegs r;
-    r.ncx = -p.cx; r.ncy = -p.cy; r.ncz = -p.cz;
+    if (kFilter == kFilterRint) { r.px = -p.cx; r.py = -p.cy; r.pz = -p.cz; }
+    else                        { r.px = fabsf(p.cx); r.py = fabsf(p.cy); r.pz = fabsf(p.cz); }
     r.icx = p.icx; r.icy = p.icy; r.icz = p.icz;
     r.thr = p.thr;
     return r;
 }
 
+template <int kFilter>
 __device__ __forceinline__ float fast_r2(float ax, float ay, float az, const float4 &b, const FrameRegs &f)
 {
-    float dx = ax - b.x;
-    float dy = ay - b.y;
-    float dz = az - b.z;
-    float nx = __fmaf_rn(dx, f.icx, NDA_MAGIC) - NDA_MAGIC;      // rintf(dx / cx)
-    float ny = __fmaf_rn(dy, f.icy, NDA_MAGIC) - NDA_MAGIC;
-    float nz = __fmaf_rn(dz, f.icz, NDA_MAGIC) - NDA_MAGIC;
-    float wx = __fmaf_rn(f.ncx, nx, dx);
-    float wy = __fmaf_rn(f.ncy, ny, dy);
-    float wz = __fmaf_rn(f.ncz, nz, dz);
+    const float dx = ax - b.x;
+    const float dy = ay - b.y;
+    const float dz = az - b.z;
+    float wx, wy, wz;
+    if (kFilter == kFilterRint) {
+        const float nx = __fmaf_rn(dx, f.icx, NDA_MAGIC) - NDA_MAGIC;      // rintf(dx / cx)
+        const float ny = __fmaf_rn(dy, f.icy, NDA_MAGIC) - NDA_MAGIC;
+        const float nz = __fmaf_rn(dz, f.icz, NDA_MAGIC) - NDA_MAGIC;
+        wx = __fmaf_rn(f.px, nx, dx);
+        wy = __fmaf_rn(f.py, ny, dy);
+        wz = __fmaf_rn(f.pz, nz, dz);
+    } else {
+        wx = fminf(fabsf(dx), f.px - fabsf(dx));
+        wy = fminf(fabsf(dy), f.py - fabsf(dy));
+        wz = fminf(fabsf(dz), f.pz - fabsf(dz));
+    }
     return __fmaf_rn(wz, wz, __fmaf_rn(wy, wy, wx * wx));
 }
 

@@ -1,7 +1,9 @@
 #!/bin/bash
-# occupancy sweep of the two persistent pair kernels (CUDA-event kernel times, no profiler)
-for c in 1 2 3 4 5; do
-  echo "== NDA_CTAS_PER_SM=$c"
-  NDA_CTAS_PER_SM=$c python tools/profile_run.py within
-  NDA_CTAS_PER_SM=$c python tools/profile_run.py rdf
+# filter / occupancy sweep of the two persistent pair kernels (CUDA-event kernel times, no profiler)
+for f in rint fold; do
+for c in 3 4 5; do
+  echo "== NDA_FILTER=$f NDA_CTAS_PER_SM=$c"
+  NDA_FILTER=$f NDA_CTAS_PER_SM=$c python tools/profile_run.py within
+  NDA_FILTER=$f NDA_CTAS_PER_SM=$c python tools/profile_run.py rdf
+done
 done
