@@ -145,21 +145,22 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // ------------------------------------------------------------------------------------------
 static int launch_pack(Ctx &c, cudaStream_t st, const float *src, int nFtot, const int *gather, int n,
                        int nPad, int f0, int nFc, const int *gid, float4 *dst, unsigned *maxAbs,
-                       const float *cell, float4 *dstW)
+                       const float *cell, float4 *dstW, int pairLayout = 0)
 {
     (void)c;
     dim3 grid(nPad / 32, (nFc + 31) / 32);
-    pack_kernel<<<grid, 256, 0, st>>>(src, nFtot, gather, n, nPad, f0, nFc, gid, dst, maxAbs, cell, dstW);
+    pack_kernel<<<grid, 256, 0, st>>>(src, nFtot, gather, n, nPad, f0, nFc, gid, dst, maxAbs, cell, dstW, pairLayout);
     LAUNCHED();
     return NDA_OK;
 }
 
-// which FP32 filter the pair kernels run (NDA_FILTER=rint|fold, default fold)
+// which FP32 filter the pair kernels run (NDA_FILTER=rint|fold|fold2, default fold2)
 static int filter_kind()
 {
     const char *e = getenv("NDA_FILTER");
     if (e && !strcmp(e, "rint")) return kFilterRint;
-    return kFilterFold;
+    if (e && !strcmp(e, "fold")) return kFilterFold;
+    return kFilterFold2;
 }
 
 // frames per pass so that the packed copies stay within a fixed HBM budget
@@ -193,7 +194,8 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
     const int n1Pad = sameSel ? round_up(n1, PAIR_BTILE) : round_up(n1, PAIR_ATILE);
     const int n2Pad = sameSel ? n1Pad : round_up(n2, PAIR_BTILE);
     const int filter = filter_kind();
-    const bool fold = filter == kFilterFold;
+    const bool fold = filter != kFilterRint;                 // wrapped copies needed
+    const int pairLayout = filter == kFilterFold2 ? 1 : 0;
     const size_t bytesPerFrame = ((size_t)n1Pad + (sameSel ? 0 : (size_t)n2Pad)) * sizeof(float4) * (fold ? 2 : 1);
     const int pass = frames_per_pass(bytesPerFrame, fe - fb);
 
@@ -222,8 +224,13 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
     a.workCounter = work; a.stats = stats;
 
     int ctasPerSM = 0;
-    const void *kfn = grouped ? (fold ? (const void *)rdf_kernel<true, kFilterFold> : (const void *)rdf_kernel<true, kFilterRint>)
-                              : (fold ? (const void *)rdf_kernel<false, kFilterFold> : (const void *)rdf_kernel<false, kFilterRint>);
+    const void *kfn = nullptr;
+    if (grouped) kfn = filter == kFilterFold2 ? (const void *)rdf_kernel<true, kFilterFold2>
+                     : filter == kFilterFold  ? (const void *)rdf_kernel<true, kFilterFold>
+                                              : (const void *)rdf_kernel<true, kFilterRint>;
+    else         kfn = filter == kFilterFold2 ? (const void *)rdf_kernel<false, kFilterFold2>
+                     : filter == kFilterFold  ? (const void *)rdf_kernel<false, kFilterFold>
+                                              : (const void *)rdf_kernel<false, kFilterRint>;
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kfn, PAIR_THREADS, smem));
     ctasPerSM = tuned_ctas(ctasPerSM);
@@ -244,11 +251,11 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
         CK(cudaMemsetAsync(c.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
         CK(cudaMemsetAsync(work, 0, 8, st));
         int rc = launch_pack(c, st, d_sel1, nF, nullptr, n1, n1Pad, f0, nFc, sameSel ? d_gid : nullptr,
-                             c.packA.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packAw.as<float4>() : nullptr);
+                             c.packA.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packAw.as<float4>() : nullptr, pairLayout);
         if (rc) return rc;
         if (!sameSel) {
             rc = launch_pack(c, st, d_sel2, nF, nullptr, n2, n2Pad, f0, nFc, d_gid,
-                             c.packB.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packBw.as<float4>() : nullptr);
+                             c.packB.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packBw.as<float4>() : nullptr, pairLayout);
             if (rc) return rc;
         }
         prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, c.maxAbs.as<unsigned>(), T,
@@ -265,11 +272,13 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
         const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)ctasPerSM * c.numSMs);
         CK(c.kev_record(st));
         if (grouped) {
-            if (fold) rdf_kernel<true, kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
-            else      rdf_kernel<true, kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
+            if (filter == kFilterFold2)     rdf_kernel<true, kFilterFold2><<<grid, PAIR_THREADS, smem, st>>>(a);
+            else if (filter == kFilterFold) rdf_kernel<true, kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
+            else                            rdf_kernel<true, kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
         } else {
-            if (fold) rdf_kernel<false, kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
-            else      rdf_kernel<false, kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
+            if (filter == kFilterFold2)     rdf_kernel<false, kFilterFold2><<<grid, PAIR_THREADS, smem, st>>>(a);
+            else if (filter == kFilterFold) rdf_kernel<false, kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
+            else                            rdf_kernel<false, kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
         }
         LAUNCHED();
         CK(c.kev_record(st));
@@ -290,7 +299,8 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
         const int nAPad = round_up(outSize, PAIR_ATILE);
         const int nBPad = round_up(refSize, PAIR_BTILE);
         const int filter = filter_kind();
-        const bool fold = filter == kFilterFold;
+        const bool fold = filter != kFilterRint;             // wrapped copies needed
+        const int pairLayout = filter == kFilterFold2 ? 1 : 0;
         const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * sizeof(float4) * (fold ? 2 : 1);
         const int pass = frames_per_pass(bytesPerFrame, fe - fb);
         CK(c.packA.reserve((size_t)nAPad * pass * sizeof(float4)));
@@ -316,7 +326,9 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
         a.literal = g_within_pure.load() ? 0 : 1;
         a.workCounter = work; a.stats = stats;
         const size_t smem = PAIR_SMEM_BASE;
-        const void *kfn = fold ? (const void *)within_kernel<kFilterFold> : (const void *)within_kernel<kFilterRint>;
+        const void *kfn = filter == kFilterFold2 ? (const void *)within_kernel<kFilterFold2>
+                        : filter == kFilterFold  ? (const void *)within_kernel<kFilterFold>
+                                                 : (const void *)within_kernel<kFilterRint>;
         CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int ctasPerSM = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kfn, PAIR_THREADS, smem));
@@ -327,10 +339,10 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
             CK(cudaMemsetAsync(c.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
             CK(cudaMemsetAsync(work, 0, 8, st));
             int rc = launch_pack(c, st, d_all, nF, d_outSel, outSize, nAPad, f0, nFc, nullptr,
-                                 c.packA.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packAw.as<float4>() : nullptr);
+                                 c.packA.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packAw.as<float4>() : nullptr, pairLayout);
             if (rc) return rc;
             rc = launch_pack(c, st, d_all, nF, d_refSel, refSize, nBPad, f0, nFc, nullptr,
-                             c.packB.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packBw.as<float4>() : nullptr);
+                             c.packB.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packBw.as<float4>() : nullptr, pairLayout);
             if (rc) return rc;
             prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, c.maxAbs.as<unsigned>(), T,
                                                                  c.fp.as<FrameParams>(), stats);
@@ -346,8 +358,9 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
             a.nItems = (unsigned)items;
             const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)ctasPerSM * c.numSMs);
             CK(c.kev_record(st));
-            if (fold) within_kernel<kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
-            else      within_kernel<kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
+            if (filter == kFilterFold2)     within_kernel<kFilterFold2><<<grid, PAIR_THREADS, smem, st>>>(a);
+            else if (filter == kFilterFold) within_kernel<kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
+            else                            within_kernel<kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
             LAUNCHED();
             CK(c.kev_record(st));
         }

@@ -68,8 +68,13 @@ __device__ __forceinline__ int strict_bin(float r2, float dr, int outSize)
 //   kFilterFold : coordinates pre-wrapped into [0, c) by pack_kernel, so d in (-c, c) and the
 //                 minimum image is |w| = min(|d|, c - |d|): FADD, FADD, FMNMX per axis
 //                 -> 9 FMA-pipe + 3 ALU-pipe instructions per pair (the two pipes run side by side).
+//   kFilterFold2: the fold filter on two B atoms at a time with Blackwell's packed FP32 pipe
+//                 instructions (sub/mul/fma.f32x2, SASS FADD2/FMUL2/FFMA2): the wrapped B tile is
+//                 stored pair-interleaved [x0 x1 y0 y1 | z0 z1 w0 w1] so both operands of a packed
+//                 instruction sit in adjacent registers -> ~9 issue slots per pair instead of 12.
 constexpr int kFilterRint = 0;
 constexpr int kFilterFold = 1;
+constexpr int kFilterFold2 = 2;
 
 struct FrameRegs {
     float px, py, pz;        // rint: -c        fold: |c|
@@ -81,7 +86,7 @@ template <int kFilter>
 __device__ __forceinline__ FrameRegs load_frame_regs(const FrameParams &p)
 {
     FrameRegs r;
-    if (kFilter == kFilterRint) { r.px = -p.cx; r.py = -p.cy; r.pz = -p.cz; }
+    if (kFilter == kFilterRint) { r.px = -p.cx; r.py = -p.cy; r.pz = -p.cz; }  // else: fold / fold2
     else                        { r.px = fabsf(p.cx); r.py = fabsf(p.cy); r.pz = fabsf(p.cz); }
     r.icx = p.icx; r.icy = p.icy; r.icz = p.icz;
     r.thr = p.thr;
@@ -108,6 +113,41 @@ __device__ __forceinline__ float fast_r2(float ax, float ay, float az, const flo
         wz = fminf(fabsf(dz), f.pz - fabsf(dz));
     }
     return __fmaf_rn(wz, wz, __fmaf_rn(wy, wy, wx * wx));
+}
+
+// fold filter for one A atom against the B atoms (j, j+1) of a pair-interleaved tile:
+// q0 = (x_j, x_j+1, y_j, y_j+1), q1 = (z_j, z_j+1, w_j, w_j+1).  d = a - b and the squared norm run
+// as packed f32x2 instructions (each half rounded exactly like the scalar instruction).
+__device__ __forceinline__ void fast_r2_fold2(float ax, float ay, float az, const float4 &q0, const float4 &q1,
+                                              const FrameRegs &f, float &r0, float &r1)
+{
+    float dx0, dx1, dy0, dy1, dz0, dz1;
+    asm("{\n\t.reg .b64 a, b, d;\n\t"
+        "mov.b64 a, {%2, %2};\n\tmov.b64 b, {%3, %4};\n\t"
+        "sub.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(dx0), "=f"(dx1) : "f"(ax), "f"(q0.x), "f"(q0.y));
+    asm("{\n\t.reg .b64 a, b, d;\n\t"
+        "mov.b64 a, {%2, %2};\n\tmov.b64 b, {%3, %4};\n\t"
+        "sub.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(dy0), "=f"(dy1) : "f"(ay), "f"(q0.z), "f"(q0.w));
+    asm("{\n\t.reg .b64 a, b, d;\n\t"
+        "mov.b64 a, {%2, %2};\n\tmov.b64 b, {%3, %4};\n\t"
+        "sub.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(dz0), "=f"(dz1) : "f"(az), "f"(q1.x), "f"(q1.y));
+    const float wx0 = fminf(fabsf(dx0), f.px - fabsf(dx0)), wx1 = fminf(fabsf(dx1), f.px - fabsf(dx1));
+    const float wy0 = fminf(fabsf(dy0), f.py - fabsf(dy0)), wy1 = fminf(fabsf(dy1), f.py - fabsf(dy1));
+    const float wz0 = fminf(fabsf(dz0), f.pz - fabsf(dz0)), wz1 = fminf(fabsf(dz1), f.pz - fabsf(dz1));
+    asm("{\n\t.reg .b64 x, y, z, r;\n\t"
+        "mov.b64 x, {%2, %3};\n\tmov.b64 y, {%4, %5};\n\tmov.b64 z, {%6, %7};\n\t"
+        "mul.f32x2 r, x, x;\n\tfma.rn.f32x2 r, y, y, r;\n\tfma.rn.f32x2 r, z, z, r;\n\t"
+        "mov.b64 {%0, %1}, r;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(wx0), "f"(wx1), "f"(wy0), "f"(wy1), "f"(wz0), "f"(wz1));
+}
+
+// float index of component k (0..3 = x,y,z,w) of atom j in a pair-interleaved array
+__device__ __forceinline__ size_t pair_layout_index(size_t j, int k)
+{
+    return (j >> 1) * 8 + (size_t)(2 * k) + (j & 1);
 }
 
 // ---------------------------------------------------------------- mbarrier + TMA bulk copy
