@@ -55,7 +55,7 @@ def parse():
 
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -69,7 +69,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except OSError:
@@ -292,7 +292,9 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": "pairs/s",
-                "h2d_bytes_per_step": int(xyz_np.nbytes + cell_np.nbytes + rs.nbytes + os_.nbytes),
+                # only the rows of refSel | outSel atoms travel (strided 2-D copies of the host array)
+                "h2d_bytes_per_step": int(np.union1d(rs, os_).size * nF * 12 + cell_np.nbytes + rs.nbytes + os_.nbytes),
+                "host_array_bytes": int(xyz_np.nbytes),
                 "d2h_bytes_per_step": int(nF * words * 4), "steps": e2e_steps,
                 "api": "namdanalyzer_b200.lib.pylibFuncs.py_getWithin (pinned host arrays)"},
         "gpu_launches": launches,

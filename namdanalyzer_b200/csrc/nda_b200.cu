@@ -74,8 +74,19 @@ struct Ctx {
     bool ready = false;
     int numSMs = 0;
     size_t smemOptin = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copyStream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evCopied[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evBits[2] = {nullptr, nullptr};
+    void *pinned = nullptr;                       // pinned host staging for small results
+    size_t pinnedCap = 0;
+    cudaError_t pinned_reserve(size_t bytes)
+    {
+        if (bytes <= pinnedCap) return cudaSuccess;
+        if (pinned) { cudaFreeHost(pinned); pinned = nullptr; pinnedCap = 0; }
+        cudaError_t e = cudaMallocHost(&pinned, bytes + bytes / 4 + 4096);
+        if (e == cudaSuccess) pinnedCap = bytes + bytes / 4 + 4096;
+        return e;
+    }
     DevBuf packA, packB, packAw, packBw, fp, maxAbs, ctl;        // ctl: [0..1] work counter (u32 x2), stats u64 at +16
     DevBuf raw1, raw2, cell, idx1, idx2, gid, counts, bits, sum;
     double stats[4] = {0, 0, 0, 0};
@@ -119,8 +130,14 @@ static int ctx_get(Ctx **out)
         c.numSMs = prop.multiProcessorCount;
         c.smemOptin = prop.sharedMemPerBlockOptin;
         CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&c.ev0));
         CK(cudaEventCreate(&c.ev1));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&c.evCopied[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c.evDone[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c.evBits[i], cudaEventDisableTiming));
+        }
         CK(c.ctl.reserve(256));
         c.ready = true;
     }
@@ -160,7 +177,8 @@ static int filter_kind()
     const char *e = getenv("NDA_FILTER");
     if (e && !strcmp(e, "rint")) return kFilterRint;
     if (e && !strcmp(e, "fold")) return kFilterFold;
-    return kFilterFold2;
+    if (e && !strncmp(e, "fold2a", 6) && e[6] >= '0' && e[6] <= '3') return kFilterFold2 + (e[6] - '0');
+    return kFilterFold2 + 1;
 }
 
 // frames per pass so that the packed copies stay within a fixed HBM budget
@@ -195,7 +213,7 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
     const int n2Pad = sameSel ? n1Pad : round_up(n2, PAIR_BTILE);
     const int filter = filter_kind();
     const bool fold = filter != kFilterRint;                 // wrapped copies needed
-    const int pairLayout = filter == kFilterFold2 ? 1 : 0;
+    const int pairLayout = is_fold2(filter) ? 1 : 0;
     const size_t bytesPerFrame = ((size_t)n1Pad + (sameSel ? 0 : (size_t)n2Pad)) * sizeof(float4) * (fold ? 2 : 1);
     const int pass = frames_per_pass(bytesPerFrame, fe - fb);
 
@@ -225,12 +243,10 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
 
     int ctasPerSM = 0;
     const void *kfn = nullptr;
-    if (grouped) kfn = filter == kFilterFold2 ? (const void *)rdf_kernel<true, kFilterFold2>
-                     : filter == kFilterFold  ? (const void *)rdf_kernel<true, kFilterFold>
-                                              : (const void *)rdf_kernel<true, kFilterRint>;
-    else         kfn = filter == kFilterFold2 ? (const void *)rdf_kernel<false, kFilterFold2>
-                     : filter == kFilterFold  ? (const void *)rdf_kernel<false, kFilterFold>
-                                              : (const void *)rdf_kernel<false, kFilterRint>;
+#define NDA_RDF_CASE(G, F) case F: kfn = (const void *)rdf_kernel<G, F>; break;
+    if (grouped) switch (filter) { NDA_RDF_CASE(true, 0) NDA_RDF_CASE(true, 1) NDA_RDF_CASE(true, 2) NDA_RDF_CASE(true, 3) NDA_RDF_CASE(true, 4) NDA_RDF_CASE(true, 5) }
+    else         switch (filter) { NDA_RDF_CASE(false, 0) NDA_RDF_CASE(false, 1) NDA_RDF_CASE(false, 2) NDA_RDF_CASE(false, 3) NDA_RDF_CASE(false, 4) NDA_RDF_CASE(false, 5) }
+#undef NDA_RDF_CASE
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kfn, PAIR_THREADS, smem));
     ctasPerSM = tuned_ctas(ctasPerSM);
@@ -271,15 +287,10 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
         a.nItems = (unsigned)items;
         const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)ctasPerSM * c.numSMs);
         CK(c.kev_record(st));
-        if (grouped) {
-            if (filter == kFilterFold2)     rdf_kernel<true, kFilterFold2><<<grid, PAIR_THREADS, smem, st>>>(a);
-            else if (filter == kFilterFold) rdf_kernel<true, kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
-            else                            rdf_kernel<true, kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
-        } else {
-            if (filter == kFilterFold2)     rdf_kernel<false, kFilterFold2><<<grid, PAIR_THREADS, smem, st>>>(a);
-            else if (filter == kFilterFold) rdf_kernel<false, kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
-            else                            rdf_kernel<false, kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
-        }
+#define NDA_RDF_LAUNCH(G, F) case F: rdf_kernel<G, F><<<grid, PAIR_THREADS, smem, st>>>(a); break;
+        if (grouped) switch (filter) { NDA_RDF_LAUNCH(true, 0) NDA_RDF_LAUNCH(true, 1) NDA_RDF_LAUNCH(true, 2) NDA_RDF_LAUNCH(true, 3) NDA_RDF_LAUNCH(true, 4) NDA_RDF_LAUNCH(true, 5) }
+        else         switch (filter) { NDA_RDF_LAUNCH(false, 0) NDA_RDF_LAUNCH(false, 1) NDA_RDF_LAUNCH(false, 2) NDA_RDF_LAUNCH(false, 3) NDA_RDF_LAUNCH(false, 4) NDA_RDF_LAUNCH(false, 5) }
+#undef NDA_RDF_LAUNCH
         LAUNCHED();
         CK(c.kev_record(st));
     }
@@ -300,7 +311,7 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
         const int nBPad = round_up(refSize, PAIR_BTILE);
         const int filter = filter_kind();
         const bool fold = filter != kFilterRint;             // wrapped copies needed
-        const int pairLayout = filter == kFilterFold2 ? 1 : 0;
+        const int pairLayout = is_fold2(filter) ? 1 : 0;
         const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * sizeof(float4) * (fold ? 2 : 1);
         const int pass = frames_per_pass(bytesPerFrame, fe - fb);
         CK(c.packA.reserve((size_t)nAPad * pass * sizeof(float4)));
@@ -326,9 +337,15 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
         a.literal = g_within_pure.load() ? 0 : 1;
         a.workCounter = work; a.stats = stats;
         const size_t smem = PAIR_SMEM_BASE;
-        const void *kfn = filter == kFilterFold2 ? (const void *)within_kernel<kFilterFold2>
-                        : filter == kFilterFold  ? (const void *)within_kernel<kFilterFold>
-                                                 : (const void *)within_kernel<kFilterRint>;
+        const void *kfn = nullptr;
+        switch (filter) {
+        case 0: kfn = (const void *)within_kernel<0>; break;
+        case 1: kfn = (const void *)within_kernel<1>; break;
+        case 2: kfn = (const void *)within_kernel<2>; break;
+        case 3: kfn = (const void *)within_kernel<3>; break;
+        case 4: kfn = (const void *)within_kernel<4>; break;
+        default: kfn = (const void *)within_kernel<5>; break;
+        }
         CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int ctasPerSM = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kfn, PAIR_THREADS, smem));
@@ -358,9 +375,14 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
             a.nItems = (unsigned)items;
             const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)ctasPerSM * c.numSMs);
             CK(c.kev_record(st));
-            if (filter == kFilterFold2)     within_kernel<kFilterFold2><<<grid, PAIR_THREADS, smem, st>>>(a);
-            else if (filter == kFilterFold) within_kernel<kFilterFold><<<grid, PAIR_THREADS, smem, st>>>(a);
-            else                            within_kernel<kFilterRint><<<grid, PAIR_THREADS, smem, st>>>(a);
+            switch (filter) {
+            case 0: within_kernel<0><<<grid, PAIR_THREADS, smem, st>>>(a); break;
+            case 1: within_kernel<1><<<grid, PAIR_THREADS, smem, st>>>(a); break;
+            case 2: within_kernel<2><<<grid, PAIR_THREADS, smem, st>>>(a); break;
+            case 3: within_kernel<3><<<grid, PAIR_THREADS, smem, st>>>(a); break;
+            case 4: within_kernel<4><<<grid, PAIR_THREADS, smem, st>>>(a); break;
+            default: within_kernel<5><<<grid, PAIR_THREADS, smem, st>>>(a); break;
+            }
             LAUNCHED();
             CK(c.kev_record(st));
         }
@@ -650,6 +672,43 @@ int nda_get_distances(const float *sel1, int n1, const float *sel2, int n2, floa
     return NDA_OK;
 }
 
+// Row plan for the within upload: only the atoms named by refSel / outSel are copied.  A row (one
+// atom, all frames) is contiguous in the reference layout, so a run of rows with a constant index
+// stride is ONE strided 2-D copy (water oxygens at 1231 + 3k: one copy).
+struct RowRun { int dstRow, srcRow, stride, count; };
+
+static void plan_rows(const int *refSel, int refSize, const int *outSel, int outSize, int nAtoms,
+                      std::vector<int> &remap, std::vector<RowRun> &runs, int &nRows)
+{
+    std::vector<unsigned char> used((size_t)nAtoms, 0);
+    for (int i = 0; i < refSize; ++i) used[refSel[i]] = 1;
+    for (int i = 0; i < outSize; ++i) used[outSel[i]] = 1;
+    std::vector<int> rows;
+    for (int a = 0; a < nAtoms; ++a) if (used[a]) rows.push_back(a);
+    runs.clear();
+    size_t i = 0;
+    while (i < rows.size()) {
+        size_t j = i + 1;
+        int stride = 1;
+        if (j < rows.size()) {
+            stride = rows[j] - rows[i];
+            while (j + 1 < rows.size() && rows[j + 1] - rows[j] == stride) ++j;
+            ++j;
+        }
+        runs.push_back({(int)i, rows[i], stride, (int)(j - i)});
+        i = j;
+    }
+    if (runs.size() > 512 && !rows.empty()) {              // scattered selection: copy the covering range
+        const int lo = rows.front(), hi = rows.back();
+        rows.clear();
+        for (int a = lo; a <= hi; ++a) rows.push_back(a);
+        runs.assign(1, RowRun{0, lo, 1, hi - lo + 1});
+    }
+    remap.assign((size_t)nAtoms, -1);
+    for (size_t r = 0; r < rows.size(); ++r) remap[rows[r]] = (int)r;
+    nRows = (int)rows.size();
+}
+
 int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *refSel, int refSize,
                         const int *outSel, int outSelSize, uint32_t *bits, int *out,
                         const float *cellDims, float distance, int fb, int fe)
@@ -671,53 +730,100 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
     begin_call(*c);
     const int nFc = fe - fb;
     const int words = (outSelSize + 31) / 32;
-    std::vector<uint32_t> hb;
-    uint32_t *hbits = bits;
-    if (!hbits) { hb.resize((size_t)nFc * words); hbits = hb.data(); }
+
+    // ---- which rows travel, and the selections re-expressed in uploaded-row numbers
+    std::vector<int> remap;
+    std::vector<RowRun> runs;
+    int nRows = 0;
+    plan_rows(refSel, refSize, outSel, outSelSize, nAtoms, remap, runs, nRows);
+    std::vector<int> ref2((size_t)std::max(refSize, 1)), out2((size_t)outSelSize);
+    for (int i = 0; i < refSize; ++i) ref2[i] = remap[refSel[i]];
+    for (int i = 0; i < outSelSize; ++i) out2[i] = remap[outSel[i]];
+
+    // ---- frame chunks: copy of chunk k+1 overlaps pack + kernel of chunk k (two raw buffers)
+    const size_t rowBytesPerFrame = (size_t)nRows * 12;
+    int nChunks = (int)std::min<size_t>(6, std::max<size_t>(1, rowBytesPerFrame * nFc / ((size_t)24 << 20)));
+    int chunk = (nFc + nChunks - 1) / nChunks;
+    const int maxChunk = (int)std::max<size_t>(1, ((size_t)3 << 30) / std::max<size_t>(rowBytesPerFrame, 1));
+    chunk = std::max(1, std::min(chunk, maxChunk));
+    nChunks = (nFc + chunk - 1) / chunk;
 
     CK(c->cell.reserve((size_t)nF * 12));
     CK(c->idx1.reserve((size_t)std::max(refSize, 1) * 4));
     CK(c->idx2.reserve((size_t)outSelSize * 4));
     CK(c->bits.reserve((size_t)nFc * words * 4));
+    CK(c->raw1.reserve(rowBytesPerFrame * chunk));
+    if (nChunks > 1) CK(c->raw2.reserve(rowBytesPerFrame * chunk));
+    CK(c->pinned_reserve((size_t)nFc * words * 4));
+    uint32_t *hbits = reinterpret_cast<uint32_t *>(c->pinned);
+
     CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
     CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
-    if (refSize) CK(cudaMemcpyAsync(c->idx1.p, refSel, (size_t)refSize * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->idx2.p, outSel, (size_t)outSelSize * 4, cudaMemcpyHostToDevice, st));
-    const size_t rowBytes = (size_t)nAtoms * 12;
-    int slab = (int)std::min<size_t>((size_t)nFc, std::max<size_t>(1, ((size_t)4 << 30) / rowBytes));
-    CK(c->raw1.reserve((size_t)nAtoms * slab * 12));
-    float ms = 0.f;
+    if (refSize) CK(cudaMemcpyAsync(c->idx1.p, ref2.data(), (size_t)refSize * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->idx2.p, out2.data(), (size_t)outSelSize * 4, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(c->ev0, st));
-    for (int f0 = fb; f0 < fe; f0 += slab) {
-        const int f1 = std::min(fe, f0 + slab);
-        rc = upload_columns(st, c->raw1.as<float>(), allAtoms, nAtoms, nF, f0, f1);
-        if (rc) return rc;
-        rc = dev_within(*c, st, c->raw1.as<float>(), nAtoms, f1 - f0, c->idx1.as<int>(), refSize,
-                        c->idx2.as<int>(), outSelSize, c->bits.as<unsigned>() + (size_t)(f0 - fb) * words, nullptr,
-                        c->cell.as<float>() + (size_t)f0 * 3, distance, 0, f1 - f0);
-        if (rc) return rc;
-        if (f1 < fe) CK(cudaStreamSynchronize(st));
-    }
-    CK(cudaEventRecord(c->ev1, st));
-    CK(cudaMemcpyAsync(hbits, c->bits.p, (size_t)nFc * words * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    rc = read_stats(*c, (double)refSize * outSelSize * nFc, ms);
-    if (rc) return rc;
-    if (out) {
-        // the reference only ever stores 1 (getWithin.cpp:77,83): scatter the set bits
-        for (int f = 0; f < nFc; ++f) {
+    CK(cudaEventRecord(c->evDone[0], st));                  // both raw buffers start out free
+    CK(cudaEventRecord(c->evDone[1], st));
+
+    auto scatter = [&](int k) {                             // host: set the 1s of chunk k
+        if (!out) return;
+        const int f0 = k * chunk, f1 = std::min(nFc, f0 + chunk);
+        for (int f = f0; f < f1; ++f) {
             const uint32_t *row = hbits + (size_t)f * words;
             for (int w = 0; w < words; ++w) {
                 uint32_t v = row[w];
-                while (v) {
+                while (v) {                                  // the reference only ever stores 1 (getWithin.cpp:77,83)
                     const int b = __builtin_ctz(v);
                     v &= v - 1;
                     out[(size_t)outSel[w * 32 + b] * nF + fb + f] = 1;
                 }
             }
         }
+    };
+
+    for (int k = 0; k < nChunks; ++k) {
+        const int f0 = fb + k * chunk, f1 = std::min(fe, f0 + chunk), wc = f1 - f0, buf = k & 1;
+        float *raw = buf ? c->raw2.as<float>() : c->raw1.as<float>();
+        // copy stream: wait until the kernel that last read this buffer is done, then upload
+        CK(cudaStreamWaitEvent(c->copyStream, c->evDone[buf], 0));
+        for (const RowRun &r : runs) {
+            const size_t w = (size_t)wc * 12;
+            if ((size_t)r.stride * nF * 12 > ((size_t)1 << 30) && r.count > 1) {
+                for (int q = 0; q < r.count; ++q)              // pitch beyond cudaMemcpy2D's limit: row by row
+                    CK(cudaMemcpyAsync(raw + (size_t)(r.dstRow + q) * wc * 3,
+                                       allAtoms + ((size_t)(r.srcRow + (size_t)q * r.stride) * nF + f0) * 3, w,
+                                       cudaMemcpyHostToDevice, c->copyStream));
+            } else if (r.count == 1 || (r.stride == 1 && wc == nF)) {
+                CK(cudaMemcpyAsync(raw + (size_t)r.dstRow * wc * 3, allAtoms + ((size_t)r.srcRow * nF + f0) * 3,
+                                   r.count == 1 ? w : w * r.count, cudaMemcpyHostToDevice, c->copyStream));
+            } else {
+                CK(cudaMemcpy2DAsync(raw + (size_t)r.dstRow * wc * 3, w, allAtoms + ((size_t)r.srcRow * nF + f0) * 3,
+                                     (size_t)r.stride * nF * 12, w, (size_t)r.count, cudaMemcpyHostToDevice, c->copyStream));
+            }
+        }
+        CK(cudaEventRecord(c->evCopied[buf], c->copyStream));
+        CK(cudaStreamWaitEvent(st, c->evCopied[buf], 0));
+        rc = dev_within(*c, st, raw, nRows, wc, c->idx1.as<int>(), refSize, c->idx2.as<int>(), outSelSize,
+                        c->bits.as<unsigned>() + (size_t)(f0 - fb) * words, nullptr,
+                        c->cell.as<float>() + (size_t)f0 * 3, distance, 0, wc);
+        if (rc) return rc;
+        CK(cudaEventRecord(c->evDone[buf], st));
+        CK(cudaMemcpyAsync(hbits + (size_t)(f0 - fb) * words, c->bits.as<unsigned>() + (size_t)(f0 - fb) * words,
+                           (size_t)wc * words * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(c->evBits[buf], st));
+        if (k > 0) {                                         // host scatters chunk k-1 while the GPU works on k
+            CK(cudaEventSynchronize(c->evBits[buf ^ 1]));
+            scatter(k - 1);
+        }
     }
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    scatter(nChunks - 1);
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    rc = read_stats(*c, (double)refSize * outSelSize * nFc, ms);
+    if (rc) return rc;
+    if (bits) memcpy(bits, hbits, (size_t)nFc * words * 4);
     return NDA_OK;
 }
 

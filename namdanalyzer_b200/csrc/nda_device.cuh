@@ -74,11 +74,12 @@ __device__ __forceinline__ int strict_bin(float r2, float dr, int outSize)
 //                 instruction sit in adjacent registers -> ~9 issue slots per pair instead of 12.
 constexpr int kFilterRint = 0;
 constexpr int kFilterFold = 1;
-constexpr int kFilterFold2 = 2;
+constexpr int kFilterFold2 = 2;     // 2..5 = fold2 with 0..3 axes in the add form (see fold_axis2)
+__host__ __device__ constexpr bool is_fold2(int f) { return f >= kFilterFold2; }
 
 struct FrameRegs {
     float px, py, pz;        // rint: -c        fold: |c|
-    float icx, icy, icz;     // rint: fl(1/c)   fold: unused
+    float icx, icy, icz;     // rint: fl(1/c)   fold: |c|/2 (exact)
     float thr;
 };
 
@@ -88,7 +89,8 @@ __device__ __forceinline__ FrameRegs load_frame_regs(const FrameParams &p)
     FrameRegs r;
     if (kFilter == kFilterRint) { r.px = -p.cx; r.py = -p.cy; r.pz = -p.cz; }  // else: fold / fold2
     else                        { r.px = fabsf(p.cx); r.py = fabsf(p.cy); r.pz = fabsf(p.cz); }
-    r.icx = p.icx; r.icy = p.icy; r.icz = p.icz;
+    if (kFilter == kFilterRint) { r.icx = p.icx; r.icy = p.icy; r.icz = p.icz; }
+    else { r.icx = 0.5f * fabsf(p.cx); r.icy = 0.5f * fabsf(p.cy); r.icz = 0.5f * fabsf(p.cz); }
     r.thr = p.thr;
     return r;
 }
@@ -116,27 +118,54 @@ __device__ __forceinline__ float fast_r2(float ax, float ay, float az, const flo
 }
 
 // fold filter for one A atom against the B atoms (j, j+1) of a pair-interleaved tile:
-// q0 = (x_j, x_j+1, y_j, y_j+1), q1 = (z_j, z_j+1, w_j, w_j+1).  d = a - b and the squared norm run
-// as packed f32x2 instructions (each half rounded exactly like the scalar instruction).
+// q0 = (x_j, x_j+1, y_j, y_j+1), q1 = (z_j, z_j+1, w_j, w_j+1).  Everything on the FMA pipe runs as
+// packed f32x2 instructions (SASS FADD2 / FMUL2 / FFMA2; each half is rounded exactly like the
+// scalar instruction, |x| and -x are free operand modifiers).  Per axis the folded component is
+//   min form : e = c - |d| (FADD2), |w| = min(|d|, e)           (2 x FMNMX on the ALU pipe)
+//   add form : t = |d| - c/2 (FADD2), |w| = c/2 - |t| (FADD2)     (no ALU instruction)
+// kAddAxes of the three axes use the add form: it trades ALU-pipe cycles (half rate) for FMA-pipe
+// cycles so that neither pipe saturates.
+__device__ __forceinline__ void sub2_bcast_a(float a, float b0, float b1, float &d0, float &d1)
+{
+    asm("{\n\t.reg .b64 a, b, d;\n\t"
+        "mov.b64 a, {%2, %2};\n\tmov.b64 b, {%3, %4};\n\t"
+        "sub.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a), "f"(b0), "f"(b1));
+}
+
+__device__ __forceinline__ void sub2_bcast_b(float a0, float a1, float b, float &d0, float &d1)
+{
+    asm("{\n\t.reg .b64 a, b, d;\n\t"
+        "mov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\t"
+        "sub.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b));
+}
+
+template <bool kAddForm>
+__device__ __forceinline__ void fold_axis2(float a, float b0, float b1, float c, float h, float &w0, float &w1)
+{
+    float d0, d1;
+    sub2_bcast_a(a, b0, b1, d0, d1);                       // d = a - b
+    if (kAddForm) {
+        float t0, t1;
+        sub2_bcast_b(fabsf(d0), fabsf(d1), h, t0, t1);     // t = |d| - c/2
+        sub2_bcast_a(h, fabsf(t0), fabsf(t1), w0, w1);     // |w| = c/2 - |t|
+    } else {
+        float e0, e1;
+        sub2_bcast_a(c, fabsf(d0), fabsf(d1), e0, e1);     // e = c - |d|
+        w0 = fminf(fabsf(d0), e0);
+        w1 = fminf(fabsf(d1), e1);
+    }
+}
+
+template <int kAddAxes>
 __device__ __forceinline__ void fast_r2_fold2(float ax, float ay, float az, const float4 &q0, const float4 &q1,
                                               const FrameRegs &f, float &r0, float &r1)
 {
-    float dx0, dx1, dy0, dy1, dz0, dz1;
-    asm("{\n\t.reg .b64 a, b, d;\n\t"
-        "mov.b64 a, {%2, %2};\n\tmov.b64 b, {%3, %4};\n\t"
-        "sub.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
-        : "=f"(dx0), "=f"(dx1) : "f"(ax), "f"(q0.x), "f"(q0.y));
-    asm("{\n\t.reg .b64 a, b, d;\n\t"
-        "mov.b64 a, {%2, %2};\n\tmov.b64 b, {%3, %4};\n\t"
-        "sub.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
-        : "=f"(dy0), "=f"(dy1) : "f"(ay), "f"(q0.z), "f"(q0.w));
-    asm("{\n\t.reg .b64 a, b, d;\n\t"
-        "mov.b64 a, {%2, %2};\n\tmov.b64 b, {%3, %4};\n\t"
-        "sub.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
-        : "=f"(dz0), "=f"(dz1) : "f"(az), "f"(q1.x), "f"(q1.y));
-    const float wx0 = fminf(fabsf(dx0), f.px - fabsf(dx0)), wx1 = fminf(fabsf(dx1), f.px - fabsf(dx1));
-    const float wy0 = fminf(fabsf(dy0), f.py - fabsf(dy0)), wy1 = fminf(fabsf(dy1), f.py - fabsf(dy1));
-    const float wz0 = fminf(fabsf(dz0), f.pz - fabsf(dz0)), wz1 = fminf(fabsf(dz1), f.pz - fabsf(dz1));
+    float wx0, wx1, wy0, wy1, wz0, wz1;
+    fold_axis2<(kAddAxes >= 3)>(ax, q0.x, q0.y, f.px, f.icx, wx0, wx1);
+    fold_axis2<(kAddAxes >= 2)>(ay, q0.z, q0.w, f.py, f.icy, wy0, wy1);
+    fold_axis2<(kAddAxes >= 1)>(az, q1.x, q1.y, f.pz, f.icz, wz0, wz1);
     asm("{\n\t.reg .b64 x, y, z, r;\n\t"
         "mov.b64 x, {%2, %3};\n\tmov.b64 y, {%4, %5};\n\tmov.b64 z, {%6, %7};\n\t"
         "mul.f32x2 r, x, x;\n\tfma.rn.f32x2 r, y, y, r;\n\tfma.rn.f32x2 r, z, z, r;\n\t"
