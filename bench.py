@@ -155,7 +155,7 @@ def run_reference(args, rank, world):
                                    "one frame per call, %d frames x 1231 x 7923 pairs per step" % sample_frames},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, sample=None):
@@ -203,8 +203,13 @@ def run_ours(args, rank, world, local_rank):
     d_os = torch.from_numpy(os_).to(dev)
     d_bits = torch.zeros((nF, words), dtype=torch.int32, device=dev)
     d_out = torch.zeros((nA, nF), dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream: the library treats a NULL stream as "use my own", and the
+    # CUDA events below must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     st = ctypes.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
+    torch.cuda.synchronize()                 # inputs above were staged on the default stream
 
     def step_resident():
         _capi.check(lib.nda_dev_within(d_xyz.data_ptr(), nA, nF, d_rs.data_ptr(), rs.size, d_os.data_ptr(), os_.size,
@@ -259,6 +264,10 @@ def run_ours(args, rank, world, local_rank):
     hits_e2e = int(out_np.sum())
     hits_dev = int(d_out.sum().item())
 
+    rdf_sharded = None
+    if world > 1 and not args.no_extras:
+        rdf_sharded = rdf_sharded_extra(lib, _capi, torch, dist, dev, st, rank, world)
+
     if rank != 0:
         return
 
@@ -303,6 +312,8 @@ def run_ours(args, rank, world, local_rank):
         "check": {"hits_resident": hits_dev, "hits_e2e": hits_e2e},
     }
 
+    if rdf_sharded is not None:
+        line["rdf_sharded"] = rdf_sharded
     if not args.no_extras and world == 1:
         line["rdf"] = rdf_extra(lib, _capi, torch, dev, st, peak)
         threads = os.cpu_count() or 1
@@ -318,7 +329,7 @@ def run_ours(args, rank, world, local_rank):
                                 "sample": "reference OpenMP getWithin (oracle/_ref/libref_fast.so, shipped flags), "
                                           "one frame per call, %d frames x %d repeats of config 2 (%.1f s)"
                                           % (sample, reps, dt)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def rdf_extra(lib, _capi, torch, dev, st, peak):
@@ -360,7 +371,60 @@ def rdf_extra(lib, _capi, torch, dev, st, peak):
             "counts_total": int(counts.sum().item())}
 
 
+def rdf_sharded_extra(lib, _capi, torch, dist, dev, st, rank, world):
+    """Frame-sharded RDF with ONE NCCL all-reduce of the u64 histogram: a config-5 shaped trajectory of
+    2*world frames, rank r generates and processes frames [2r, 2r+2) (strong scaling of the frame
+    axis); device time = max over ranks of (kernel + all-reduce)."""
+    from namdanalyzer_b200.distributed import frame_range
+    n_side = 69
+    n = n_side ** 3
+    nF = 2 * world
+    fb, fe = frame_range(nF, rank, world)
+    L = float(np.float32((n / 0.0334) ** (1.0 / 3.0)))
+    xyz = torch.empty((n, nF, 3), dtype=torch.float32, device=dev)
+    cell = torch.empty((nF, 3), dtype=torch.float32, device=dev)
+    _capi.check(lib.nda_dev_synth_water_box(xyz.data_ptr(), cell.data_ptr(), n_side, nF, fb, fe, L, 0.6, 1005, st))
+    counts = torch.zeros(149, dtype=torch.int64, device=dev)
+
+    def go():
+        counts.zero_()
+        _capi.check(lib.nda_dev_radial_nbr_counts(xyz.data_ptr(), n, xyz.data_ptr(), n, None, 1, counts.data_ptr(), 149,
+                                                  cell.data_ptr(), nF, fb, fe, 1, 0.1, st))
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    go()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        go()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pairs = 0.5 * n * (n - 1.0) * nF
+    return {"workload": "config-5 shape: %d O atoms, %d frames sharded over %d ranks, one NCCL all-reduce of 149 x u64"
+                        % (n, nF, world),
+            "ms_per_pass": float(t.item()), "pairs_per_s": pairs / (float(t.item()) * 1e-3),
+            "counts_total": int(counts.sum().item())}
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was
+    redirected to stderr by main()"""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -339,3 +339,48 @@ def test_device_pointer_api_and_synth_generator():
     w = port.distances_sum(host["sel1"][:20], host["sel1"], host["cellDims"], 0)
     assert np.max(np.abs(s.cpu().numpy() - w) / np.maximum(w, 1e-30)) <= 1e-12
     assert L.nda_launch_count() > 0
+
+
+def test_device_api_frame_ranges_match_whole():
+    """device entry points with frameBegin > 0 (what a rank of a multi-GPU job calls)"""
+    import ctypes
+    import torch
+    from namdanalyzer_b200 import _capi
+    L = _capi.load()
+    c = synth.config5(n_side=16, n_frames=5)
+    n, nF = c["sel1"].shape[:2]
+    xyz = torch.from_numpy(c["sel1"]).cuda()
+    cell = torch.from_numpy(c["cellDims"]).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    want = port.rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, NB, 0.1).astype(np.int64)
+    tot = torch.zeros(NB, dtype=torch.int64, device="cuda")
+    for fb, fe in ((0, 2), (2, 3), (3, 5)):
+        part = torch.zeros(NB, dtype=torch.int64, device="cuda")
+        _capi.check(L.nda_dev_radial_nbr_counts(xyz.data_ptr(), n, xyz.data_ptr(), n, None, 1, part.data_ptr(), NB,
+                                                cell.data_ptr(), nF, fb, fe, 1, 0.1, st))
+        torch.cuda.synchronize()
+        w = port.rdf_counts(c["sel1"][:, fb:fe], c["sel1"][:, fb:fe], c["cellDims"][fb:fe], 1, NB, 0.1).astype(np.int64)
+        assert np.array_equal(part.cpu().numpy(), w), (fb, fe)
+        tot += part
+    assert np.array_equal(tot.cpu().numpy(), want)
+    # within with a frame range: bits rows are relative to frameBegin, d_out columns absolute
+    refSel = torch.arange(0, 300, dtype=torch.int32, device="cuda")
+    outSel = torch.arange(200, n, dtype=torch.int32, device="cuda")
+    words = (outSel.numel() + 31) // 32
+    out = torch.zeros((n, nF), dtype=torch.int32, device="cuda")
+    for fb, fe in ((0, 1), (1, 4), (4, 5)):
+        bits = torch.zeros((fe - fb, words), dtype=torch.int32, device="cuda")
+        _capi.check(L.nda_dev_within(xyz.data_ptr(), n, nF, refSel.data_ptr(), 300, outSel.data_ptr(), outSel.numel(),
+                                     bits.data_ptr(), out.data_ptr(), cell.data_ptr(), 3.4, fb, fe, st))
+    torch.cuda.synchronize()
+    wantm = port.within(c["sel1"], refSel.cpu().numpy(), outSel.cpu().numpy(), c["cellDims"], 3.4)
+    assert np.array_equal(out.cpu().numpy(), wantm)
+    # distances with a frame range
+    s = torch.zeros((10, n), dtype=torch.float64, device="cuda")
+    sub = xyz[:10].contiguous()
+    for fb, fe in ((0, 3), (3, 5)):
+        _capi.check(L.nda_dev_distances_sum(sub.data_ptr(), 10, xyz.data_ptr(), n, s.data_ptr(), cell.data_ptr(),
+                                            nF, fb, fe, 0, st))
+    torch.cuda.synchronize()
+    w = port.distances_sum(c["sel1"][:10], c["sel1"], c["cellDims"], 0)
+    assert np.max(np.abs(s.cpu().numpy() - w) / np.maximum(w, 1e-30)) <= 1e-12
