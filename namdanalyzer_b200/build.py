@@ -13,7 +13,7 @@ OUT = os.path.join(_HERE, "lib", "libnda_b200.so")
 SOURCES = ["nda_b200.cu"]
 DEPS = ["nda_b200.cu", "nda_kernels.cuh", "nda_device.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+              "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-fopenmp", "-lgomp"]
 
 
 def _stale():

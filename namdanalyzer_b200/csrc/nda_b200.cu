@@ -9,6 +9,7 @@
 #include <math.h>
 #include <atomic>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -23,6 +24,7 @@ static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_within_pure{0};
 static std::mutex g_mutex;
+static int g_host_threads = 4;          // host threads gathering pageable rows into pinned staging
 
 static int fail(int code, const char *fmt, ...)
 {
@@ -88,7 +90,18 @@ struct Ctx {
         return e;
     }
     DevBuf packA, packB, packAw, packBw, fp, maxAbs, ctl;        // ctl: [0..1] work counter (u32 x2), stats u64 at +16
-    DevBuf raw1, raw2, cell, idx1, idx2, gid, counts, bits, sum;
+    DevBuf raw[2][2];                             // [array][double buffer] raw coordinate chunks
+    DevBuf cell, idx1, idx2, gid, counts, bits, sum;
+    void *stage[2] = {nullptr, nullptr};          // pinned staging for pageable inputs
+    size_t stageCap[2] = {0, 0};
+    cudaError_t stage_reserve(int b, size_t bytes)
+    {
+        if (bytes <= stageCap[b]) return cudaSuccess;
+        if (stage[b]) { cudaFreeHost(stage[b]); stage[b] = nullptr; stageCap[b] = 0; }
+        cudaError_t e = cudaMallocHost(&stage[b], bytes + bytes / 8 + 4096);
+        if (e == cudaSuccess) stageCap[b] = bytes + bytes / 8 + 4096;
+        return e;
+    }
     double stats[4] = {0, 0, 0, 0};
     // CUDA-event brackets around the pair kernel of every pass of the last entry-point call
     std::vector<cudaEvent_t> kev;
@@ -139,6 +152,12 @@ static int ctx_get(Ctx **out)
             CK(cudaEventCreateWithFlags(&c.evBits[i], cudaEventDisableTiming));
         }
         CK(c.ctl.reserve(256));
+        {
+            unsigned hw = std::thread::hardware_concurrency();
+            int t = (int)std::max(1u, std::min(8u, hw / 2));
+            if (const char *e = getenv("NDA_HOST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) t = v; }
+            g_host_threads = t;
+        }
         c.ready = true;
     }
     *out = &c;
@@ -413,17 +432,183 @@ static int dev_distances(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, c
 // ------------------------------------------------------------------------------------------
 // host helpers
 // ------------------------------------------------------------------------------------------
-// copy columns [fb, fe) of a host [n][nF][3] array into a compact device [n][fe-fb][3] array
-static int upload_columns(cudaStream_t st, float *dst, const float *src, int n, int nF, int fb, int fe)
+// Pipelined upload of frame chunks of reference-layout arrays ([row][nF][3] float32).
+//
+//  * A row (one atom, all frames) is contiguous, so a run of rows with a constant index stride and a
+//    frame window is ONE strided 2-D copy (water oxygens at 1231 + 3k: one copy).
+//  * Pinned (or registered) host memory is DMA'd directly.  Pageable memory -- what numpy gives the
+//    reference's callers -- is first gathered by a few host threads into pinned staging and then
+//    DMA'd as one contiguous block; the driver's own pageable path moves narrow rows one by one.
+//  * Two device buffers per array alternate between the copy stream and the compute stream:
+//    the upload of chunk k+1 overlaps pack + kernel of chunk k.
+struct RowRun { int dstRow, srcRow, stride, count; };
+
+static void runs_from_rows(const std::vector<int> &rows, std::vector<RowRun> &runs)
 {
-    const size_t w = (size_t)(fe - fb) * 12;
-    if (fb == 0 && fe == nF) {
-        CK(cudaMemcpyAsync(dst, src, (size_t)n * w, cudaMemcpyHostToDevice, st));
-    } else {
-        CK(cudaMemcpy2DAsync(dst, w, src + (size_t)fb * 3, (size_t)nF * 12, w, (size_t)n, cudaMemcpyHostToDevice, st));
+    runs.clear();
+    size_t i = 0;
+    while (i < rows.size()) {
+        size_t j = i + 1;
+        int stride = 1;
+        if (j < rows.size()) {
+            stride = rows[j] - rows[i];
+            while (j + 1 < rows.size() && rows[j + 1] - rows[j] == stride) ++j;
+            ++j;
+        }
+        runs.push_back({(int)i, rows[i], stride, (int)(j - i)});
+        i = j;
     }
-    return NDA_OK;
 }
+
+// rows needed by a within call and the selections re-expressed in uploaded-row numbers
+static void plan_rows(const int *refSel, int refSize, const int *outSel, int outSize, int nAtoms,
+                      std::vector<int> &remap, std::vector<RowRun> &runs, int &nRows)
+{
+    std::vector<unsigned char> used((size_t)nAtoms, 0);
+    for (int i = 0; i < refSize; ++i) used[refSel[i]] = 1;
+    for (int i = 0; i < outSize; ++i) used[outSel[i]] = 1;
+    std::vector<int> rows;
+    for (int a = 0; a < nAtoms; ++a) if (used[a]) rows.push_back(a);
+    runs_from_rows(rows, runs);
+    if (runs.size() > 512 && !rows.empty()) {              // scattered selection: copy the covering range
+        const int lo = rows.front(), hi = rows.back();
+        rows.clear();
+        for (int a = lo; a <= hi; ++a) rows.push_back(a);
+        runs.assign(1, RowRun{0, lo, 1, hi - lo + 1});
+    }
+    remap.assign((size_t)nAtoms, -1);
+    for (size_t r = 0; r < rows.size(); ++r) remap[rows[r]] = (int)r;
+    nRows = (int)rows.size();
+}
+
+static bool host_ptr_is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+struct UploadArray {
+    const float *host = nullptr;
+    int nRows = 0;                       // rows uploaded (after the row plan)
+    std::vector<RowRun> runs;
+    bool pinned = false;
+    size_t stageOff = 0;                 // byte offset of this array inside a staging buffer
+};
+
+struct Uploader {
+    Ctx &c;
+    int nF, fb, fe, chunk = 0, nChunks = 0;
+    std::vector<UploadArray> arr;
+    Uploader(Ctx &ctx, int nF_, int fb_, int fe_) : c(ctx), nF(nF_), fb(fb_), fe(fe_) {}
+
+    void add(const float *host, int nRows)                              // all rows 0..nRows-1
+    {
+        UploadArray a;
+        a.host = host; a.nRows = nRows;
+        if (nRows > 0) a.runs.push_back({0, 0, 1, nRows});
+        arr.push_back(a);
+    }
+    void add(const float *host, int nRows, const std::vector<RowRun> &runs)
+    {
+        UploadArray a;
+        a.host = host; a.nRows = nRows; a.runs = runs;
+        arr.push_back(a);
+    }
+
+    // choose the chunking, reserve device / staging buffers, mark both buffers free
+    int begin(int maxChunks, const char *envOverride)
+    {
+        const int nFc = fe - fb;
+        size_t bytesPerFrame = 0;
+        for (auto &a : arr) { a.pinned = host_ptr_is_pinned(a.host); bytesPerFrame += (size_t)a.nRows * 12; }
+        if (bytesPerFrame == 0) bytesPerFrame = 12;
+        nChunks = (int)std::min<size_t>((size_t)maxChunks, std::max<size_t>(1, bytesPerFrame * nFc / ((size_t)16 << 20)));
+        if (envOverride) if (const char *e = getenv(envOverride)) { int v = atoi(e); if (v >= 1) nChunks = v; }
+        nChunks = std::max(1, std::min(nChunks, nFc));
+        chunk = (nFc + nChunks - 1) / nChunks;
+        const int maxChunk = (int)std::max<size_t>(1, ((size_t)3 << 30) / bytesPerFrame);   // <= 3 GB per buffer
+        chunk = std::max(1, std::min(chunk, maxChunk));
+        nChunks = (nFc + chunk - 1) / chunk;
+        size_t stageBytes = 0;
+        for (size_t i = 0; i < arr.size(); ++i) {
+            if (arr.size() > 2) return fail(NDA_ERR_ARG, "internal: at most two arrays per upload");
+            CK(c.raw[i][0].reserve((size_t)arr[i].nRows * chunk * 12 + 16));
+            if (nChunks > 1) CK(c.raw[i][1].reserve((size_t)arr[i].nRows * chunk * 12 + 16));
+            if (!arr[i].pinned) { arr[i].stageOff = stageBytes; stageBytes += ((size_t)arr[i].nRows * chunk * 12 + 255) & ~(size_t)255; }
+        }
+        if (stageBytes) {
+            CK(c.stage_reserve(0, stageBytes));
+            if (nChunks > 1) CK(c.stage_reserve(1, stageBytes));
+        }
+        CK(cudaEventRecord(c.evDone[0], c.stream));
+        CK(cudaEventRecord(c.evDone[1], c.stream));
+        CK(cudaEventRecord(c.evCopied[0], c.copyStream));
+        CK(cudaEventRecord(c.evCopied[1], c.copyStream));
+        return NDA_OK;
+    }
+
+    int f0(int k) const { return fb + k * chunk; }
+    int f1(int k) const { return std::min(fe, f0(k) + chunk); }
+    float *dev(int i, int k) const { return c.raw[i][k & 1].as<float>(); }
+
+    // enqueue the upload of chunk k on the copy stream (gathering on the host first if pageable)
+    int issue(int k)
+    {
+        const int b = k & 1, a0 = f0(k), wc = f1(k) - a0;
+        const size_t w = (size_t)wc * 12;
+        bool anyStage = false;
+        for (auto &a : arr) anyStage = anyStage || (!a.pinned && a.nRows > 0);
+        if (anyStage) CK(cudaEventSynchronize(c.evCopied[b]));           // staging buffer b has been consumed
+        for (size_t i = 0; i < arr.size(); ++i) {
+            UploadArray &a = arr[i];
+            if (a.pinned || a.nRows == 0) continue;
+            char *dst = static_cast<char *>(c.stage[b]) + a.stageOff;
+            const float *src = a.host;
+            const int nRuns = (int)a.runs.size();
+            const long long nFl = nF;
+            #pragma omp parallel for schedule(static) num_threads(g_host_threads) if (a.nRows * w > (1u << 20))
+            for (int r = 0; r < a.nRows; ++r) {
+                // locate the run of uploaded row r (runs are few; linear scan from a cached guess is enough)
+                int q = 0;
+                while (q + 1 < nRuns && a.runs[q + 1].dstRow <= r) ++q;
+                const long long srcRow = a.runs[q].srcRow + (long long)(r - a.runs[q].dstRow) * a.runs[q].stride;
+                memcpy(dst + (size_t)r * w, src + (srcRow * nFl + a0) * 3, w);
+            }
+        }
+        CK(cudaStreamWaitEvent(c.copyStream, c.evDone[b], 0));             // device buffer b is free again
+        for (size_t i = 0; i < arr.size(); ++i) {
+            UploadArray &a = arr[i];
+            if (a.nRows == 0) continue;
+            float *raw = dev((int)i, k);
+            if (!a.pinned) {
+                CK(cudaMemcpyAsync(raw, static_cast<char *>(c.stage[b]) + a.stageOff, (size_t)a.nRows * w,
+                                   cudaMemcpyHostToDevice, c.copyStream));
+                continue;
+            }
+            for (const RowRun &r : a.runs) {
+                const float *src = a.host + ((size_t)r.srcRow * nF + a0) * 3;
+                float *dst = raw + (size_t)r.dstRow * wc * 3;
+                if (r.count == 1 || (r.stride == 1 && wc == nF)) {
+                    CK(cudaMemcpyAsync(dst, src, w * r.count, cudaMemcpyHostToDevice, c.copyStream));
+                } else if ((size_t)r.stride * nF * 12 > ((size_t)1 << 30)) {
+                    for (int q = 0; q < r.count; ++q)              // pitch beyond the 2-D copy limit: row by row
+                        CK(cudaMemcpyAsync(dst + (size_t)q * wc * 3, src + (size_t)q * r.stride * nF * 3, w,
+                                           cudaMemcpyHostToDevice, c.copyStream));
+                } else {
+                    CK(cudaMemcpy2DAsync(dst, w, src, (size_t)r.stride * nF * 12, w, (size_t)r.count,
+                                         cudaMemcpyHostToDevice, c.copyStream));
+                }
+            }
+        }
+        CK(cudaEventRecord(c.evCopied[b], c.copyStream));
+        return NDA_OK;
+    }
+
+    // compute stream: wait for chunk k's data / declare its buffers consumed
+    int acquire(int k) { CK(cudaStreamWaitEvent(c.stream, c.evCopied[k & 1], 0)); return NDA_OK; }
+    int release(int k) { CK(cudaEventRecord(c.evDone[k & 1], c.stream)); return NDA_OK; }
+};
 
 static int read_stats(Ctx &c, double pairs, float ms)
 {
@@ -578,22 +763,26 @@ int nda_get_radial_nbr_counts(const float *sel1, int n1, const float *sel2, int 
             CK(c->gid.reserve((size_t)n2 * 4));
             CK(cudaMemcpyAsync(c->gid.p, groupId, (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
         }
-        // upload in frame slabs so the raw copies stay bounded
-        const size_t rowBytes = ((size_t)n1 + (sameSel ? 0 : (size_t)n2)) * 12;
-        int slab = (int)std::min<size_t>((size_t)nFc, std::max<size_t>(1, ((size_t)4 << 30) / rowBytes));
-        CK(c->raw1.reserve((size_t)n1 * slab * 12));
-        if (!sameSel) CK(c->raw2.reserve((size_t)n2 * slab * 12));
+        // frame chunks: the upload of chunk k+1 overlaps pack + kernel of chunk k
+        Uploader up(*c, nF, fb, fe);
+        up.add(sel1, n1);
+        if (!sameSel) up.add(sel2, n2);
+        rc = up.begin(8, "NDA_UPLOAD_CHUNKS");
+        if (rc) return rc;
         CK(cudaEventRecord(c->ev0, st));
-        for (int f0 = fb; f0 < fe; f0 += slab) {
-            const int f1 = std::min(fe, f0 + slab);
-            rc = upload_columns(st, c->raw1.as<float>(), sel1, n1, nF, f0, f1);
+        rc = up.issue(0);
+        if (rc) return rc;
+        for (int k = 0; k < up.nChunks; ++k) {
+            const int wc = up.f1(k) - up.f0(k);
+            rc = up.acquire(k);
             if (rc) return rc;
-            if (!sameSel) { rc = upload_columns(st, c->raw2.as<float>(), sel2, n2, nF, f0, f1); if (rc) return rc; }
-            rc = dev_rdf(*c, st, c->raw1.as<float>(), n1, sameSel ? c->raw1.as<float>() : c->raw2.as<float>(), n2,
+            rc = dev_rdf(*c, st, up.dev(0, k), n1, sameSel ? up.dev(0, k) : up.dev(1, k), n2,
                          groupId ? c->gid.as<int>() : nullptr, nGroups, c->counts.as<unsigned long long>(), outSize,
-                         c->cell.as<float>() + (size_t)f0 * 3, f1 - f0, 0, f1 - f0, sameSel, dr);
+                         c->cell.as<float>() + (size_t)up.f0(k) * 3, wc, 0, wc, sameSel, dr);
             if (rc) return rc;
-            if (f1 < fe) CK(cudaStreamSynchronize(st));      // raw slabs are reused
+            rc = up.release(k);
+            if (rc) return rc;
+            if (k + 1 < up.nChunks) { rc = up.issue(k + 1); if (rc) return rc; }
         }
         CK(cudaEventRecord(c->ev1, st));
         CK(cudaMemcpyAsync(h.data(), c->counts.p, H * 8, cudaMemcpyDeviceToHost, st));
@@ -631,24 +820,27 @@ int nda_get_distances_sum(const float *sel1, int n1, const float *sel2, int n2, 
     const size_t M = (size_t)n1 * n2;
     if (M == 0) return NDA_OK;
     if (fe == fb) { memset(sum, 0, M * 8); return NDA_OK; }
-    const int nFc = fe - fb;
     CK(c->sum.reserve(M * 8));
     CK(c->cell.reserve((size_t)nF * 12));
     CK(cudaMemsetAsync(c->sum.p, 0, M * 8, st));
     CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
-    const size_t rowBytes = ((size_t)n1 + (sameSel ? 0 : (size_t)n2)) * 12;
-    int slab = (int)std::min<size_t>((size_t)nFc, std::max<size_t>(1, ((size_t)4 << 30) / rowBytes));
-    CK(c->raw1.reserve((size_t)n1 * slab * 12));
-    if (!sameSel) CK(c->raw2.reserve((size_t)n2 * slab * 12));
-    for (int f0 = fb; f0 < fe; f0 += slab) {
-        const int f1 = std::min(fe, f0 + slab);
-        rc = upload_columns(st, c->raw1.as<float>(), sel1, n1, nF, f0, f1);
+    Uploader up(*c, nF, fb, fe);
+    up.add(sel1, n1);
+    if (!sameSel) up.add(sel2, n2);
+    rc = up.begin(8, "NDA_UPLOAD_CHUNKS");
+    if (rc) return rc;
+    rc = up.issue(0);
+    if (rc) return rc;
+    for (int k = 0; k < up.nChunks; ++k) {
+        const int wc = up.f1(k) - up.f0(k);
+        rc = up.acquire(k);
         if (rc) return rc;
-        if (!sameSel) { rc = upload_columns(st, c->raw2.as<float>(), sel2, n2, nF, f0, f1); if (rc) return rc; }
-        rc = dev_distances(*c, st, c->raw1.as<float>(), n1, sameSel ? c->raw1.as<float>() : c->raw2.as<float>(), n2,
-                           c->sum.as<double>(), c->cell.as<float>() + (size_t)f0 * 3, f1 - f0, 0, f1 - f0, sameSel);
+        rc = dev_distances(*c, st, up.dev(0, k), n1, sameSel ? up.dev(0, k) : up.dev(1, k), n2,
+                           c->sum.as<double>(), c->cell.as<float>() + (size_t)up.f0(k) * 3, wc, 0, wc, sameSel);
         if (rc) return rc;
-        if (f1 < fe) CK(cudaStreamSynchronize(st));
+        rc = up.release(k);
+        if (rc) return rc;
+        if (k + 1 < up.nChunks) { rc = up.issue(k + 1); if (rc) return rc; }
     }
     if (sameSel) {
         dim3 grid((n1 + 255) / 256, n1);
@@ -670,43 +862,6 @@ int nda_get_distances(const float *sel1, int n1, const float *sel2, int n2, floa
     if (rc) return rc;
     for (size_t i = 0; i < s.size(); ++i) out[i] = (float)(s[i] / (double)nF);
     return NDA_OK;
-}
-
-// Row plan for the within upload: only the atoms named by refSel / outSel are copied.  A row (one
-// atom, all frames) is contiguous in the reference layout, so a run of rows with a constant index
-// stride is ONE strided 2-D copy (water oxygens at 1231 + 3k: one copy).
-struct RowRun { int dstRow, srcRow, stride, count; };
-
-static void plan_rows(const int *refSel, int refSize, const int *outSel, int outSize, int nAtoms,
-                      std::vector<int> &remap, std::vector<RowRun> &runs, int &nRows)
-{
-    std::vector<unsigned char> used((size_t)nAtoms, 0);
-    for (int i = 0; i < refSize; ++i) used[refSel[i]] = 1;
-    for (int i = 0; i < outSize; ++i) used[outSel[i]] = 1;
-    std::vector<int> rows;
-    for (int a = 0; a < nAtoms; ++a) if (used[a]) rows.push_back(a);
-    runs.clear();
-    size_t i = 0;
-    while (i < rows.size()) {
-        size_t j = i + 1;
-        int stride = 1;
-        if (j < rows.size()) {
-            stride = rows[j] - rows[i];
-            while (j + 1 < rows.size() && rows[j + 1] - rows[j] == stride) ++j;
-            ++j;
-        }
-        runs.push_back({(int)i, rows[i], stride, (int)(j - i)});
-        i = j;
-    }
-    if (runs.size() > 512 && !rows.empty()) {              // scattered selection: copy the covering range
-        const int lo = rows.front(), hi = rows.back();
-        rows.clear();
-        for (int a = lo; a <= hi; ++a) rows.push_back(a);
-        runs.assign(1, RowRun{0, lo, 1, hi - lo + 1});
-    }
-    remap.assign((size_t)nAtoms, -1);
-    for (size_t r = 0; r < rows.size(); ++r) remap[rows[r]] = (int)r;
-    nRows = (int)rows.size();
 }
 
 int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *refSel, int refSize,
@@ -741,19 +896,16 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
     for (int i = 0; i < outSelSize; ++i) out2[i] = remap[outSel[i]];
 
     // ---- frame chunks: copy of chunk k+1 overlaps pack + kernel of chunk k (two raw buffers)
-    const size_t rowBytesPerFrame = (size_t)nRows * 12;
-    int nChunks = (int)std::min<size_t>(6, std::max<size_t>(1, rowBytesPerFrame * nFc / ((size_t)24 << 20)));
-    int chunk = (nFc + nChunks - 1) / nChunks;
-    const int maxChunk = (int)std::max<size_t>(1, ((size_t)3 << 30) / std::max<size_t>(rowBytesPerFrame, 1));
-    chunk = std::max(1, std::min(chunk, maxChunk));
-    nChunks = (nFc + chunk - 1) / chunk;
+    Uploader up(*c, nF, fb, fe);
+    up.add(allAtoms, nRows, runs);
+    rc = up.begin(8, "NDA_WITHIN_CHUNKS");
+    if (rc) return rc;
+    const int chunk = up.chunk, nChunks = up.nChunks;
 
     CK(c->cell.reserve((size_t)nF * 12));
     CK(c->idx1.reserve((size_t)std::max(refSize, 1) * 4));
     CK(c->idx2.reserve((size_t)outSelSize * 4));
     CK(c->bits.reserve((size_t)nFc * words * 4));
-    CK(c->raw1.reserve(rowBytesPerFrame * chunk));
-    if (nChunks > 1) CK(c->raw2.reserve(rowBytesPerFrame * chunk));
     CK(c->pinned_reserve((size_t)nFc * words * 4));
     uint32_t *hbits = reinterpret_cast<uint32_t *>(c->pinned);
 
@@ -762,8 +914,6 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
     if (refSize) CK(cudaMemcpyAsync(c->idx1.p, ref2.data(), (size_t)refSize * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->idx2.p, out2.data(), (size_t)outSelSize * 4, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(c->ev0, st));
-    CK(cudaEventRecord(c->evDone[0], st));                  // both raw buffers start out free
-    CK(cudaEventRecord(c->evDone[1], st));
 
     auto scatter = [&](int k) {                             // host: set the 1s of chunk k
         if (!out) return;
@@ -781,37 +931,23 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
         }
     };
 
+    rc = up.issue(0);
+    if (rc) return rc;
     for (int k = 0; k < nChunks; ++k) {
-        const int f0 = fb + k * chunk, f1 = std::min(fe, f0 + chunk), wc = f1 - f0, buf = k & 1;
-        float *raw = buf ? c->raw2.as<float>() : c->raw1.as<float>();
-        // copy stream: wait until the kernel that last read this buffer is done, then upload
-        CK(cudaStreamWaitEvent(c->copyStream, c->evDone[buf], 0));
-        for (const RowRun &r : runs) {
-            const size_t w = (size_t)wc * 12;
-            if ((size_t)r.stride * nF * 12 > ((size_t)1 << 30) && r.count > 1) {
-                for (int q = 0; q < r.count; ++q)              // pitch beyond cudaMemcpy2D's limit: row by row
-                    CK(cudaMemcpyAsync(raw + (size_t)(r.dstRow + q) * wc * 3,
-                                       allAtoms + ((size_t)(r.srcRow + (size_t)q * r.stride) * nF + f0) * 3, w,
-                                       cudaMemcpyHostToDevice, c->copyStream));
-            } else if (r.count == 1 || (r.stride == 1 && wc == nF)) {
-                CK(cudaMemcpyAsync(raw + (size_t)r.dstRow * wc * 3, allAtoms + ((size_t)r.srcRow * nF + f0) * 3,
-                                   r.count == 1 ? w : w * r.count, cudaMemcpyHostToDevice, c->copyStream));
-            } else {
-                CK(cudaMemcpy2DAsync(raw + (size_t)r.dstRow * wc * 3, w, allAtoms + ((size_t)r.srcRow * nF + f0) * 3,
-                                     (size_t)r.stride * nF * 12, w, (size_t)r.count, cudaMemcpyHostToDevice, c->copyStream));
-            }
-        }
-        CK(cudaEventRecord(c->evCopied[buf], c->copyStream));
-        CK(cudaStreamWaitEvent(st, c->evCopied[buf], 0));
-        rc = dev_within(*c, st, raw, nRows, wc, c->idx1.as<int>(), refSize, c->idx2.as<int>(), outSelSize,
+        const int f0 = up.f0(k), wc = up.f1(k) - f0, buf = k & 1;
+        rc = up.acquire(k);
+        if (rc) return rc;
+        rc = dev_within(*c, st, up.dev(0, k), nRows, wc, c->idx1.as<int>(), refSize, c->idx2.as<int>(), outSelSize,
                         c->bits.as<unsigned>() + (size_t)(f0 - fb) * words, nullptr,
                         c->cell.as<float>() + (size_t)f0 * 3, distance, 0, wc);
         if (rc) return rc;
-        CK(cudaEventRecord(c->evDone[buf], st));
+        rc = up.release(k);
+        if (rc) return rc;
         CK(cudaMemcpyAsync(hbits + (size_t)(f0 - fb) * words, c->bits.as<unsigned>() + (size_t)(f0 - fb) * words,
                            (size_t)wc * words * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(c->evBits[buf], st));
-        if (k > 0) {                                         // host scatters chunk k-1 while the GPU works on k
+        if (k + 1 < nChunks) { rc = up.issue(k + 1); if (rc) return rc; }   // host gathers k+1 while the GPU works on k
+        if (k > 0) {                                         // ... and scatters chunk k-1
             CK(cudaEventSynchronize(c->evBits[buf ^ 1]));
             scatter(k - 1);
         }
