@@ -258,6 +258,7 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
     a.nBTiles = (n2 + PAIR_BTILE - 1) / PAIR_BTILE;
     a.counts = d_counts; a.nBins = nBins; a.nGroups = nGroups; a.histCopies = copies;
     a.sameSel = sameSel ? 1 : 0; a.dr = dr;
+    a.fastStrict = getenv("NDA_STRICT_SLOW") ? 0 : 1;
     a.workCounter = work; a.stats = stats;
 
     int ctasPerSM = 0;

@@ -12,6 +12,7 @@ sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(_
 from namdanalyzer_b200 import synth, _capi  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
+WITHIN_FRAMES = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 lib = _capi.load()
 dev = torch.device("cuda", 0)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -24,7 +25,7 @@ def ms():
 
 
 if what in ("within", "all"):
-    nF = 200
+    nF = WITHIN_FRAMES
     c = synth.config2(n_frames=nF)
     xyz = torch.from_numpy(c["allAtoms"]).to(dev)
     cell = torch.from_numpy(c["cellDims"]).to(dev)
