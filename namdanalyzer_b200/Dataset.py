@@ -153,10 +153,15 @@ class ArrayDataset(PairOps):
         out_mask = self._static(out_terms[-1]) if out_terms else np.ones(self.nbrAtoms, bool)
         rest_mask = self._static(" and ".join(out_terms[:-1])) if len(out_terms) > 1 else np.ones(self.nbrAtoms, bool)
         ref_idx = np.flatnonzero(self._static(ref_txt.strip()))
-        keep = self.getWithin(float(dist_txt), ref_idx, np.flatnonzero(out_mask), frame)
-        if keep.ndim == 1:                                # one frame: index vector
-            return Selection(self, np.intersect1d(keep, np.flatnonzero(rest_mask)), frame)
-        # several frames: one index array per frame (selParser.py:117-126), from the 0/1 matrix
-        rest = np.flatnonzero(rest_mask)
-        per_frame = [np.intersect1d(np.flatnonzero(keep[:, k]), rest) for k in range(keep.shape[1])]
+        out_idx = np.flatnonzero(out_mask & rest_mask).astype(np.int32)   # ascending -> lists come out sorted
+        if np.ndim(frame) == 0:                           # one frame: index vector
+            keep = self.getWithin(float(dist_txt), ref_idx, out_idx, frame)
+            return Selection(self, keep, frame)
+        # several frames: one index array per frame (selParser.py:117-126), decoded from the bitmask
+        # in one pass instead of nFrames x (argwhere + intersect1d)
+        from .lib.pylibFuncs import py_getWithinLists
+        frames = np.asarray(frame)
+        xyz = np.ascontiguousarray(self.dcdData[:, frames], dtype=np.float32)
+        off, atoms = py_getWithinLists(xyz, ref_idx.astype(np.int32), out_idx, self.cellDims[frames], float(dist_txt))
+        per_frame = [atoms[off[k]:off[k + 1]] for k in range(frames.size)]
         return Selection(self, per_frame, frame)

@@ -26,7 +26,7 @@ from .._capi import c_f32p, c_f64p, c_i32p, c_u32p, c_u64p
 
 __all__ = ["py_getWithin", "py_getDistances", "py_getRadialNbrDensity", "py_getParallelBackend",
            "py_getRadialNbrDensityGrouped", "py_getRadialNbrCounts", "py_getDistancesSum",
-           "py_getWithinBits"]
+           "py_getWithinBits", "py_getWithinLists"]
 
 _CNAME = {np.dtype(np.float32): "float", np.dtype(np.float64): "double", np.dtype(np.int32): "int",
           np.dtype(np.int64): "long", np.dtype(np.uint64): "unsigned long", np.dtype(np.uint32): "unsigned int"}
@@ -206,3 +206,22 @@ def py_getWithinBits(allAtoms, refSel, outSel, cellDims, distance, frameBegin=0,
                                       _p(outSel, c_i32p), outSel.size, _p(bits, c_u32p), None,
                                       _p(cell, c_f32p), float(distance), int(frameBegin), frameEnd))
     return bits
+
+
+def py_getWithinLists(allAtoms, refSel, outSel, cellDims, distance, frameBegin=0, frameEnd=None):
+    """Per-frame lists of the outSel atoms within ``distance`` of refSel, in CSR form:
+    ``(offsets int64 (nFrames+1,), atoms int32 (total,))`` with frame f's atoms at
+    ``atoms[offsets[f]:offsets[f+1]]`` in outSel order.  This is what the reference's multi-frame
+    selection loop builds one frame at a time with np.argwhere on the int32 matrix
+    (NAMDAnalyzer/selection/selParser.py:117-126); here it is decoded from the bitmask in one
+    vectorised pass."""
+    outSel = _buf(outSel, "outSel", np.int32, 1)
+    bits = py_getWithinBits(allAtoms, refSel, outSel, cellDims, distance, frameBegin, frameEnd)
+    nFc = bits.shape[0]
+    if nFc == 0 or outSel.size == 0:
+        return np.zeros(nFc + 1, np.int64), np.zeros(0, np.int32)
+    flags = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :outSel.size]
+    f_idx, a_idx = np.nonzero(flags)                       # row-major: sorted by frame, then outSel order
+    offsets = np.zeros(nFc + 1, np.int64)
+    np.cumsum(np.bincount(f_idx, minlength=nFc), out=offsets[1:])
+    return offsets, outSel[a_idx]

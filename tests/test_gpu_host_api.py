@@ -138,3 +138,13 @@ def _nccl_worker(rank, world, port_no, q):
             q.put(counts)
     finally:
         dist.destroy_process_group()
+
+
+def test_within_lists_csr_matches_mask():
+    from namdanalyzer_b200.lib import pylibFuncs as plf
+    c = synth.config2(n_frames=7, n_water=1200)
+    off, atoms = plf.py_getWithinLists(c["allAtoms"], c["refSel"], c["outSel"], c["cellDims"], 3.5)
+    want = port.within(c["allAtoms"], c["refSel"], c["outSel"], c["cellDims"], 3.5)
+    assert off.shape == (8,) and off[0] == 0 and off[-1] == atoms.size == want.sum()
+    for f in range(7):
+        assert np.array_equal(atoms[off[f]:off[f + 1]], np.flatnonzero(want[:, f]))
