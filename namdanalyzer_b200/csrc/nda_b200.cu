@@ -76,7 +76,8 @@ struct Ctx {
     bool ready = false;
     int numSMs = 0;
     size_t smemOptin = 0;
-    cudaStream_t stream = nullptr, copyStream = nullptr;
+    cudaStream_t stream = nullptr, copyStream = nullptr, copyStream2 = nullptr;
+    cudaEvent_t evJoin = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t evCopied[2] = {nullptr, nullptr}, evDone[2] = {nullptr, nullptr}, evBits[2] = {nullptr, nullptr};
     void *pinned = nullptr;                       // pinned host staging for small results
@@ -144,6 +145,8 @@ static int ctx_get(Ctx **out)
         c.smemOptin = prop.sharedMemPerBlockOptin;
         CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c.copyStream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming));
         CK(cudaEventCreate(&c.ev0));
         CK(cudaEventCreate(&c.ev1));
         for (int i = 0; i < 2; ++i) {
@@ -578,6 +581,10 @@ struct Uploader {
             }
         }
         CK(cudaStreamWaitEvent(c.copyStream, c.evDone[b], 0));             // device buffer b is free again
+        // strided 2-D DMA from pinned memory runs at about half the link rate on one copy engine,
+        // so the rows of every run are split over two copy streams (NDA_COPY_STREAMS=1 disables)
+        static const bool twoStreams = !(getenv("NDA_COPY_STREAMS") && atoi(getenv("NDA_COPY_STREAMS")) == 1);
+        bool usedSecond = false;
         for (size_t i = 0; i < arr.size(); ++i) {
             UploadArray &a = arr[i];
             if (a.nRows == 0) continue;
@@ -587,20 +594,38 @@ struct Uploader {
                                    cudaMemcpyHostToDevice, c.copyStream));
                 continue;
             }
-            for (const RowRun &r : a.runs) {
-                const float *src = a.host + ((size_t)r.srcRow * nF + a0) * 3;
-                float *dst = raw + (size_t)r.dstRow * wc * 3;
-                if (r.count == 1 || (r.stride == 1 && wc == nF)) {
-                    CK(cudaMemcpyAsync(dst, src, w * r.count, cudaMemcpyHostToDevice, c.copyStream));
-                } else if ((size_t)r.stride * nF * 12 > ((size_t)1 << 30)) {
-                    for (int q = 0; q < r.count; ++q)              // pitch beyond the 2-D copy limit: row by row
-                        CK(cudaMemcpyAsync(dst + (size_t)q * wc * 3, src + (size_t)q * r.stride * nF * 3, w,
-                                           cudaMemcpyHostToDevice, c.copyStream));
-                } else {
-                    CK(cudaMemcpy2DAsync(dst, w, src, (size_t)r.stride * nF * 12, w, (size_t)r.count,
-                                         cudaMemcpyHostToDevice, c.copyStream));
+            for (const RowRun &r0 : a.runs) {
+                RowRun part[2] = {r0, r0};
+                int nPart = 1;
+                if (twoStreams && r0.count >= 64) {
+                    part[0].count = r0.count / 2;
+                    part[1].dstRow = r0.dstRow + part[0].count;
+                    part[1].srcRow = r0.srcRow + part[0].count * r0.stride;
+                    part[1].count = r0.count - part[0].count;
+                    nPart = 2;
+                }
+                for (int h = 0; h < nPart; ++h) {
+                    const RowRun &r = part[h];
+                    cudaStream_t cs = h ? c.copyStream2 : c.copyStream;
+                    if (h && !usedSecond) { CK(cudaStreamWaitEvent(c.copyStream2, c.evDone[b], 0)); usedSecond = true; }
+                    const float *src = a.host + ((size_t)r.srcRow * nF + a0) * 3;
+                    float *dst = raw + (size_t)r.dstRow * wc * 3;
+                    if (r.count == 1 || (r.stride == 1 && wc == nF)) {
+                        CK(cudaMemcpyAsync(dst, src, w * r.count, cudaMemcpyHostToDevice, cs));
+                    } else if ((size_t)r.stride * nF * 12 > ((size_t)1 << 30)) {
+                        for (int q = 0; q < r.count; ++q)          // pitch beyond the 2-D copy limit: row by row
+                            CK(cudaMemcpyAsync(dst + (size_t)q * wc * 3, src + (size_t)q * r.stride * nF * 3, w,
+                                               cudaMemcpyHostToDevice, cs));
+                    } else {
+                        CK(cudaMemcpy2DAsync(dst, w, src, (size_t)r.stride * nF * 12, w, (size_t)r.count,
+                                             cudaMemcpyHostToDevice, cs));
+                    }
                 }
             }
+        }
+        if (usedSecond) {
+            CK(cudaEventRecord(c.evJoin, c.copyStream2));
+            CK(cudaStreamWaitEvent(c.copyStream, c.evJoin, 0));
         }
         CK(cudaEventRecord(c.evCopied[b], c.copyStream));
         return NDA_OK;
@@ -919,6 +944,8 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
     auto scatter = [&](int k) {                             // host: set the 1s of chunk k
         if (!out) return;
         const int f0 = k * chunk, f1 = std::min(nFc, f0 + chunk);
+        // ~6e5 cache-missing stores for config 2: spread the frames over the host threads
+        #pragma omp parallel for schedule(static) num_threads(g_host_threads) if (f1 - f0 >= 16)
         for (int f = f0; f < f1; ++f) {
             const uint32_t *row = hbits + (size_t)f * words;
             for (int w = 0; w < words; ++w) {

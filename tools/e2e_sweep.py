@@ -14,14 +14,20 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         xyz = xyz.pin_memory()
     xyz = xyz.numpy()
     out = np.zeros(xyz.shape[:2], np.int32)
+    bits_only = os.environ.get("BITS", "0") == "1"
+    def call():
+        if bits_only:
+            plf.py_getWithinBits(xyz, c["refSel"], c["outSel"], c["cellDims"], 3.0)
+        else:
+            plf.py_getWithin(xyz, c["refSel"], c["outSel"], out, c["cellDims"], 3.0)
     for _ in range(3):
-        plf.py_getWithin(xyz, c["refSel"], c["outSel"], out, c["cellDims"], 3.0)
+        call()
     t0 = time.perf_counter()
     n = 10
     for _ in range(n):
-        plf.py_getWithin(xyz, c["refSel"], c["outSel"], out, c["cellDims"], 3.0)
+        call()
     dt = (time.perf_counter() - t0) / n
-    print("chunks=%s pinned=%d: %.2f ms/call, %.3e pairs/s" % (os.environ.get("NDA_WITHIN_CHUNKS", "auto"), pin, dt * 1e3, 1231 * 7923 * 1000 / dt))
+    print("bits_only=%d chunks=%s pinned=%d: %.2f ms/call, %.3e pairs/s" % (bits_only, os.environ.get("NDA_WITHIN_CHUNKS", "auto"), pin, dt * 1e3, 1231 * 7923 * 1000 / dt))
 else:
     for pin in ("1", "0"):
         for ch in ("1", "2", "4", "6", "8", "12", "16"):
