@@ -55,6 +55,21 @@ if what in ("rdf", "all"):
     st4 = (ctypes.c_double * 4)()
     print("rdf: %.3f ms, %.3e pairs/s, in-range %d" % (t, pairs / t * 1e3, int(counts.sum().item())))
 
+if what in ("rdf3",):
+    nF = 60
+    c = synth.config3(n_frames=nF)
+    w_, p_ = torch.from_numpy(c["waters"]).to(dev), torch.from_numpy(c["protein"]).to(dev)
+    gid = torch.from_numpy(c["groupId"]).to(dev)
+    cell = torch.from_numpy(c["cellDims"]).to(dev)
+    counts = torch.zeros((76, 149), dtype=torch.int64, device=dev)
+    for _ in range(2):
+        counts.zero_()
+        _capi.check(lib.nda_dev_radial_nbr_counts(w_.data_ptr(), w_.shape[0], p_.data_ptr(), p_.shape[0], gid.data_ptr(), 76,
+                                                  counts.data_ptr(), 149, cell.data_ptr(), nF, 0, nF, 0, 0.1, st))
+        t = ms()
+    pairs = 20000.0 * 1231 * nF
+    print("rdf3 (grouped, config 3): %.3f ms, %.3e pairs/s, in-range %d" % (t, pairs / t * 1e3, int(counts.sum().item())))
+
 if what in ("dist", "all"):
     nF = 2000
     c = synth.config4(n_frames=nF)
