@@ -384,3 +384,40 @@ def test_device_api_frame_ranges_match_whole():
     torch.cuda.synchronize()
     w = port.distances_sum(c["sel1"][:10], c["sel1"], c["cellDims"], 0)
     assert np.max(np.abs(s.cpu().numpy() - w) / np.maximum(w, 1e-30)) <= 1e-12
+
+
+def test_full_size_config3_grouped_rows_sum_to_ungrouped():
+    """BASELINE config 3 shape (20 000 waters x 1231 protein atoms, 76 residues) on 100 frames:
+    the grouped histogram's rows add up to the ungrouped histogram (a checksum of checksums), rows
+    of single residues equal call-by-call results, and a sampled frame equals the oracle."""
+    c = synth.config3(n_frames=100)
+    g = rdf_counts(c["waters"], c["protein"], c["cellDims"], 0, NB, 0.1, groupId=c["groupId"], nGroups=c["nGroups"])
+    u = rdf_counts(c["waters"], c["protein"], c["cellDims"], 0, NB, 0.1)
+    assert g.shape == (76, NB) and np.array_equal(g.sum(0), u)
+    for r in (3, 50):
+        sel = np.ascontiguousarray(c["protein"][c["groupId"] == r])
+        assert np.array_equal(rdf_counts(c["waters"], sel, c["cellDims"], 0, NB, 0.1), g[r])
+    f = 57
+    w1, p1 = np.ascontiguousarray(c["waters"][:, f:f + 1]), np.ascontiguousarray(c["protein"][:, f:f + 1])
+    want = port.rdf_counts(w1, p1, c["cellDims"][f:f + 1], 0, NB, 0.1, groupId=c["groupId"], nGroups=76).astype(np.int64)
+    got = rdf_counts(c["waters"], c["protein"], c["cellDims"], 0, NB, 0.1, groupId=c["groupId"], nGroups=76,
+                     frameBegin=f, frameEnd=f + 1)
+    assert np.array_equal(got, want)
+
+
+def test_full_size_config4_mean_is_linear_in_frames():
+    """BASELINE config 4 at full size (7 x 1231, 10 000 frames): the mean over all frames equals the
+    frame-weighted mean of the means of two halves (linearity), and a sampled block of frames
+    equals the oracle to float64 round-off."""
+    c = synth.config4(n_frames=10000)
+    out = np.zeros((7, 1231), np.float32)
+    plf.py_getDistances(c["sel1"], c["sel2"], out, c["cellDims"], 0)
+    s = plf.py_getDistancesSum(c["sel1"], c["sel2"], c["cellDims"], 0)
+    s1 = plf.py_getDistancesSum(c["sel1"], c["sel2"], c["cellDims"], 0, 0, 4321)
+    s2 = plf.py_getDistancesSum(c["sel1"], c["sel2"], c["cellDims"], 0, 4321, 10000)
+    assert np.max(np.abs(s - (s1 + s2)) / np.maximum(s, 1e-30)) < 1e-13
+    assert np.max(np.abs(out - s / 10000) / np.maximum(s / 10000, 1e-30)) <= REL_TOL
+    blk = slice(7000, 7040)
+    w = port.distances_sum(c["sel1"][:, blk], c["sel2"][:, blk], c["cellDims"][blk], 0)
+    g = plf.py_getDistancesSum(c["sel1"], c["sel2"], c["cellDims"], 0, 7000, 7040)
+    assert np.max(np.abs(g - w) / np.maximum(w, 1e-30)) <= 1e-12
