@@ -411,7 +411,8 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
         }
     }
     if (d_out) {
-        dim3 grid((fe - fb + 255) / 256, outSize);
+        if ((fe - fb + 255) / 256 > 65535) return fail(NDA_ERR_ARG, "frame range too large for the mask expansion");
+        dim3 grid(outSize, (fe - fb + 255) / 256);
         expand_mask_kernel<<<grid, 256, 0, st>>>(d_bits, words, d_outSel, outSize, nF, fb, fe - fb, d_out);
         LAUNCHED();
     }
@@ -869,7 +870,7 @@ int nda_get_distances_sum(const float *sel1, int n1, const float *sel2, int n2, 
         if (k + 1 < up.nChunks) { rc = up.issue(k + 1); if (rc) return rc; }
     }
     if (sameSel) {
-        dim3 grid((n1 + 255) / 256, n1);
+        dim3 grid((n1 + 255) / 256, std::min(n1, 4096));
         symmetrize_kernel<<<grid, 256, 0, st>>>(c->sum.as<double>(), n1);
         LAUNCHED();
     }

@@ -421,3 +421,40 @@ def test_full_size_config4_mean_is_linear_in_frames():
     w = port.distances_sum(c["sel1"][:, blk], c["sel2"][:, blk], c["cellDims"][blk], 0)
     g = plf.py_getDistancesSum(c["sel1"], c["sel2"], c["cellDims"], 0, 7000, 7040)
     assert np.max(np.abs(g - w) / np.maximum(w, 1e-30)) <= 1e-12
+
+
+def test_large_out_selection_and_mask_expansion():
+    """more than 65535 outSel atoms (grid-dimension limits) through the device mask expansion"""
+    import torch
+    from namdanalyzer_b200 import _capi
+    L = _capi.load()
+    c = synth.config5(n_side=42, n_frames=2)                          # 74 088 atoms
+    n, nF = c["sel1"].shape[:2]
+    xyz = torch.from_numpy(c["sel1"]).cuda()
+    cell = torch.from_numpy(c["cellDims"]).cuda()
+    refSel = torch.arange(0, 150, dtype=torch.int32, device="cuda")
+    outSel = torch.arange(0, n, dtype=torch.int32, device="cuda")
+    bits = torch.zeros((nF, (n + 31) // 32), dtype=torch.int32, device="cuda")
+    out = torch.zeros((n, nF), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _capi.check(L.nda_dev_within(xyz.data_ptr(), n, nF, refSel.data_ptr(), 150, outSel.data_ptr(), n,
+                                 bits.data_ptr(), out.data_ptr(), cell.data_ptr(), 4.0, 0, nF, st))
+    torch.cuda.synchronize()
+    want = port.within(c["sel1"], refSel.cpu().numpy(), outSel.cpu().numpy(), c["cellDims"], 4.0)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_c_abi_errors_raise_runtime_error():
+    xyz = np.zeros((10, 2, 3), np.float32)
+    cell = np.ones((2, 3), np.float32)
+    with pytest.raises(RuntimeError, match="groupId"):
+        plf.py_getRadialNbrCounts(xyz, xyz, cell, 0, 10, 0.1, groupId=np.full(10, 7, np.int32), nGroups=3)
+    with pytest.raises(RuntimeError, match="sameSel"):
+        plf.py_getRadialNbrCounts(xyz, xyz[:5].copy(), cell, 1, 10, 0.1)
+    with pytest.raises(RuntimeError, match="shared memory"):
+        plf.py_getRadialNbrCounts(xyz, xyz, cell, 0, 60000, 0.1)     # 60000 bins x u32 > 227 KB
+    out = np.zeros((10, 2), np.int32)
+    with pytest.raises(RuntimeError, match="outside"):
+        plf.py_getWithin(xyz, np.array([11], np.int32), np.array([0], np.int32), out, cell, 1.0)
+    # the library is still usable after an error
+    assert plf.py_getRadialNbrCounts(xyz, xyz, cell, 1, 10, 0.1).sum() == 45 * 2     # all coincident: bin 0
