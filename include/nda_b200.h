@@ -126,6 +126,21 @@ int nda_dev_distances_sum(const float *d_sel1, int sel1_size, const float *d_sel
                           double *d_sum, const float *d_cellDims, int nbrFrames,
                           int frameBegin, int frameEnd, int sameSel, void *stream);
 
+/* The same with the selections given as row indices into ONE resident all-atom array
+ * d_allAtoms float32 [nbrAtoms][nbrFrames][3]: upload a trajectory once, query it many times
+ * (B200: 180 GB of HBM holds whole trajectories).  d_groupId has one entry per idx2 entry.
+ * sameSel != 0 requires d_idx2 == d_idx1. */
+int nda_dev_radial_nbr_counts_sel(const float *d_allAtoms, int nbrAtoms,
+                                  const int *d_idx1, int sel1_size, const int *d_idx2, int sel2_size,
+                                  const int *d_groupId, int nGroups,
+                                  unsigned long long *d_counts, int outSize,
+                                  const float *d_cellDims, int nbrFrames, int frameBegin, int frameEnd,
+                                  int sameSel, float dr, void *stream);
+int nda_dev_distances_sum_sel(const float *d_allAtoms, int nbrAtoms,
+                              const int *d_idx1, int sel1_size, const int *d_idx2, int sel2_size,
+                              double *d_sum, const float *d_cellDims, int nbrFrames,
+                              int frameBegin, int frameEnd, int sameSel, void *stream);
+
 /* ---- measurement / test support ---------------------------------------------------- */
 
 /* Config-5 generator (namdanalyzer_b200/synth.py water_box_frame, bit-identical): writes

@@ -42,6 +42,10 @@ SIGNATURES = {
                                c_void_p, c_float, c_int, c_int, c_void_p]),
     "nda_dev_distances_sum": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_void_p]),
+    "nda_dev_radial_nbr_counts_sel": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                              c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "nda_dev_distances_sum_sel": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                          c_int, c_int, c_int, c_void_p]),
     "nda_dev_synth_water_box": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                         ctypes.c_uint32, c_void_p]),
     "nda_measure_fp32_peak": (c_int, [c_int, c_f64p]),

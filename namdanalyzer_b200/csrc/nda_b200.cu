@@ -215,7 +215,8 @@ static int frames_per_pass(size_t bytesPerFrame, int nF)
 
 static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const float *d_sel2, int n2,
                    const int *d_gid, int nGroups, unsigned long long *d_counts, int nBins,
-                   const float *d_cell, int nF, int fb, int fe, int sameSel, float dr)
+                   const float *d_cell, int nF, int fb, int fe, int sameSel, float dr,
+                   const int *d_idx1 = nullptr, const int *d_idx2 = nullptr)   // optional row indices into d_sel1/2
 {
     if (n1 <= 0 || n2 <= 0 || fe <= fb || nBins <= 0) return NDA_OK;
     if (nGroups < 1) nGroups = 1;
@@ -289,11 +290,11 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
         const int nFc = std::min(pass, fe - f0);
         CK(cudaMemsetAsync(c.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
         CK(cudaMemsetAsync(work, 0, 8, st));
-        int rc = launch_pack(c, st, d_sel1, nF, nullptr, n1, n1Pad, f0, nFc, sameSel ? d_gid : nullptr,
+        int rc = launch_pack(c, st, d_sel1, nF, d_idx1, n1, n1Pad, f0, nFc, sameSel ? d_gid : nullptr,
                              c.packA.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packAw.as<float4>() : nullptr, pairLayout);
         if (rc) return rc;
         if (!sameSel) {
-            rc = launch_pack(c, st, d_sel2, nF, nullptr, n2, n2Pad, f0, nFc, d_gid,
+            rc = launch_pack(c, st, d_sel2, nF, d_idx2, n2, n2Pad, f0, nFc, d_gid,
                              c.packB.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packBw.as<float4>() : nullptr, pairLayout);
             if (rc) return rc;
         }
@@ -420,7 +421,8 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
 }
 
 static int dev_distances(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const float *d_sel2, int n2,
-                         double *d_sum, const float *d_cell, int nF, int fb, int fe, int sameSel)
+                         double *d_sum, const float *d_cell, int nF, int fb, int fe, int sameSel,
+                         const int *d_idx1 = nullptr, const int *d_idx2 = nullptr)
 {
     if (n1 <= 0 || n2 <= 0 || fe <= fb) return NDA_OK;
     const int chunks = (fe - fb + DIST_FCHUNK - 1) / DIST_FCHUNK;
@@ -428,7 +430,7 @@ static int dev_distances(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, c
     if (chunks > 65535 || zt > 65535) return fail(NDA_ERR_ARG, "selection or frame range too large for one launch");
     dim3 grid((n2 + 7) / 8, chunks, zt);
     CK(c.kev_record(st));
-    distances_kernel<<<grid, 256, 0, st>>>(d_sel1, n1, d_sel2, n2, d_cell, nF, fb, fe, sameSel ? 1 : 0, d_sum);
+    distances_kernel<<<grid, 256, 0, st>>>(d_sel1, n1, d_sel2, n2, d_cell, nF, fb, fe, sameSel ? 1 : 0, d_sum, d_idx1, d_idx2);
     LAUNCHED();
     CK(c.kev_record(st));
     return NDA_OK;
@@ -756,6 +758,41 @@ int nda_dev_distances_sum(const float *d_sel1, int n1, const float *d_sel2, int 
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     begin_call(*c);
     return dev_distances(*c, st, d_sel1, n1, d_sel2, n2, d_sum, d_cellDims, nF, fb, fe, sameSel);
+}
+
+// Selections given as row indices into ONE resident all-atom array (a trajectory uploaded once and
+// queried many times: ResidueWiseWaterDensity residue by residue, ResidenceTime per time origin, ...)
+int nda_dev_radial_nbr_counts_sel(const float *d_all, int nAtoms, const int *d_idx1, int n1, const int *d_idx2, int n2,
+                                  const int *d_groupId, int nGroups, unsigned long long *d_counts, int outSize,
+                                  const float *d_cellDims, int nF, int fb, int fe, int sameSel, float dr, void *stream)
+{
+    if (!d_all || !d_idx1 || !d_idx2 || !d_counts || !d_cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (nAtoms < 0 || n1 < 0 || n2 < 0 || outSize < 0 || nF < 0 || fb < 0 || fe > nF) return fail(NDA_ERR_ARG, "bad size / frame range");
+    if (sameSel && (d_idx1 != d_idx2 || n1 != n2)) return fail(NDA_ERR_ARG, "sameSel requires idx2 == idx1");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    begin_call(*c);
+    CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
+    return dev_rdf(*c, st, d_all, n1, d_all, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr,
+                   d_idx1, d_idx2);
+}
+
+int nda_dev_distances_sum_sel(const float *d_all, int nAtoms, const int *d_idx1, int n1, const int *d_idx2, int n2,
+                              double *d_sum, const float *d_cellDims, int nF, int fb, int fe, int sameSel, void *stream)
+{
+    if (!d_all || !d_idx1 || !d_idx2 || !d_sum || !d_cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (nAtoms < 0 || n1 < 0 || n2 < 0 || nF < 0 || fb < 0 || fe > nF) return fail(NDA_ERR_ARG, "bad size / frame range");
+    if (sameSel && n1 != n2) return fail(NDA_ERR_ARG, "sameSel requires idx2 == idx1");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    begin_call(*c);
+    return dev_distances(*c, st, d_all, n1, d_all, n2, d_sum, d_cellDims, nF, fb, fe, sameSel, d_idx1, d_idx2);
 }
 
 // ---- host entry points ---------------------------------------------------------------------

@@ -148,3 +148,38 @@ def test_within_lists_csr_matches_mask():
     assert off.shape == (8,) and off[0] == 0 and off[-1] == atoms.size == want.sum()
     for f in range(7):
         assert np.array_equal(atoms[off[f]:off[f + 1]], np.flatnonzero(want[:, f]))
+
+
+def test_resident_trajectory_matches_host_operators():
+    from namdanalyzer_b200.resident import ResidentTrajectory
+    from namdanalyzer_b200.lib import pylibFuncs as plf
+    c = synth.config2(n_frames=9, n_water=1500)
+    xyz, cell, r, o = c["allAtoms"], c["cellDims"], c["refSel"], c["outSel"]
+    T = ResidentTrajectory(xyz, cell)
+    want = port.within(xyz, r, o, cell, 3.5)
+    assert np.array_equal(T.within(r, o, 3.5), want)
+    assert np.array_equal(T.within(r, o, 3.5, frames=(2, 7)), want[:, 2:7])
+    # RDF between two index selections, grouped and plain, and a frame range
+    fx = synth.fixture()
+    gid = fx["protein_resindex"].astype(np.int32)
+    wO = o[:800]
+    cnt = T.radial_nbr_counts(wO, r, 149, 0.1, groupId=gid, nGroups=76)
+    w = port.rdf_counts(np.ascontiguousarray(xyz[wO]), np.ascontiguousarray(xyz[r]), cell, 0, 149, 0.1,
+                        groupId=gid, nGroups=76).astype(np.int64)
+    assert np.array_equal(cnt, w)
+    oo = T.radial_nbr_counts(wO, None, 149, 0.1, sameSel=1, frames=(1, 4))
+    a = np.ascontiguousarray(xyz[wO][:, 1:4])
+    assert np.array_equal(oo, port.rdf_counts(a, a, cell[1:4], 1, 149, 0.1).astype(np.int64))
+    dens = np.zeros(149, np.float32)
+    T.radial_nbr_density(wO, wO, dens, 1, 15.0, 0.1)
+    ref = np.zeros(149, np.float32)
+    aa = np.ascontiguousarray(xyz[wO])
+    plf.py_getRadialNbrDensity(aa, aa, ref, cell, 1, 15.0, 0.1)
+    assert np.array_equal(dens, ref)
+    # distances between index selections
+    d = T.distances(r[:12], r)
+    w = port.distances_sum(np.ascontiguousarray(xyz[r[:12]]), np.ascontiguousarray(xyz[r]), cell, 0) / 9
+    assert np.max(np.abs(d - w) / np.maximum(w, 1e-30)) <= 1e-6
+    ds = T.distances(r[:12])
+    assert np.array_equal(ds, ds.T) and np.all(np.diag(ds) == 0)
+    assert np.max(np.abs(ds - d[:, :12]) / np.maximum(d[:, :12], 1e-30)) <= 1e-6
