@@ -90,7 +90,12 @@ struct Ctx {
         if (e == cudaSuccess) pinnedCap = bytes + bytes / 4 + 4096;
         return e;
     }
-    DevBuf packA, packB, packAw, packBw, fp, maxAbs, ctl;        // ctl: [0..1] work counter (u32 x2), stats u64 at +16
+    // two LANES = two compute streams with their own pass buffers: consecutive frame chunks of the
+    // host entry points run on alternating lanes so the head of chunk k+1's persistent kernel fills
+    // the tail of chunk k's.  ctl: [0..1] work counter (u32 x2), stats u64 x2 at +16.
+    struct Lane { DevBuf packA, packB, packAw, packBw, fp, maxAbs, ctl; cudaStream_t stream = nullptr; };
+    Lane lane[2];
+    cudaEvent_t evSetup = nullptr, evLaneJoin = nullptr;
     DevBuf raw[2][2];                             // [array][double buffer] raw coordinate chunks
     DevBuf cell, idx1, idx2, gid, counts, bits, sum;
     void *stage[2] = {nullptr, nullptr};          // pinned staging for pageable inputs
@@ -144,6 +149,10 @@ static int ctx_get(Ctx **out)
         c.numSMs = prop.multiProcessorCount;
         c.smemOptin = prop.sharedMemPerBlockOptin;
         CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        c.lane[0].stream = c.stream;
+        CK(cudaStreamCreateWithFlags(&c.lane[1].stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c.evSetup, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.evLaneJoin, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.copyStream2, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming));
@@ -154,7 +163,10 @@ static int ctx_get(Ctx **out)
             CK(cudaEventCreateWithFlags(&c.evDone[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c.evBits[i], cudaEventDisableTiming));
         }
-        CK(c.ctl.reserve(256));
+        CK(c.lane[0].ctl.reserve(256));
+        CK(c.lane[1].ctl.reserve(256));
+        CK(cudaMemset(c.lane[0].ctl.p, 0, 256));
+        CK(cudaMemset(c.lane[1].ctl.p, 0, 256));
         {
             unsigned hw = std::thread::hardware_concurrency();
             int t = (int)std::max(1u, std::min(8u, hw / 2));
@@ -168,6 +180,7 @@ static int ctx_get(Ctx **out)
 }
 
 static inline void begin_call(Ctx &c) { c.kevUsed = 0; }
+static cudaError_t reset_stats(Ctx &c, cudaStream_t st);
 
 // tuning override for experiments: NDA_CTAS_PER_SM=<n> caps the persistent grid at n CTAs per SM
 static int tuned_ctas(int occ)
@@ -213,7 +226,7 @@ static int frames_per_pass(size_t bytesPerFrame, int nF)
     return (int)f;
 }
 
-static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const float *d_sel2, int n2,
+static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, int n1, const float *d_sel2, int n2,
                    const int *d_gid, int nGroups, unsigned long long *d_counts, int nBins,
                    const float *d_cell, int nF, int fb, int fe, int sameSel, float dr,
                    const int *d_idx1 = nullptr, const int *d_idx2 = nullptr)   // optional row indices into d_sel1/2
@@ -240,21 +253,21 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
     const size_t bytesPerFrame = ((size_t)n1Pad + (sameSel ? 0 : (size_t)n2Pad)) * sizeof(float4) * (fold ? 2 : 1);
     const int pass = frames_per_pass(bytesPerFrame, fe - fb);
 
-    CK(c.packA.reserve((size_t)n1Pad * pass * sizeof(float4)));
-    if (!sameSel) CK(c.packB.reserve((size_t)n2Pad * pass * sizeof(float4)));
+    CK(L.packA.reserve((size_t)n1Pad * pass * sizeof(float4)));
+    if (!sameSel) CK(L.packB.reserve((size_t)n2Pad * pass * sizeof(float4)));
     if (fold) {
-        CK(c.packAw.reserve((size_t)n1Pad * pass * sizeof(float4)));
-        if (!sameSel) CK(c.packBw.reserve((size_t)n2Pad * pass * sizeof(float4)));
+        CK(L.packAw.reserve((size_t)n1Pad * pass * sizeof(float4)));
+        if (!sameSel) CK(L.packBw.reserve((size_t)n2Pad * pass * sizeof(float4)));
     }
-    CK(c.fp.reserve((size_t)pass * sizeof(FrameParams)));
-    CK(c.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
+    CK(L.fp.reserve((size_t)pass * sizeof(FrameParams)));
+    CK(L.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
 
     const double drd = (double)dr;
     const double lim = (double)nBins * fabs(drd);
     const double T = lim * lim * (1.0 + 9.5367431640625e-07);       // (nBins*dr)^2 (1 + 2^-20)
 
-    unsigned *work = c.ctl.as<unsigned>();
-    unsigned long long *stats = reinterpret_cast<unsigned long long *>(c.ctl.as<unsigned char>() + 16);
+    unsigned *work = L.ctl.as<unsigned>();
+    unsigned long long *stats = reinterpret_cast<unsigned long long *>(L.ctl.as<unsigned char>() + 16);
 
     RdfArgs a;
     a.n1 = n1; a.n1Pad = n1Pad; a.n2 = n2; a.n2Pad = n2Pad;
@@ -288,24 +301,24 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
 
     for (int f0 = fb; f0 < fe; f0 += pass) {
         const int nFc = std::min(pass, fe - f0);
-        CK(cudaMemsetAsync(c.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
+        CK(cudaMemsetAsync(L.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
         CK(cudaMemsetAsync(work, 0, 8, st));
         int rc = launch_pack(c, st, d_sel1, nF, d_idx1, n1, n1Pad, f0, nFc, sameSel ? d_gid : nullptr,
-                             c.packA.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packAw.as<float4>() : nullptr, pairLayout);
+                             L.packA.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, fold ? L.packAw.as<float4>() : nullptr, pairLayout);
         if (rc) return rc;
         if (!sameSel) {
             rc = launch_pack(c, st, d_sel2, nF, d_idx2, n2, n2Pad, f0, nFc, d_gid,
-                             c.packB.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packBw.as<float4>() : nullptr, pairLayout);
+                             L.packB.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, fold ? L.packBw.as<float4>() : nullptr, pairLayout);
             if (rc) return rc;
         }
-        prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, c.maxAbs.as<unsigned>(), T,
-                                                             c.fp.as<FrameParams>(), stats);
+        prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
+                                                             L.fp.as<FrameParams>(), stats);
         LAUNCHED();
-        a.A = c.packA.as<float4>();
-        a.B = sameSel ? a.A : c.packB.as<float4>();
-        a.Aw = fold ? c.packAw.as<float4>() : a.A;
-        a.Bw = fold ? (sameSel ? a.Aw : c.packBw.as<float4>()) : a.B;
-        a.fp = c.fp.as<FrameParams>();
+        a.A = L.packA.as<float4>();
+        a.B = sameSel ? a.A : L.packB.as<float4>();
+        a.Aw = fold ? L.packAw.as<float4>() : a.A;
+        a.Bw = fold ? (sameSel ? a.Aw : L.packBw.as<float4>()) : a.B;
+        a.fp = L.fp.as<FrameParams>();
         const unsigned long long items = (unsigned long long)nFc * a.nATiles * a.nBChunks;
         if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
         a.nItems = (unsigned)items;
@@ -321,7 +334,7 @@ static int dev_rdf(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, const f
     return NDA_OK;
 }
 
-static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, int nF,
+static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all, int nAtoms, int nF,
                       const int *d_refSel, int refSize, const int *d_outSel, int outSize,
                       unsigned *d_bits, int *d_out, const float *d_cell, float distance, int fb, int fe)
 {
@@ -338,16 +351,16 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
         const int pairLayout = is_fold2(filter) ? 1 : 0;
         const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * sizeof(float4) * (fold ? 2 : 1);
         const int pass = frames_per_pass(bytesPerFrame, fe - fb);
-        CK(c.packA.reserve((size_t)nAPad * pass * sizeof(float4)));
-        CK(c.packB.reserve((size_t)nBPad * pass * sizeof(float4)));
+        CK(L.packA.reserve((size_t)nAPad * pass * sizeof(float4)));
+        CK(L.packB.reserve((size_t)nBPad * pass * sizeof(float4)));
         if (fold) {
-            CK(c.packAw.reserve((size_t)nAPad * pass * sizeof(float4)));
-            CK(c.packBw.reserve((size_t)nBPad * pass * sizeof(float4)));
+            CK(L.packAw.reserve((size_t)nAPad * pass * sizeof(float4)));
+            CK(L.packBw.reserve((size_t)nBPad * pass * sizeof(float4)));
         }
-        CK(c.fp.reserve((size_t)pass * sizeof(FrameParams)));
-        CK(c.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
-        unsigned *work = c.ctl.as<unsigned>();
-        unsigned long long *stats = reinterpret_cast<unsigned long long *>(c.ctl.as<unsigned char>() + 16);
+        CK(L.fp.reserve((size_t)pass * sizeof(FrameParams)));
+        CK(L.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
+        unsigned *work = L.ctl.as<unsigned>();
+        unsigned long long *stats = reinterpret_cast<unsigned long long *>(L.ctl.as<unsigned char>() + 16);
 
         const float d2 = distance * distance;                  // one float32 rounding, getWithin.cpp:29
         const double T = (double)d2 * (1.0 + 9.5367431640625e-07);
@@ -377,22 +390,22 @@ static int dev_within(Ctx &c, cudaStream_t st, const float *d_all, int nAtoms, i
 
         for (int f0 = fb; f0 < fe; f0 += pass) {
             const int nFc = std::min(pass, fe - f0);
-            CK(cudaMemsetAsync(c.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
+            CK(cudaMemsetAsync(L.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
             CK(cudaMemsetAsync(work, 0, 8, st));
             int rc = launch_pack(c, st, d_all, nF, d_outSel, outSize, nAPad, f0, nFc, nullptr,
-                                 c.packA.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packAw.as<float4>() : nullptr, pairLayout);
+                                 L.packA.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, fold ? L.packAw.as<float4>() : nullptr, pairLayout);
             if (rc) return rc;
             rc = launch_pack(c, st, d_all, nF, d_refSel, refSize, nBPad, f0, nFc, nullptr,
-                             c.packB.as<float4>(), c.maxAbs.as<unsigned>(), d_cell, fold ? c.packBw.as<float4>() : nullptr, pairLayout);
+                             L.packB.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, fold ? L.packBw.as<float4>() : nullptr, pairLayout);
             if (rc) return rc;
-            prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, c.maxAbs.as<unsigned>(), T,
-                                                                 c.fp.as<FrameParams>(), stats);
+            prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
+                                                                 L.fp.as<FrameParams>(), stats);
             LAUNCHED();
-            a.A = c.packA.as<float4>();
-            a.B = c.packB.as<float4>();
-            a.Aw = fold ? c.packAw.as<float4>() : a.A;
-            a.Bw = fold ? c.packBw.as<float4>() : a.B;
-            a.fp = c.fp.as<FrameParams>();
+            a.A = L.packA.as<float4>();
+            a.B = L.packB.as<float4>();
+            a.Aw = fold ? L.packAw.as<float4>() : a.A;
+            a.Bw = fold ? L.packBw.as<float4>() : a.B;
+            a.fp = L.fp.as<FrameParams>();
             a.bits = d_bits + (size_t)(f0 - fb) * words;
             const unsigned long long items = (unsigned long long)nFc * a.nATiles;
             if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
@@ -530,7 +543,7 @@ struct Uploader {
         size_t bytesPerFrame = 0;
         for (auto &a : arr) { a.pinned = host_ptr_is_pinned(a.host); bytesPerFrame += (size_t)a.nRows * 12; }
         if (bytesPerFrame == 0) bytesPerFrame = 12;
-        nChunks = (int)std::min<size_t>((size_t)maxChunks, std::max<size_t>(1, bytesPerFrame * nFc / ((size_t)16 << 20)));
+        nChunks = (int)std::min<size_t>((size_t)maxChunks, std::max<size_t>(1, bytesPerFrame * nFc / ((size_t)12 << 20)));
         if (envOverride) if (const char *e = getenv(envOverride)) { int v = atoi(e); if (v >= 1) nChunks = v; }
         nChunks = std::max(1, std::min(nChunks, nFc));
         chunk = (nFc + nChunks - 1) / nChunks;
@@ -635,17 +648,25 @@ struct Uploader {
     }
 
     // compute stream: wait for chunk k's data / declare its buffers consumed
-    int acquire(int k) { CK(cudaStreamWaitEvent(c.stream, c.evCopied[k & 1], 0)); return NDA_OK; }
-    int release(int k) { CK(cudaEventRecord(c.evDone[k & 1], c.stream)); return NDA_OK; }
+    int acquire(int k, cudaStream_t st) { CK(cudaStreamWaitEvent(st, c.evCopied[k & 1], 0)); return NDA_OK; }
+    int release(int k, cudaStream_t st) { CK(cudaEventRecord(c.evDone[k & 1], st)); return NDA_OK; }
 };
+
+static cudaError_t reset_stats(Ctx &c, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(c.lane[0].ctl.as<unsigned char>() + 16, 0, 16, st);
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(c.lane[1].ctl.as<unsigned char>() + 16, 0, 16, st);
+}
 
 static int read_stats(Ctx &c, double pairs, float ms)
 {
-    unsigned long long h[2] = {0, 0};
-    CK(cudaMemcpy(h, c.ctl.as<unsigned char>() + 16, sizeof h, cudaMemcpyDeviceToHost));
+    unsigned long long h[2][2] = {{0, 0}, {0, 0}};
+    CK(cudaMemcpy(h[0], c.lane[0].ctl.as<unsigned char>() + 16, 16, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h[1], c.lane[1].ctl.as<unsigned char>() + 16, 16, cudaMemcpyDeviceToHost));
     c.stats[0] = pairs;
-    c.stats[1] = (double)h[0];
-    c.stats[2] = (double)h[1];
+    c.stats[1] = (double)(h[0][0] + h[1][0]);
+    c.stats[2] = (double)(h[0][1] + h[1][1]);
     c.stats[3] = (double)ms;
     return NDA_OK;
 }
@@ -723,8 +744,8 @@ int nda_dev_radial_nbr_counts(const float *d_sel1, int n1, const float *d_sel2, 
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     begin_call(*c);
-    CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
-    return dev_rdf(*c, st, d_sel1, n1, d_sel2, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr);
+    CK(reset_stats(*c, st));
+    return dev_rdf(*c, c->lane[0], st, d_sel1, n1, d_sel2, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr);
 }
 
 int nda_dev_within(const float *d_allAtoms, int nAtoms, int nF, const int *d_refSel, int refSize,
@@ -740,8 +761,8 @@ int nda_dev_within(const float *d_allAtoms, int nAtoms, int nF, const int *d_ref
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     begin_call(*c);
-    CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
-    return dev_within(*c, st, d_allAtoms, nAtoms, nF, d_refSel, refSize, d_outSel, outSelSize, d_bits, d_out,
+    CK(reset_stats(*c, st));
+    return dev_within(*c, c->lane[0], st, d_allAtoms, nAtoms, nF, d_refSel, refSize, d_outSel, outSelSize, d_bits, d_out,
                       d_cellDims, distance, fb, fe);
 }
 
@@ -775,8 +796,8 @@ int nda_dev_radial_nbr_counts_sel(const float *d_all, int nAtoms, const int *d_i
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     begin_call(*c);
-    CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
-    return dev_rdf(*c, st, d_all, n1, d_all, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr,
+    CK(reset_stats(*c, st));
+    return dev_rdf(*c, c->lane[0], st, d_all, n1, d_all, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr,
                    d_idx1, d_idx2);
 }
 
@@ -819,7 +840,7 @@ int nda_get_radial_nbr_counts(const float *sel1, int n1, const float *sel2, int 
         CK(c->counts.reserve(H * 8));
         CK(c->cell.reserve((size_t)nF * 12));
         CK(cudaMemsetAsync(c->counts.p, 0, H * 8, st));
-        CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
+        CK(reset_stats(*c, st));
         CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
         if (groupId) {
             for (int i = 0; i < n2; ++i)
@@ -834,20 +855,25 @@ int nda_get_radial_nbr_counts(const float *sel1, int n1, const float *sel2, int 
         rc = up.begin(8, "NDA_UPLOAD_CHUNKS");
         if (rc) return rc;
         CK(cudaEventRecord(c->ev0, st));
+        CK(cudaEventRecord(c->evSetup, st));                // lane 1 must see counts / cell / gid initialised
+        CK(cudaStreamWaitEvent(c->lane[1].stream, c->evSetup, 0));
         rc = up.issue(0);
         if (rc) return rc;
         for (int k = 0; k < up.nChunks; ++k) {
             const int wc = up.f1(k) - up.f0(k);
-            rc = up.acquire(k);
+            Ctx::Lane &L = c->lane[k & 1];                  // alternate lanes: kernel k+1 fills the tail of kernel k
+            rc = up.acquire(k, L.stream);
             if (rc) return rc;
-            rc = dev_rdf(*c, st, up.dev(0, k), n1, sameSel ? up.dev(0, k) : up.dev(1, k), n2,
+            rc = dev_rdf(*c, L, L.stream, up.dev(0, k), n1, sameSel ? up.dev(0, k) : up.dev(1, k), n2,
                          groupId ? c->gid.as<int>() : nullptr, nGroups, c->counts.as<unsigned long long>(), outSize,
                          c->cell.as<float>() + (size_t)up.f0(k) * 3, wc, 0, wc, sameSel, dr);
             if (rc) return rc;
-            rc = up.release(k);
+            rc = up.release(k, L.stream);
             if (rc) return rc;
             if (k + 1 < up.nChunks) { rc = up.issue(k + 1); if (rc) return rc; }
         }
+        CK(cudaEventRecord(c->evLaneJoin, c->lane[1].stream));
+        CK(cudaStreamWaitEvent(st, c->evLaneJoin, 0));
         CK(cudaEventRecord(c->ev1, st));
         CK(cudaMemcpyAsync(h.data(), c->counts.p, H * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -897,12 +923,12 @@ int nda_get_distances_sum(const float *sel1, int n1, const float *sel2, int n2, 
     if (rc) return rc;
     for (int k = 0; k < up.nChunks; ++k) {
         const int wc = up.f1(k) - up.f0(k);
-        rc = up.acquire(k);
+        rc = up.acquire(k, st);
         if (rc) return rc;
         rc = dev_distances(*c, st, up.dev(0, k), n1, sameSel ? up.dev(0, k) : up.dev(1, k), n2,
                            c->sum.as<double>(), c->cell.as<float>() + (size_t)up.f0(k) * 3, wc, 0, wc, sameSel);
         if (rc) return rc;
-        rc = up.release(k);
+        rc = up.release(k, st);
         if (rc) return rc;
         if (k + 1 < up.nChunks) { rc = up.issue(k + 1); if (rc) return rc; }
     }
@@ -973,7 +999,7 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
     CK(c->pinned_reserve((size_t)nFc * words * 4));
     uint32_t *hbits = reinterpret_cast<uint32_t *>(c->pinned);
 
-    CK(cudaMemsetAsync(c->ctl.as<unsigned char>() + 16, 0, 16, st));
+    CK(reset_stats(*c, st));
     CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
     if (refSize) CK(cudaMemcpyAsync(c->idx1.p, ref2.data(), (size_t)refSize * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->idx2.p, out2.data(), (size_t)outSelSize * 4, cudaMemcpyHostToDevice, st));
@@ -997,27 +1023,33 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
         }
     };
 
+    CK(cudaEventRecord(c->evSetup, st));                    // lane 1 must see cell / selections uploaded
+    CK(cudaStreamWaitEvent(c->lane[1].stream, c->evSetup, 0));
     rc = up.issue(0);
     if (rc) return rc;
     for (int k = 0; k < nChunks; ++k) {
         const int f0 = up.f0(k), wc = up.f1(k) - f0, buf = k & 1;
-        rc = up.acquire(k);
+        Ctx::Lane &L = c->lane[buf];                        // alternate lanes: kernel k+1 fills the tail of kernel k
+        cudaStream_t ls = L.stream;
+        rc = up.acquire(k, ls);
         if (rc) return rc;
-        rc = dev_within(*c, st, up.dev(0, k), nRows, wc, c->idx1.as<int>(), refSize, c->idx2.as<int>(), outSelSize,
+        rc = dev_within(*c, L, ls, up.dev(0, k), nRows, wc, c->idx1.as<int>(), refSize, c->idx2.as<int>(), outSelSize,
                         c->bits.as<unsigned>() + (size_t)(f0 - fb) * words, nullptr,
                         c->cell.as<float>() + (size_t)f0 * 3, distance, 0, wc);
         if (rc) return rc;
-        rc = up.release(k);
+        rc = up.release(k, ls);
         if (rc) return rc;
         CK(cudaMemcpyAsync(hbits + (size_t)(f0 - fb) * words, c->bits.as<unsigned>() + (size_t)(f0 - fb) * words,
-                           (size_t)wc * words * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(c->evBits[buf], st));
+                           (size_t)wc * words * 4, cudaMemcpyDeviceToHost, ls));
+        CK(cudaEventRecord(c->evBits[buf], ls));
         if (k + 1 < nChunks) { rc = up.issue(k + 1); if (rc) return rc; }   // host gathers k+1 while the GPU works on k
         if (k > 0) {                                         // ... and scatters chunk k-1
             CK(cudaEventSynchronize(c->evBits[buf ^ 1]));
             scatter(k - 1);
         }
     }
+    CK(cudaEventRecord(c->evLaneJoin, c->lane[1].stream));
+    CK(cudaStreamWaitEvent(st, c->evLaneJoin, 0));
     CK(cudaEventRecord(c->ev1, st));
     CK(cudaStreamSynchronize(st));
     scatter(nChunks - 1);
