@@ -238,13 +238,15 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
     const size_t H = (size_t)nGroups * nBins;
     // shared memory: as many warp-private histogram copies as still allow PAIR_MIN_CTAS CTAs per SM
     const size_t perCta = ((size_t)227 * 1024) / PAIR_MIN_CTAS - 1024;
-    size_t histBudget = (perCta > PAIR_SMEM_BASE) ? perCta - PAIR_SMEM_BASE : 0;
+    const int bTile = grouped ? PAIR_BTILE_GROUPED : PAIR_BTILE;
+    const size_t base = pair_smem_base(bTile);
+    size_t histBudget = (perCta > base) ? perCta - base : 0;
     int copies = (int)std::min<size_t>(PAIR_WARPS, histBudget / (H * 4));
     if (copies < 1) copies = 1;
-    const size_t smem = PAIR_SMEM_BASE + (size_t)copies * H * 4;
+    const size_t smem = base + (size_t)copies * H * 4;
     if (smem > c.smemOptin)
         return fail(NDA_ERR_ARG, "nGroups*outSize = %zu histogram cells do not fit in shared memory (max %zu)",
-                    H, (c.smemOptin - PAIR_SMEM_BASE) / 4);
+                    H, (c.smemOptin - base) / 4);
     const int n1Pad = sameSel ? round_up(n1, PAIR_BTILE) : round_up(n1, PAIR_ATILE);
     const int n2Pad = sameSel ? n1Pad : round_up(n2, PAIR_BTILE);
     const int filter = filter_kind();
@@ -272,7 +274,7 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
     RdfArgs a;
     a.n1 = n1; a.n1Pad = n1Pad; a.n2 = n2; a.n2Pad = n2Pad;
     a.nATiles = (n1 + PAIR_ATILE - 1) / PAIR_ATILE;
-    a.nBTiles = (n2 + PAIR_BTILE - 1) / PAIR_BTILE;
+    a.nBTiles = (n2 + bTile - 1) / bTile;
     a.counts = d_counts; a.nBins = nBins; a.nGroups = nGroups; a.histCopies = copies;
     a.sameSel = sameSel ? 1 : 0; a.dr = dr;
     a.fastStrict = getenv("NDA_STRICT_SLOW") ? 0 : 1;
