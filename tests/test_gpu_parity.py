@@ -458,3 +458,29 @@ def test_c_abi_errors_raise_runtime_error():
         plf.py_getWithin(xyz, np.array([11], np.int32), np.array([0], np.int32), out, cell, 1.0)
     # the library is still usable after an error
     assert plf.py_getRadialNbrCounts(xyz, xyz, cell, 1, 10, 0.1).sum() == 45 * 2     # all coincident: bin 0
+
+
+@pytest.mark.parametrize("n1,n2,nF", [(1, 1, 1), (1, 4, 33), (2, 5, 1), (511, 255, 2), (512, 256, 3), (513, 257, 1),
+                                      (1025, 1023, 2), (64, 1024, 31), (7, 1025, 32), (300, 2047, 1),
+                                      (33, 2048, 2), (129, 2049, 1)])
+def test_tile_boundary_shapes(n1, n2, nF):
+    """sizes on and around every tile / group / pad boundary (A tile 512, B tile 1024 resp. 256
+    grouped, vote group 4, pair layout 2, pack tile 32), dense enough that most bins are hit"""
+    rng = np.random.default_rng(1000 * n1 + n2 + nF)
+    cell = rng.uniform(14, 17, (nF, 3)).astype(np.float32)
+    a = rng.uniform(-5, 25, (n1, nF, 3)).astype(np.float32)
+    b = rng.uniform(-5, 25, (n2, nF, 3)).astype(np.float32)
+    nb, dr = 60, 0.11
+    assert np.array_equal(rdf_counts(a, b, cell, 0, nb, dr), port.rdf_counts(a, b, cell, 0, nb, dr).astype(np.int64))
+    assert np.array_equal(rdf_counts(b, b, cell, 1, nb, dr), port.rdf_counts(b, b, cell, 1, nb, dr).astype(np.int64))
+    gid = rng.integers(0, 5, n2).astype(np.int32)
+    assert np.array_equal(rdf_counts(a, b, cell, 0, nb, dr, groupId=gid, nGroups=5),
+                          port.rdf_counts(a, b, cell, 0, nb, dr, groupId=gid, nGroups=5).astype(np.int64))
+    allA = np.concatenate([a, b])
+    r = np.arange(n1, dtype=np.int32)
+    o = np.arange(n1, n1 + n2, dtype=np.int32)
+    assert np.array_equal(within_mask(allA, r, o, cell, 2.5), port.within(allA, r, o, cell, 2.5))
+    assert np.array_equal(within_mask(allA, o, r, cell, 1.7), port.within(allA, o, r, cell, 1.7))
+    s = plf.py_getDistancesSum(a[:9], b[:40], cell, 0)
+    w = port.distances_sum(a[:9], b[:40], cell, 0)
+    assert np.max(np.abs(s - w) / np.maximum(w, 1e-30)) <= 1e-12
