@@ -484,3 +484,38 @@ def test_tile_boundary_shapes(n1, n2, nF):
     s = plf.py_getDistancesSum(a[:9], b[:40], cell, 0)
     w = port.distances_sum(a[:9], b[:40], cell, 0)
     assert np.max(np.abs(s - w) / np.maximum(w, 1e-30)) <= 1e-12
+
+
+def test_far_from_origin_and_runaway_coordinates():
+    """unwrapped trajectories: coordinates thousands of boxes away from the origin.  At |x| ~ 5e3 the
+    float32 spacing (5e-4) widens the guard band but every result stays exact; at |x| ~ 1e8
+    (more than 2^20 boxes) the frame is run all-exact."""
+    rng = np.random.default_rng(77)
+    nF = 2
+    cell = np.array([[30.0, 31.0, 29.5], [30.5, 30.0, 30.2]], np.float32)
+    for offset in (5.0e3, -2.0e5, 1.0e8):
+        a = (offset + rng.uniform(0, 60, (400, nF, 3))).astype(np.float32)
+        b = (offset + rng.uniform(0, 60, (700, nF, 3))).astype(np.float32)
+        assert np.array_equal(rdf_counts(a, b, cell, 0, 100, 0.12), port.rdf_counts(a, b, cell, 0, 100, 0.12).astype(np.int64))
+        assert np.array_equal(rdf_counts(a, a, cell, 1, 100, 0.12), port.rdf_counts(a, a, cell, 1, 100, 0.12).astype(np.int64))
+        allA = np.concatenate([a, b])
+        r, o = np.arange(400, dtype=np.int32), np.arange(400, 1100, dtype=np.int32)
+        assert np.array_equal(within_mask(allA, r, o, cell, 3.0), port.within(allA, r, o, cell, 3.0))
+        s = plf.py_getDistancesSum(a[:16], b[:64], cell, 0)
+        w = port.distances_sum(a[:16], b[:64], cell, 0)
+        assert np.max(np.abs(s - w) / np.maximum(w, 1e-30)) <= 1e-12
+
+
+def test_degenerate_cells():
+    """zero, negative, infinite and NaN cell edges: the reference arithmetic decides (mostly: nothing
+    counts), and the kernels must agree with it instead of trusting their filters"""
+    rng = np.random.default_rng(78)
+    a = rng.uniform(0, 20, (200, 4, 3)).astype(np.float32)
+    b = rng.uniform(0, 20, (300, 4, 3)).astype(np.float32)
+    cell = np.array([[20, 20, 20], [0, 20, 20], [-20, 20, -20], [np.inf, np.nan, 20]], np.float32)
+    with np.errstate(all="ignore"):
+        want = port.rdf_counts(a, b, cell, 0, 80, 0.1).astype(np.int64)
+        assert np.array_equal(rdf_counts(a, b, cell, 0, 80, 0.1), want)
+        allA = np.concatenate([a, b])
+        r, o = np.arange(200, dtype=np.int32), np.arange(200, 500, dtype=np.int32)
+        assert np.array_equal(within_mask(allA, r, o, cell, 3.0), port.within(allA, r, o, cell, 3.0))
