@@ -102,6 +102,24 @@ int nda_get_within_bits(const float *allAtoms, int nbrAtoms, int nbrFrames,
                         uint32_t *bits, int *out, const float *cellDims, float distance,
                         int frameBegin, int frameEnd);
 
+/* ---- the two water-at-surface loops that reuse the minimum-image inner loop ---- */
+
+/* lib/libFunc.h:53-54 setWaterDistPBC, lib/openmp/src/setWaterDistPBC.cpp:9-77.  water float32
+ * [sizeW*nbrWAtoms][nbrFrames][3] is shifted IN PLACE, molecule by molecule, by the periodic image
+ * vector c*roundf(d/c) of the protein atom nearest to the molecule's first atom.  The minimum is
+ * taken PER MOLECULE (legacy CUDA build, lib/cuda/src/setWaterDistPBC.cu:33, and the docstring);
+ * the OpenMP text carries closestDist over from one molecule to the next. */
+int nda_set_water_dist_pbc(float *water, int sizeW, const float *prot, int sizeP,
+                           const float *cellDims, int nbrFrames, int nbrWAtoms);
+
+/* lib/libFunc.h:50-51 waterOrientAtSurface, lib/openmp/src/waterOrientAtSurface.cpp:10-112.
+ * waterO float32 [sizeO][nbrFrames][3] is OVERWRITTEN in place with (cosine of watVec against the
+ * surface normal built from the maxN nearest protein atoms with minR <= dist <= maxR, 0/1 flag,
+ * distance of the nearest one); `out` is accepted and ignored like in the reference. 1 <= maxN <= 16. */
+int nda_water_orient_at_surface(float *waterO, int sizeO, const float *watVec, const float *prot, int sizeP,
+                                float *out, const float *cellDims, int nbrFrames,
+                                float minR, float maxR, int maxN);
+
 /* ---- device-pointer entry points (inputs resident in HBM, stream-ordered) ---------- */
 
 /* d_counts uint64 [nGroups][outSize] is ACCUMULATED into (zero it first).

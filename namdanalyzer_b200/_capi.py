@@ -36,6 +36,9 @@ SIGNATURES = {
     "nda_get_distances_sum": (c_int, [c_f32p, c_int, c_f32p, c_int, c_f64p, c_f32p, c_int, c_int, c_int, c_int]),
     "nda_get_within_bits": (c_int, [c_f32p, c_int, c_int, c_i32p, c_int, c_i32p, c_int, c_u32p, c_i32p, c_f32p,
                                     c_float, c_int, c_int]),
+    "nda_set_water_dist_pbc": (c_int, [c_f32p, c_int, c_f32p, c_int, c_f32p, c_int, c_int]),
+    "nda_water_orient_at_surface": (c_int, [c_f32p, c_int, c_f32p, c_f32p, c_int, c_f32p, c_f32p, c_int,
+                                            c_float, c_float, c_int]),
     "nda_dev_radial_nbr_counts": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                           c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "nda_dev_within": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,

@@ -16,6 +16,7 @@
 
 #include "../../include/nda_b200.h"
 #include "nda_kernels.cuh"
+#include "nda_surface.cuh"
 
 // ------------------------------------------------------------------------------------------
 // errors, launch accounting
@@ -1069,6 +1070,107 @@ int nda_get_within(const float *allAtoms, int nAtoms, int nF, const int *refSel,
     if (!out) return fail(NDA_ERR_ARG, "null pointer argument");
     return nda_get_within_bits(allAtoms, nAtoms, nF, refSel, refSize, outSel, outSelSize, nullptr, out,
                                cellDims, distance, 0, nF);
+}
+
+// ---- water at the protein surface ----------------------------------------------
+// Both calls work IN PLACE on a host array, like the reference: upload, pack the protein frames into
+// 16-byte tiles, one kernel per pass of frames, download.
+static int surface_common(Ctx &c, cudaStream_t st, const float *prot, int sizeP, const float *cellDims, int nF,
+                          float **d_prot, float **d_cell)
+{
+    CK(c.raw[0][1].reserve((size_t)sizeP * nF * 12 + 16));
+    CK(c.cell.reserve((size_t)nF * 12));
+    CK(cudaMemcpyAsync(c.raw[0][1].p, prot, (size_t)sizeP * nF * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c.cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
+    *d_prot = c.raw[0][1].as<float>();
+    *d_cell = c.cell.as<float>();
+    return NDA_OK;
+}
+
+int nda_set_water_dist_pbc(float *water, int sizeW, const float *prot, int sizeP,
+                           const float *cellDims, int nF, int nbrWAtoms)
+{
+    if (!water || !prot || !cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (sizeW < 0 || sizeP < 0 || nF <= 0 || nbrWAtoms <= 0) return fail(NDA_ERR_ARG, "bad size");
+    if (sizeW == 0) return NDA_OK;
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    begin_call(*c);
+    Ctx::Lane &L = c->lane[0];
+    const size_t wBytes = (size_t)sizeW * nbrWAtoms * nF * 12;
+    CK(c->raw[0][0].reserve(wBytes + 16));
+    CK(cudaMemcpyAsync(c->raw[0][0].p, water, wBytes, cudaMemcpyHostToDevice, st));
+    float *d_prot = nullptr, *d_cell = nullptr;
+    rc = surface_common(*c, st, prot, sizeP, cellDims, nF, &d_prot, &d_cell);
+    if (rc) return rc;
+    const int nPPad = round_up(std::max(sizeP, 1), 32);
+    const int pass = std::min(32768, frames_per_pass((size_t)nPPad * sizeof(float4), nF));
+    CK(L.packB.reserve((size_t)nPPad * pass * sizeof(float4)));
+    CK(L.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
+    for (int f0 = 0; f0 < nF; f0 += pass) {
+        const int nFc = std::min(pass, nF - f0);
+        CK(cudaMemsetAsync(L.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
+        rc = launch_pack(*c, st, d_prot, nF, nullptr, sizeP, nPPad, f0, nFc, nullptr, L.packB.as<float4>(),
+                         L.maxAbs.as<unsigned>(), d_cell, nullptr);
+        if (rc) return rc;
+        dim3 grid((sizeW + SURF_THREADS - 1) / SURF_THREADS, nFc);
+        CK(c->kev_record(st));
+        water_nearest_shift_kernel<<<grid, SURF_THREADS, 0, st>>>(c->raw[0][0].as<float>(), sizeW, nbrWAtoms, nF, f0,
+                                                                  L.packB.as<float4>(), sizeP, nPPad, d_cell);
+        LAUNCHED();
+        CK(c->kev_record(st));
+    }
+    CK(cudaMemcpyAsync(water, c->raw[0][0].p, wBytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return NDA_OK;
+}
+
+int nda_water_orient_at_surface(float *waterO, int sizeO, const float *watVec, const float *prot, int sizeP,
+                                float *out_unused, const float *cellDims, int nF, float minR, float maxR, int maxN)
+{
+    (void)out_unused;                                       // unused by the reference as well (libFunc.h)
+    if (!waterO || !watVec || !prot || !cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (sizeO < 0 || sizeP < 0 || nF <= 0) return fail(NDA_ERR_ARG, "bad size");
+    if (maxN < 1 || maxN > SURF_MAXN) return fail(NDA_ERR_ARG, "maxN = %d outside [1, %d]", maxN, SURF_MAXN);
+    if (sizeO == 0) return NDA_OK;
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    begin_call(*c);
+    Ctx::Lane &L = c->lane[0];
+    const size_t wBytes = (size_t)sizeO * nF * 12;
+    CK(c->raw[0][0].reserve(wBytes + 16));
+    CK(c->raw[1][0].reserve(wBytes + 16));
+    CK(cudaMemcpyAsync(c->raw[0][0].p, waterO, wBytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->raw[1][0].p, watVec, wBytes, cudaMemcpyHostToDevice, st));
+    float *d_prot = nullptr, *d_cell = nullptr;
+    rc = surface_common(*c, st, prot, sizeP, cellDims, nF, &d_prot, &d_cell);
+    if (rc) return rc;
+    const int nPPad = round_up(std::max(sizeP, 1), 32);
+    const int pass = std::min(32768, frames_per_pass((size_t)nPPad * sizeof(float4), nF));
+    CK(L.packB.reserve((size_t)nPPad * pass * sizeof(float4)));
+    CK(L.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
+    for (int f0 = 0; f0 < nF; f0 += pass) {
+        const int nFc = std::min(pass, nF - f0);
+        CK(cudaMemsetAsync(L.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
+        rc = launch_pack(*c, st, d_prot, nF, nullptr, sizeP, nPPad, f0, nFc, nullptr, L.packB.as<float4>(),
+                         L.maxAbs.as<unsigned>(), d_cell, nullptr);
+        if (rc) return rc;
+        dim3 grid((sizeO + SURF_THREADS - 1) / SURF_THREADS, nFc);
+        CK(c->kev_record(st));
+        water_orient_kernel<<<grid, SURF_THREADS, 0, st>>>(c->raw[0][0].as<float>(), c->raw[1][0].as<float>(), sizeO, nF, f0,
+                                                           L.packB.as<float4>(), sizeP, nPPad, d_cell, minR, maxR, maxN);
+        LAUNCHED();
+        CK(c->kev_record(st));
+    }
+    CK(cudaMemcpyAsync(waterO, c->raw[0][0].p, wBytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return NDA_OK;
 }
 
 // ---- measurement / test support --------------------------------------------------------------

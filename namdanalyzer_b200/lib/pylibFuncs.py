@@ -26,7 +26,7 @@ from .._capi import c_f32p, c_f64p, c_i32p, c_u32p, c_u64p
 
 __all__ = ["py_getWithin", "py_getDistances", "py_getRadialNbrDensity", "py_getParallelBackend",
            "py_getRadialNbrDensityGrouped", "py_getRadialNbrCounts", "py_getDistancesSum",
-           "py_getWithinBits", "py_getWithinLists"]
+           "py_getWithinBits", "py_getWithinLists", "py_setWaterDistPBC", "py_waterOrientAtSurface"]
 
 _CNAME = {np.dtype(np.float32): "float", np.dtype(np.float64): "double", np.dtype(np.int32): "int",
           np.dtype(np.int64): "long", np.dtype(np.uint64): "unsigned long", np.dtype(np.uint32): "unsigned int"}
@@ -225,3 +225,47 @@ def py_getWithinLists(allAtoms, refSel, outSel, cellDims, distance, frameBegin=0
     offsets = np.zeros(nFc + 1, np.int64)
     np.cumsum(np.bincount(f_idx, minlength=nFc), out=offsets[1:])
     return offsets, outSel[a_idx]
+
+
+# ---- SURVEY row f-3 ---------------------------------------------------------------------------------
+
+def py_setWaterDistPBC(water, prot, cellDims, nbrWAtoms):
+    """Shifts every water molecule IN PLACE by the periodic image vector of its nearest protein atom
+    (NAMDAnalyzer/lib/libFunc.pyx:206-213, lib/openmp/src/setWaterDistPBC.cpp).  ``water`` float32
+    (nMolecules*nbrWAtoms, nFrames, 3), atoms of a molecule adjacent, first atom = reference point."""
+    water = _coords(water, "water")
+    prot = _coords(prot, "prot")
+    nF = water.shape[1]
+    if prot.shape[1] != nF:
+        raise ValueError("water and prot have different frame counts (%d, %d)" % (nF, prot.shape[1]))
+    nbrWAtoms = int(nbrWAtoms)
+    if nbrWAtoms < 1 or water.shape[0] % nbrWAtoms:
+        raise ValueError("water.shape[0] must be a multiple of nbrWAtoms")
+    if not water.flags.writeable:
+        raise ValueError("water is modified in place and must be writeable")
+    cell = _cell(cellDims, nF)
+    L = _capi.load()
+    _capi.check(L.nda_set_water_dist_pbc(_p(water, c_f32p), water.shape[0] // nbrWAtoms, _p(prot, c_f32p),
+                                         prot.shape[0], _p(cell, c_f32p), nF, nbrWAtoms))
+
+
+def py_waterOrientAtSurface(waterO, watVec, prot, out, cellDims, minR, maxR, maxN):
+    """Overwrites ``waterO`` (nWater, nFrames, 3) IN PLACE with (cos angle to the surface normal, 0/1
+    flag, nearest distance) -- NAMDAnalyzer/lib/libFunc.pyx:189-203 (``out`` is unused there too),
+    lib/openmp/src/waterOrientAtSurface.cpp."""
+    waterO = _coords(waterO, "waterO")
+    watVec = _coords(watVec, "watVec")
+    prot = _coords(prot, "prot")
+    _buf(out, "out", np.float32, 2)
+    nF = waterO.shape[1]
+    if watVec.shape != waterO.shape:
+        raise ValueError("watVec must have the shape of waterO")
+    if prot.shape[1] != nF:
+        raise ValueError("waterO and prot have different frame counts (%d, %d)" % (nF, prot.shape[1]))
+    if not waterO.flags.writeable:
+        raise ValueError("waterO is modified in place and must be writeable")
+    cell = _cell(cellDims, nF)
+    L = _capi.load()
+    _capi.check(L.nda_water_orient_at_surface(_p(waterO, c_f32p), waterO.shape[0], _p(watVec, c_f32p),
+                                              _p(prot, c_f32p), prot.shape[0], _p(out, c_f32p), _p(cell, c_f32p),
+                                              nF, float(minR), float(maxR), int(maxN)))

@@ -202,3 +202,107 @@ int port_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * the two water-at-surface loops that reuse the minimum-image
+ * inner loop.  Paths relative to lib/openmp/src/.
+ * ------------------------------------------------------------------------------------------ */
+
+/* setWaterDistPBC.cpp:9-77.  water [sizeW*nbrWAtoms][nF][3] is shifted IN PLACE, molecule by
+ * molecule, by the periodic image vector c*roundf(d/c) of its nearest protein atom (distance
+ * measured from the molecule's first atom, :33-35).
+ *
+ * reset_per_water == 0 is the literal OpenMP text: closestDist / closest_xyz are initialised
+ * ONCE before all loops (:13-16), so they form a running minimum over every water and frame
+ * processed so far and most molecules receive the stale shift of an earlier one.
+ * reset_per_water == 1 re-initialises them for every molecule, which is what the legacy CUDA
+ * build does (lib/cuda/src/setWaterDistPBC.cu:33) and what the docstring describes; the two
+ * coincide when the reference is called with one molecule and one frame. */
+void port_set_water_dist_pbc(float *water, int sizeW, const float *prot, int sizeP,
+                             const float *cellDims, int nFrames, int nbrWAtoms, int reset_per_water)
+{
+    float closestDist = 1000, closest_x = 0, closest_y = 0, closest_z = 0;       /* :13-16 */
+    for (int frame = 0; frame < nFrames; ++frame) {                              /* :22 */
+        const float cx = cellDims[3 * frame], cy = cellDims[3 * frame + 1], cz = cellDims[3 * frame + 2];
+        for (int w = 0; w < sizeW; ++w) {                                        /* :30 */
+            if (reset_per_water) { closestDist = 1000; closest_x = closest_y = closest_z = 0; }
+            const float *wp = water + 3 * ((size_t)nbrWAtoms * nFrames * w + frame);
+            const float wx = wp[0], wy = wp[1], wz = wp[2];
+            for (int p = 0; p < sizeP; ++p) {                                    /* :36 */
+                const float *pp = prot + 3 * ((size_t)p * nFrames + frame);
+                float dx = wx - pp[0], dy = wy - pp[1], dz = wz - pp[2];         /* :42-44 */
+                const float px = cx * roundf(dx / cx);                           /* :47-49 */
+                const float py = cy * roundf(dy / cy);
+                const float pz = cz * roundf(dz / cz);
+                dx -= px; dy -= py; dz -= pz;                                    /* :51-53 */
+                const float dist = sqrtf(norm2(dx, dy, dz));                     /* :55 */
+                if (dist < closestDist) {                                        /* :57-63 */
+                    closestDist = dist;
+                    closest_x = px; closest_y = py; closest_z = pz;
+                }
+            }
+            for (int k = 0; k < nbrWAtoms; ++k) {                                /* :67-72 */
+                float *q = water + 3 * ((size_t)nbrWAtoms * nFrames * w + frame + (size_t)k * nFrames);
+                q[0] -= closest_x; q[1] -= closest_y; q[2] -= closest_z;
+            }
+        }
+    }
+}
+
+/* waterOrientAtSurface.cpp:10-112.  waterO [sizeO][nF][3] is OVERWRITTEN in place:
+ * [..][0] = cosine between watVec and the surface normal built from the maxN nearest protein
+ * atoms with minR <= dist <= maxR, [..][1] = 1 if any such atom exists else 0,
+ * [..][2] = sqrtf(closest[1]) (distance of the nearest one, sqrtf(1000) if none). */
+void port_water_orient_at_surface(float *waterO, int sizeO, const float *watVec, const float *prot, int sizeP,
+                                  const float *cellDims, int nFrames, float minR, float maxR, int maxN)
+{
+    #pragma omp parallel
+    {
+        float *closest = (float *)malloc(sizeof(float) * 5 * (size_t)(maxN > 0 ? maxN : 1));
+        #pragma omp for collapse(2) schedule(static)
+        for (int frame = 0; frame < nFrames; ++frame) {                          /* :19 */
+            for (int w = 0; w < sizeO; ++w) {                                    /* :31 */
+                const float cx = cellDims[3 * frame], cy = cellDims[3 * frame + 1], cz = cellDims[3 * frame + 2];
+                for (int i = 0; i < 5 * maxN; ++i) closest[i] = 1000;            /* :27-28 */
+                float *wo = waterO + 3 * ((size_t)nFrames * w + frame);
+                const float *wv = watVec + 3 * ((size_t)nFrames * w + frame);
+                const float wx = wo[0], wy = wo[1], wz = wo[2];
+                const float vx = wv[0], vy = wv[1], vz = wv[2];
+                wo[1] = 0;                                                       /* :43 */
+                for (int p = 0; p < sizeP; ++p) {                                /* :45 */
+                    const float *pp = prot + 3 * ((size_t)p * nFrames + frame);
+                    float dx = pp[0] - wx, dy = pp[1] - wy, dz = pp[2] - wz;     /* :47-49 prot - water */
+                    dx = wrap1(dx, cx); dy = wrap1(dy, cy); dz = wrap1(dz, cz);  /* :52-54 */
+                    const float dist = sqrtf(norm2(dx, dy, dz));                 /* :56 */
+                    if (dist <= maxR && dist >= minR) {                          /* :58 */
+                        wo[1] = 1;
+                        for (int i = 0; i < maxN; ++i) {                         /* :62 */
+                            if (dist < sqrtf(closest[5 * i + 1])) {              /* :64 */
+                                /* :65-72 LITERALLY: the copy runs upwards, so it is not a shift --
+                                 * every slot after i ends up holding the OLD slot i */
+                                for (int k = i + 1; k < maxN; ++k)
+                                    memcpy(closest + 5 * k, closest + 5 * (k - 1), 5 * sizeof(float));
+                                closest[5 * i] = (float)p;
+                                closest[5 * i + 1] = dist * dist;
+                                closest[5 * i + 2] = dx; closest[5 * i + 3] = dy; closest[5 * i + 4] = dz;
+                                break;
+                            }
+                        }
+                    }
+                }
+                float n0 = 0, n1 = 0, n2 = 0;                                    /* :91-98 */
+                for (int i = 0; i < maxN; ++i) {
+                    n0 += closest[5 * i + 2] / closest[5 * i + 1];
+                    n1 += closest[5 * i + 3] / closest[5 * i + 1];
+                    n2 += closest[5 * i + 4] / closest[5 * i + 1];
+                }
+                float cosA = vx * n0 + vy * n1 + vz * n2;                        /* :101-103 */
+                cosA /= sqrtf(vx * vx + vy * vy + vz * vz);
+                cosA /= sqrtf(n0 * n0 + n1 * n1 + n2 * n2);
+                wo[0] = cosA;                                                    /* :106-107 */
+                wo[2] = sqrtf(closest[1]);
+            }
+        }
+        free(closest);
+    }
+}

@@ -38,6 +38,12 @@ def lib():
                                           _i32p, ctypes.c_int, _f32p, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_float, ctypes.c_float]
         L.port_get_rdf_counts.restype = None
+        L.port_set_water_dist_pbc.argtypes = [_f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_int]
+        L.port_set_water_dist_pbc.restype = None
+        L.port_water_orient_at_surface.argtypes = [_f32p, ctypes.c_int, _f32p, _f32p, ctypes.c_int, _f32p,
+                                                   ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int]
+        L.port_water_orient_at_surface.restype = None
         L.port_pair_r2.argtypes = [_f32p, _f32p, _f32p]
         L.port_pair_r2.restype = ctypes.c_float
         L.port_num_threads.restype = ctypes.c_int
@@ -112,3 +118,26 @@ def pair_r2(a, b, cell):
     cell = np.ascontiguousarray(cell, np.float32)
     return float(lib().port_pair_r2(a.ctypes.data_as(_f32p), b.ctypes.data_as(_f32p),
                                     cell.ctypes.data_as(_f32p)))
+
+
+def set_water_dist_pbc(water, prot, cellDims, nbrWAtoms, reset_per_water=True):
+    """-> shifted copy of water [nMol*nbrWAtoms][nF][3] (setWaterDistPBC.cpp:9-77)"""
+    w = np.array(water, np.float32, order="C")
+    prot = np.ascontiguousarray(prot, np.float32)
+    cell = np.ascontiguousarray(cellDims, np.float32)
+    lib().port_set_water_dist_pbc(w.ctypes.data_as(_f32p), w.shape[0] // nbrWAtoms, prot.ctypes.data_as(_f32p),
+                                  prot.shape[0], cell.ctypes.data_as(_f32p), w.shape[1], int(nbrWAtoms),
+                                  int(bool(reset_per_water)))
+    return w
+
+
+def water_orient_at_surface(waterO, watVec, prot, cellDims, minR, maxR, maxN):
+    """-> overwritten copy of waterO (waterOrientAtSurface.cpp:10-112)"""
+    w = np.array(waterO, np.float32, order="C")
+    v = np.ascontiguousarray(watVec, np.float32)
+    prot = np.ascontiguousarray(prot, np.float32)
+    cell = np.ascontiguousarray(cellDims, np.float32)
+    lib().port_water_orient_at_surface(w.ctypes.data_as(_f32p), w.shape[0], v.ctypes.data_as(_f32p),
+                                       prot.ctypes.data_as(_f32p), prot.shape[0], cell.ctypes.data_as(_f32p),
+                                       w.shape[1], ctypes.c_float(minR), ctypes.c_float(maxR), int(maxN))
+    return w

@@ -31,6 +31,12 @@ _SYMS = {
                             [_f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p,
                              ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float]),
     "getParallelBackend": ("_Z18getParallelBackendv", []),
+    # SURVEY row f-3 (lib/openmp/src/setWaterDistPBC.cpp, waterOrientAtSurface.cpp)
+    "setWaterDistPBC": ("_Z15setWaterDistPBCPfiS_iS_ii",
+                        [_f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p, ctypes.c_int, ctypes.c_int]),
+    "waterOrientAtSurface": ("_Z20waterOrientAtSurfacePfiS_S_iS_S_iffi",
+                             [_f32p, ctypes.c_int, _f32p, _f32p, ctypes.c_int, _f32p, _f32p, ctypes.c_int,
+                              ctypes.c_float, ctypes.c_float, ctypes.c_int]),
 }
 
 
@@ -139,6 +145,51 @@ class RefLib:
                 assert o.max(initial=0.0) < 2 ** 24, "per-frame bin count left float32's exact range"
                 tot += o.astype(np.int64)
         return tot
+
+    # -- row f-3 -----------------------------------------------------------------------
+    def set_water_dist_pbc_literal(self, water, prot, cellDims, nbrWAtoms):
+        """the reference call as its callers make it (one call, all molecules and frames): shifts a
+        COPY of water and returns it.  closestDist is a running minimum over the whole call."""
+        w = np.array(water, np.float32, order="C")
+        prot = np.ascontiguousarray(prot, np.float32)
+        cell = np.ascontiguousarray(cellDims, np.float32)
+        with self._quiet():
+            self.fn["setWaterDistPBC"](w.ctypes.data_as(_f32p), w.shape[0] // nbrWAtoms, prot.ctypes.data_as(_f32p),
+                                       prot.shape[0], cell.ctypes.data_as(_f32p), w.shape[1], int(nbrWAtoms))
+        return w
+
+    def set_water_dist_pbc_per_molecule(self, water, prot, cellDims, nbrWAtoms):
+        """one reference call per (molecule, frame): the per-molecule nearest-atom shift (what the
+        legacy CUDA build and the docstring mean), free of the running-minimum carry-over"""
+        water = np.ascontiguousarray(water, np.float32)
+        prot = np.ascontiguousarray(prot, np.float32)
+        cell = np.ascontiguousarray(cellDims, np.float32)
+        out = water.copy()
+        nW, nF = water.shape[0] // nbrWAtoms, water.shape[1]
+        with self._quiet():
+            for f in range(nF):
+                p1 = np.ascontiguousarray(prot[:, f:f + 1])
+                c1 = np.ascontiguousarray(cell[f:f + 1])
+                for m in range(nW):
+                    w1 = np.ascontiguousarray(water[m * nbrWAtoms:(m + 1) * nbrWAtoms, f:f + 1])
+                    self.fn["setWaterDistPBC"](w1.ctypes.data_as(_f32p), 1, p1.ctypes.data_as(_f32p), p1.shape[0],
+                                               c1.ctypes.data_as(_f32p), 1, int(nbrWAtoms))
+                    out[m * nbrWAtoms:(m + 1) * nbrWAtoms, f] = w1[:, 0]
+        return out
+
+    def water_orient_at_surface(self, waterO, watVec, prot, cellDims, minR, maxR, maxN):
+        """-> the overwritten copy of waterO: [..,0] cosine, [..,1] flag, [..,2] nearest distance"""
+        w = np.array(waterO, np.float32, order="C")
+        v = np.ascontiguousarray(watVec, np.float32)
+        prot = np.ascontiguousarray(prot, np.float32)
+        cell = np.ascontiguousarray(cellDims, np.float32)
+        dummy = np.zeros((1, 1), np.float32)
+        with self._quiet():
+            self.fn["waterOrientAtSurface"](w.ctypes.data_as(_f32p), w.shape[0], v.ctypes.data_as(_f32p),
+                                            prot.ctypes.data_as(_f32p), prot.shape[0], dummy.ctypes.data_as(_f32p),
+                                            cell.ctypes.data_as(_f32p), w.shape[1], ctypes.c_float(minR),
+                                            ctypes.c_float(maxR), int(maxN))
+        return w
 
     # -- raw multi-frame calls, as the reference's callers make them (for timing) ---
     def raw_rdf(self, sel1, sel2, out, cellDims, sameSel, maxR, dr):

@@ -162,3 +162,47 @@ def test_shipped_flags_build_differs_only_at_bin_edges():
     diff = f - s
     assert np.abs(diff).sum() <= 1e-4 * s.sum()
     assert abs(int(diff.sum())) <= 2          # only the outermost edge can leak a pair
+
+
+# ---------------------------------------------------------------- SURVEY row f-3 (water at the surface)
+
+def _surface_case(seed, nW=60, nP=200, nF=3, L=24.0):
+    rng = np.random.default_rng(seed)
+    cell = (L * (1 + 0.01 * rng.standard_normal((nF, 3)))).astype(np.float32)
+    prot = rng.uniform(6, 18, (nP, nF, 3)).astype(np.float32)
+    water = rng.uniform(-10, 34, (3 * nW, nF, 3)).astype(np.float32)       # 3 atoms per molecule, unwrapped
+    water[1::3] = water[0::3] + rng.normal(0, 0.6, (nW, nF, 3)).astype(np.float32)
+    water[2::3] = water[0::3] + rng.normal(0, 0.6, (nW, nF, 3)).astype(np.float32)
+    return water, prot, cell
+
+
+@pytest.mark.skipif(not ref.available("strict"), reason="oracle/_ref not built")
+def test_port_set_water_dist_pbc_equals_reference():
+    R = ref.RefLib("strict")
+    water, prot, cell = _surface_case(31)
+    # literal text: one call, running minimum carried across molecules and frames
+    assert np.array_equal(port.set_water_dist_pbc(water, prot, cell, 3, reset_per_water=False),
+                          R.set_water_dist_pbc_literal(water, prot, cell, 3))
+    # per-molecule semantics = the reference called one molecule and one frame at a time
+    per = port.set_water_dist_pbc(water, prot, cell, 3, reset_per_water=True)
+    assert np.array_equal(per, R.set_water_dist_pbc_per_molecule(water, prot, cell, 3))
+    # the carry-over is real: the two disagree on this input
+    assert not np.array_equal(per, R.set_water_dist_pbc_literal(water, prot, cell, 3))
+    # every molecule ends up within half a box (per axis) of its nearest protein atom: the shift
+    # is a whole number of cell vectors
+    shift = (water - per)[0::3]
+    assert np.allclose(shift / cell[None], np.round(shift / cell[None]), atol=1e-4)
+
+
+@pytest.mark.skipif(not ref.available("strict"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("maxN", [1, 3, 5])
+def test_port_water_orient_equals_reference(maxN):
+    R = ref.RefLib("strict")
+    water, prot, cell = _surface_case(32 + maxN, nW=150)
+    wO = np.ascontiguousarray(water[0::3])
+    vec = np.ascontiguousarray((wO - water[1::3]) + (wO - water[2::3])) / np.float32(2)
+    with np.errstate(all="ignore"):
+        got = port.water_orient_at_surface(wO, vec, prot, cell, 0.0, 5.0, maxN)
+        want = R.water_orient_at_surface(wO, vec, prot, cell, 0.0, 5.0, maxN)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert 0 < want[..., 1].sum() < want[..., 1].size          # some waters at the surface, some not
