@@ -120,6 +120,24 @@ int nda_water_orient_at_surface(float *waterO, int sizeO, const float *watVec, c
                                 float *out, const float *cellDims, int nbrFrames,
                                 float minR, float maxR, int maxN);
 
+/* ---- hydrogen-bond autocorrelation ------------------------------------ */
+
+/* lib/libFunc.h:13-19 getHBCorr, lib/openmp/src/getHydrogenBonds.cpp:9-91.  acceptors
+ * [size_acceptors][nbrFrames][3], donors / hydrogens [size_donors][nbrFrames][3] (hydrogen col is
+ * bound to donor col).  out float32 [nbrFrames] is ACCUMULATED into, as in the reference:
+ * out[dt] += number of pairs (row, col > row) bonded at dt = 0 that are bonded (continuous == 0)
+ * or still unbroken (continuous == 1) at dt.  maxTime, step, nbrTimeOri are accepted and unused,
+ * as in the reference.  The reference adds 1.0f per event; this adds the integer count once
+ * (identical while a call's counts stay below 2^24). */
+int nda_get_hb_corr(const float *acceptors, int size_acceptors, int nbrFrames,
+                    const float *donors, int size_donors, const float *hydrogens, int size_hydrogens,
+                    const float *cellDims, float *out, int maxTime, int step, int nbrTimeOri,
+                    float maxR, float minAngle, int continuous);
+/* the exact integer counts, uint64 [nbrFrames], OVERWRITTEN */
+int nda_get_hb_counts(const float *acceptors, int size_acceptors, int nbrFrames,
+                      const float *donors, int size_donors, const float *hydrogens, int size_hydrogens,
+                      const float *cellDims, uint64_t *counts, float maxR, float minAngle, int continuous);
+
 /* ---- device-pointer entry points (inputs resident in HBM, stream-ordered) ---------- */
 
 /* d_counts uint64 [nGroups][outSize] is ACCUMULATED into (zero it first).

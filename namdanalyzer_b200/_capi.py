@@ -39,6 +39,10 @@ SIGNATURES = {
     "nda_set_water_dist_pbc": (c_int, [c_f32p, c_int, c_f32p, c_int, c_f32p, c_int, c_int]),
     "nda_water_orient_at_surface": (c_int, [c_f32p, c_int, c_f32p, c_f32p, c_int, c_f32p, c_f32p, c_int,
                                             c_float, c_float, c_int]),
+    "nda_get_hb_corr": (c_int, [c_f32p, c_int, c_int, c_f32p, c_int, c_f32p, c_int, c_f32p, c_f32p, c_int, c_int, c_int,
+                                c_float, c_float, c_int]),
+    "nda_get_hb_counts": (c_int, [c_f32p, c_int, c_int, c_f32p, c_int, c_f32p, c_int, c_f32p, c_u64p, c_float, c_float,
+                                  c_int]),
     "nda_dev_radial_nbr_counts": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                           c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "nda_dev_within": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,

@@ -1173,6 +1173,78 @@ int nda_water_orient_at_surface(float *waterO, int sizeO, const float *watVec, c
     return NDA_OK;
 }
 
+// ---- hydrogen-bond autocorrelation ----------------------------------------------
+int nda_get_hb_counts(const float *acceptors, int nA, int nF, const float *donors, int nD,
+                      const float *hydrogens, int nH, const float *cellDims, uint64_t *counts,
+                      float maxR, float minAngle, int continuous)
+{
+    if (!acceptors || !donors || !hydrogens || !cellDims || !counts) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (nA < 0 || nD < 0 || nH < nD || nF <= 0) return fail(NDA_ERR_ARG, "bad size (every donor needs its hydrogen)");
+    for (int dt = 0; dt < nF; ++dt) counts[dt] = 0;
+    if (nA == 0 || nD == 0) return NDA_OK;
+    std::lock_guard<std::mutex> lk(g_mutex);
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaStream_t st = c->stream;
+    begin_call(*c);
+    const float cosAngle = cosf(minAngle);                  // getHydrogenBonds.cpp:16, the host's libm like the reference
+    CK(c->raw[0][0].reserve((size_t)nA * nF * 12 + 16));
+    CK(c->raw[0][1].reserve((size_t)nD * nF * 12 + 16));
+    CK(c->raw[1][0].reserve((size_t)nD * nF * 12 + 16));
+    CK(c->cell.reserve((size_t)nF * 12));
+    CK(c->counts.reserve((size_t)nF * 8 + 16));
+    CK(cudaMemcpyAsync(c->raw[0][0].p, acceptors, (size_t)nA * nF * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->raw[0][1].p, donors, (size_t)nD * nF * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->raw[1][0].p, hydrogens, (size_t)nD * nF * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(c->counts.p, 0, (size_t)nF * 8, st));
+    unsigned *d_n = c->lane[0].ctl.as<unsigned>() + 2;      // spare word of the control block
+    unsigned capacity = 64u * (unsigned)std::max(nA, nD) + 4096u;
+    unsigned nPairs = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(c->idx1.reserve((size_t)capacity * 8));
+        CK(cudaMemsetAsync(d_n, 0, 4, st));
+        dim3 grid((nD + 255) / 256, std::min(nA, 4096));
+        hb_frame0_kernel<<<grid, 256, 0, st>>>(c->raw[0][0].as<float>(), nA, c->raw[0][1].as<float>(), nD,
+                                               c->raw[1][0].as<float>(), c->cell.as<float>(), nF, maxR, cosAngle,
+                                               c->idx1.as<int>(), capacity, d_n);
+        LAUNCHED();
+        CK(cudaMemcpyAsync(&nPairs, d_n, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (nPairs <= capacity) break;
+        capacity = nPairs;                                   // denser than guessed: redo with the exact size
+    }
+    if (nPairs > 0) {
+        CK(c->kev_record(st));
+        hb_walk_kernel<<<(nPairs + 7) / 8, 256, 0, st>>>(c->raw[0][0].as<float>(), c->raw[0][1].as<float>(),
+                                                         c->raw[1][0].as<float>(), c->cell.as<float>(), nF, maxR, cosAngle,
+                                                         continuous == 1 ? 1 : 0, c->idx1.as<int>(), nPairs,
+                                                         c->counts.as<unsigned long long>());
+        LAUNCHED();
+        CK(c->kev_record(st));
+    }
+    CK(cudaMemcpyAsync(counts, c->counts.p, (size_t)nF * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    c->stats[0] = 0.5 * (double)nA * (double)nD;
+    c->stats[1] = (double)nPairs;
+    return NDA_OK;
+}
+
+int nda_get_hb_corr(const float *acceptors, int nA, int nF, const float *donors, int nD,
+                    const float *hydrogens, int nH, const float *cellDims, float *out,
+                    int maxTime, int step, int nbrTimeOri, float maxR, float minAngle, int continuous)
+{
+    (void)maxTime; (void)step; (void)nbrTimeOri;            // unused by the reference as well
+    if (!out) return fail(NDA_ERR_ARG, "null pointer argument");
+    if (nF <= 0) return fail(NDA_ERR_ARG, "bad size");
+    std::vector<uint64_t> cnt((size_t)nF, 0);
+    int rc = nda_get_hb_counts(acceptors, nA, nF, donors, nD, hydrogens, nH, cellDims, cnt.data(), maxR, minAngle, continuous);
+    if (rc) return rc;
+    for (int dt = 0; dt < nF; ++dt) out[dt] += (float)cnt[dt];   // the reference ACCUMULATES into out (:73)
+    return NDA_OK;
+}
+
 // ---- measurement / test support --------------------------------------------------------------
 int nda_dev_synth_water_box(float *d_xyz, float *d_cellDims, int n_side, int nF, int fb, int fe,
                             float L, float sigma, uint32_t seed, void *stream)

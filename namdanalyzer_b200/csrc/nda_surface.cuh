@@ -173,3 +173,83 @@ water_orient_kernel(float *__restrict__ waterO, const float *__restrict__ watVec
         wo[2] = __fsqrt_rn(cl[1]);                                           // :107
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// hydrogen-bond autocorrelation (lib/openmp/src/getHydrogenBonds.cpp:9-91)
+//
+// Only pairs (acceptor row, donor/hydrogen col > row) bonded at dt = 0 contribute (:78-79), so the
+// work splits into
+//   hb_frame0_kernel  every pair at frame 0 with the strict criterion -> compact list of bonded pairs
+//   hb_walk_kernel    one warp per bonded pair, lanes = 32 consecutive frames (coalesced rows of the
+//                     reference layout); intermittent: count every bonded frame; continuous: count
+//                     the leading run of bonded frames and stop at the first break (:81-82)
+// Counts are integers (the reference adds 1.0f per event into a float under `omp critical`).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool hb_bonded(const float *__restrict__ a, const float *__restrict__ h,
+                                          const float *__restrict__ d, float cx, float cy, float cz,
+                                          float maxR, float cosAngle)
+{
+    float hx, hy, hz, sx, sy, sz;
+    strict_wrap_with_shift(__fsub_rn(h[0], a[0]), cx, __frcp_rn(cx), hx, sx);     // :37-49, h - acc, wrapped
+    strict_wrap_with_shift(__fsub_rn(h[1], a[1]), cy, __frcp_rn(cy), hy, sy);
+    strict_wrap_with_shift(__fsub_rn(h[2], a[2]), cz, __frcp_rn(cz), hz, sz);
+    const float ax = __fsub_rn(a[0], d[0]), ay = __fsub_rn(a[1], d[1]), az = __fsub_rn(a[2], d[2]);   // :52-57, NOT wrapped
+    const float hh = strict_norm2(hx, hy, hz);
+    const float dist = __fsqrt_rn(hh);                                             // :60
+    const float dot = __fadd_rn(__fadd_rn(__fmul_rn(hx, ax), __fmul_rn(hy, ay)), __fmul_rn(hz, az));   // :63
+    const float den = __fmul_rn(__fsqrt_rn(hh), __fsqrt_rn(strict_norm2(ax, ay, az)));                 // :64-65
+    const float angle = __fdiv_rn(dot, den);
+    return dist < maxR && angle < cosAngle;                                        // :67
+}
+
+// grid (ceil(nD/256), min(nA, 4096)), block 256.  pairs[2*k], pairs[2*k+1] = (row, col).
+__global__ void __launch_bounds__(256)
+hb_frame0_kernel(const float *__restrict__ acc, int nA, const float *__restrict__ don, int nD,
+                 const float *__restrict__ hyd, const float *__restrict__ cell, int nF,
+                 float maxR, float cosAngle, int *__restrict__ pairs, unsigned capacity,
+                 unsigned *__restrict__ nPairs)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= nD) return;
+    const float cx = cell[0], cy = cell[1], cz = cell[2];
+    const float *h = hyd + (size_t)col * nF * 3;
+    const float *d = don + (size_t)col * nF * 3;
+    for (int row = blockIdx.y; row < nA && row < col; row += gridDim.y) {
+        if (hb_bonded(acc + (size_t)row * nF * 3, h, d, cx, cy, cz, maxR, cosAngle)) {
+            const unsigned k = atomicAdd(nPairs, 1u);
+            if (k < capacity) { pairs[2 * k] = row; pairs[2 * k + 1] = col; }
+        }
+    }
+}
+
+// one warp per bonded pair; grid ceil(nPairs/8), block 256
+__global__ void __launch_bounds__(256)
+hb_walk_kernel(const float *__restrict__ acc, const float *__restrict__ don, const float *__restrict__ hyd,
+               const float *__restrict__ cell, int nF, float maxR, float cosAngle, int continuous,
+               const int *__restrict__ pairs, unsigned nPairs, unsigned long long *__restrict__ counts)
+{
+    const unsigned pidx = blockIdx.x * 8u + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pidx >= nPairs) return;
+    const int row = pairs[2 * pidx], col = pairs[2 * pidx + 1];
+    const float *a = acc + (size_t)row * nF * 3;
+    const float *h = hyd + (size_t)col * nF * 3;
+    const float *d = don + (size_t)col * nF * 3;
+    for (int dt0 = 0; dt0 < nF; dt0 += 32) {
+        const int dt = dt0 + lane;
+        bool bonded = false;
+        if (dt < nF)
+            bonded = hb_bonded(a + 3 * dt, h + 3 * dt, d + 3 * dt, cell[3 * dt], cell[3 * dt + 1], cell[3 * dt + 2],
+                               maxR, cosAngle);
+        const unsigned mask = __ballot_sync(NDA_FULL_MASK, bonded);
+        const unsigned valid = (nF - dt0 >= 32) ? NDA_FULL_MASK : ((1u << (nF - dt0)) - 1u);
+        if (!continuous) {
+            if (bonded) atomicAdd(&counts[dt], 1ull);                              // :69-73, notBroken stays 1
+        } else {
+            const unsigned broken = ~mask & valid;
+            const int firstBreak = broken ? (__ffs(broken) - 1) : 32;
+            if (bonded && lane < firstBreak) atomicAdd(&counts[dt], 1ull);
+            if (broken) break;                                                      // :81-82: never counted again
+        }
+    }
+}

@@ -26,7 +26,8 @@ from .._capi import c_f32p, c_f64p, c_i32p, c_u32p, c_u64p
 
 __all__ = ["py_getWithin", "py_getDistances", "py_getRadialNbrDensity", "py_getParallelBackend",
            "py_getRadialNbrDensityGrouped", "py_getRadialNbrCounts", "py_getDistancesSum",
-           "py_getWithinBits", "py_getWithinLists", "py_setWaterDistPBC", "py_waterOrientAtSurface"]
+           "py_getWithinBits", "py_getWithinLists", "py_setWaterDistPBC", "py_waterOrientAtSurface",
+           "py_getHBCorr", "py_getHBCounts"]
 
 _CNAME = {np.dtype(np.float32): "float", np.dtype(np.float64): "double", np.dtype(np.int32): "int",
           np.dtype(np.int64): "long", np.dtype(np.uint64): "unsigned long", np.dtype(np.uint32): "unsigned int"}
@@ -269,3 +270,41 @@ def py_waterOrientAtSurface(waterO, watVec, prot, out, cellDims, minR, maxR, max
     _capi.check(L.nda_water_orient_at_surface(_p(waterO, c_f32p), waterO.shape[0], _p(watVec, c_f32p),
                                               _p(prot, c_f32p), prot.shape[0], _p(out, c_f32p), _p(cell, c_f32p),
                                               nF, float(minR), float(maxR), int(maxN)))
+
+
+# ---- SURVEY row f-4 ---------------------------------------------------------------------------------
+
+def py_getHBCorr(acceptors, nbrFrames, donors, hydrogens, cellDims, out, maxTime, step, nbrTimeOri, maxR, minAngle,
+                 continuous):
+    """Hydrogen-bond autocorrelation, ACCUMULATED into ``out`` float32 (nbrFrames,) like the reference
+    (NAMDAnalyzer/lib/libFunc.pyx:144-155, lib/openmp/src/getHydrogenBonds.cpp:9-91)."""
+    acceptors = _coords(acceptors, "acceptors")
+    donors = _coords(donors, "donors")
+    hydrogens = _coords(hydrogens, "hydrogens")
+    out = _buf(out, "out", np.float32, 1)
+    nF = int(nbrFrames)
+    for name, x in (("acceptors", acceptors), ("donors", donors), ("hydrogens", hydrogens)):
+        if x.shape[1] != nF:
+            raise ValueError("%s has %d frames, nbrFrames is %d" % (name, x.shape[1], nF))
+    if out.size != nF:
+        raise ValueError("out must have nbrFrames entries")
+    cell = _cell(cellDims, nF)
+    L = _capi.load()
+    _capi.check(L.nda_get_hb_corr(_p(acceptors, c_f32p), acceptors.shape[0], nF, _p(donors, c_f32p), donors.shape[0],
+                                  _p(hydrogens, c_f32p), hydrogens.shape[0], _p(cell, c_f32p), _p(out, c_f32p),
+                                  int(maxTime), int(step), int(nbrTimeOri), float(maxR), float(minAngle), int(continuous)))
+
+
+def py_getHBCounts(acceptors, donors, hydrogens, cellDims, maxR, minAngle, continuous):
+    """the exact integer counts behind py_getHBCorr: uint64 (nFrames,)"""
+    acceptors = _coords(acceptors, "acceptors")
+    donors = _coords(donors, "donors")
+    hydrogens = _coords(hydrogens, "hydrogens")
+    nF = acceptors.shape[1]
+    cell = _cell(cellDims, nF)
+    counts = np.zeros(nF, np.uint64)
+    L = _capi.load()
+    _capi.check(L.nda_get_hb_counts(_p(acceptors, c_f32p), acceptors.shape[0], nF, _p(donors, c_f32p), donors.shape[0],
+                                    _p(hydrogens, c_f32p), hydrogens.shape[0], _p(cell, c_f32p), _p(counts, c_u64p),
+                                    float(maxR), float(minAngle), int(continuous)))
+    return counts

@@ -147,3 +147,25 @@ def n_bins(dr, maxR):
     """outSize exactly as the reference's callers size it
     (NAMDAnalyzer/dataAnalysis/RadialDensity.py:206-208): len(np.arange(dr, maxR, dr))."""
     return int(np.arange(dr, maxR, dr).size)
+
+
+def hbond_case(n_water=400, n_frames=30, L=22.0, seed=1006, persist=0.9):
+    """Water-like triples for the H-bond autocorrelation: oxygens on a jittered
+    lattice that move slowly from frame to frame (so bonds persist for a while), one hydrogen per
+    oxygen pointing at a neighbour.  acceptors = donors = oxygens, hydrogens[i] bound to donors[i]."""
+    rng = np.random.default_rng(seed)
+    side = int(np.ceil(n_water ** (1.0 / 3.0)))
+    g = (np.arange(side) + 0.5) * (L / side)
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)[:n_water]
+    o = np.empty((n_water, n_frames, 3))
+    o[:, 0] = lat + 0.3 * rng.standard_normal((n_water, 3))
+    for f in range(1, n_frames):
+        o[:, f] = o[:, f - 1] + 0.12 * rng.standard_normal((n_water, 3))
+    u = rng.standard_normal((n_water, n_frames, 3))
+    for f in range(1, n_frames):                                  # slowly rotating O-H directions
+        u[:, f] = persist * u[:, f - 1] + (1 - persist) * u[:, f]
+    u /= np.linalg.norm(u, axis=2, keepdims=True)
+    h = o + 0.96 * u
+    cell = _cells(rng, L, n_frames)
+    return dict(acceptors=np.ascontiguousarray(o, F), donors=np.ascontiguousarray(o, F),
+                hydrogens=np.ascontiguousarray(h, F), cellDims=cell, maxR=2.8, minAngle=130.0)

@@ -306,3 +306,53 @@ void port_water_orient_at_surface(float *waterO, int sizeO, const float *watVec,
         free(closest);
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * hydrogen-bond autocorrelation.
+ * getHydrogenBonds.cpp:9-91 (getHBCorr).  acceptors [nA][nF][3], donors [nD][nF][3],
+ * hydrogens [nH][nF][3] (hydrogen col belongs to donor col).  For every pair (row, col > row)
+ * that is bonded at dt = 0 -- |h - acc| (minimum image) < maxR and the cosine between (h - acc)
+ * and the UNWRAPPED (acc - donor) below cosf(minAngle) -- counts[dt] += 1 for every later frame
+ * at which it is bonded (intermittent) or still unbroken (continuous).  The reference adds
+ * 1.0f into a float per event (:73); the port counts in uint64.  maxTime, step and nbrTimeOri
+ * are accepted and unused, as in the reference.
+ * ------------------------------------------------------------------------------------------ */
+void port_get_hb_corr(const float *acceptors, int nA, int nFrames, const float *donors, int nD,
+                      const float *hydrogens, int nH, const float *cellDims, uint64_t *counts,
+                      float maxR, float minAngle, int continuous)
+{
+    (void)nH;
+    const float cosAngle = cosf(minAngle);                                       /* :16 */
+    #pragma omp parallel
+    {
+        uint64_t *local = (uint64_t *)calloc((size_t)(nFrames > 0 ? nFrames : 1), sizeof(uint64_t));
+        #pragma omp for schedule(dynamic, 4)
+        for (int row = 0; row < nA; ++row) {                                     /* :23 */
+            for (int col = row + 1; col < nD; ++col) {                           /* :25 */
+                int notBroken = 1;
+                for (int dt = 0; dt < nFrames; ++dt) {                           /* :30 */
+                    const float cx = cellDims[3 * dt], cy = cellDims[3 * dt + 1], cz = cellDims[3 * dt + 2];
+                    const float *a = acceptors + 3 * ((size_t)nFrames * row + dt);
+                    const float *h = hydrogens + 3 * ((size_t)nFrames * col + dt);
+                    const float *d = donors + 3 * ((size_t)nFrames * col + dt);
+                    float hx = h[0] - a[0], hy = h[1] - a[1], hz = h[2] - a[2]; /* :37-44 */
+                    hx = wrap1(hx, cx); hy = wrap1(hy, cy); hz = wrap1(hz, cz);  /* :47-49 */
+                    const float ax = a[0] - d[0], ay = a[1] - d[1], az = a[2] - d[2];   /* :52-57, not wrapped */
+                    const float hh = norm2(hx, hy, hz);
+                    const float dist = sqrtf(hh);                                /* :60 */
+                    float angle = (hx * ax + hy * ay) + hz * az;                 /* :63 */
+                    angle /= (sqrtf(hh) * sqrtf(norm2(ax, ay, az)));            /* :64-65 */
+                    if (dist < maxR && angle < cosAngle) {                       /* :67 */
+                        local[dt] += (uint64_t)notBroken;                        /* :69-73 (t0 = 1 here) */
+                    } else {
+                        if (dt == 0) break;                                      /* :78-79 */
+                        if (continuous == 1) notBroken = 0;                      /* :81-82 */
+                    }
+                }
+            }
+        }
+        #pragma omp critical
+        for (int dt = 0; dt < nFrames; ++dt) counts[dt] += local[dt];
+        free(local);
+    }
+}

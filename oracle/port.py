@@ -44,6 +44,9 @@ def lib():
         L.port_water_orient_at_surface.argtypes = [_f32p, ctypes.c_int, _f32p, _f32p, ctypes.c_int, _f32p,
                                                    ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int]
         L.port_water_orient_at_surface.restype = None
+        L.port_get_hb_corr.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, _f32p, ctypes.c_int, _f32p, ctypes.c_int,
+                                       _f32p, _u64p, ctypes.c_float, ctypes.c_float, ctypes.c_int]
+        L.port_get_hb_corr.restype = None
         L.port_pair_r2.argtypes = [_f32p, _f32p, _f32p]
         L.port_pair_r2.restype = ctypes.c_float
         L.port_num_threads.restype = ctypes.c_int
@@ -141,3 +144,18 @@ def water_orient_at_surface(waterO, watVec, prot, cellDims, minR, maxR, maxN):
                                        prot.ctypes.data_as(_f32p), prot.shape[0], cell.ctypes.data_as(_f32p),
                                        w.shape[1], ctypes.c_float(minR), ctypes.c_float(maxR), int(maxN))
     return w
+
+
+def hb_corr(acceptors, donors, hydrogens, cellDims, maxR, minAngle, continuous):
+    """-> uint64 [nFrames] H-bond autocorrelation counts (getHydrogenBonds.cpp:9-91)"""
+    a = np.ascontiguousarray(acceptors, np.float32)
+    d = np.ascontiguousarray(donors, np.float32)
+    h = np.ascontiguousarray(hydrogens, np.float32)
+    cell = np.ascontiguousarray(cellDims, np.float32)
+    nF = a.shape[1]
+    counts = np.zeros(nF, np.uint64)
+    lib().port_get_hb_corr(a.ctypes.data_as(_f32p), a.shape[0], nF, d.ctypes.data_as(_f32p), d.shape[0],
+                           h.ctypes.data_as(_f32p), h.shape[0], cell.ctypes.data_as(_f32p),
+                           counts.ctypes.data_as(_u64p), ctypes.c_float(maxR), ctypes.c_float(minAngle),
+                           int(continuous))
+    return counts

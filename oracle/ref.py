@@ -31,6 +31,10 @@ _SYMS = {
                             [_f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p,
                              ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float]),
     "getParallelBackend": ("_Z18getParallelBackendv", []),
+    # SURVEY row f-4 (lib/openmp/src/getHydrogenBonds.cpp)
+    "getHBCorr": ("_Z9getHBCorrPfiiS_iS_iS_S_iiiffi",
+                  [_f32p, ctypes.c_int, ctypes.c_int, _f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p, _f32p,
+                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int]),
     # SURVEY row f-3 (lib/openmp/src/setWaterDistPBC.cpp, waterOrientAtSurface.cpp)
     "setWaterDistPBC": ("_Z15setWaterDistPBCPfiS_iS_ii",
                         [_f32p, ctypes.c_int, _f32p, ctypes.c_int, _f32p, ctypes.c_int, ctypes.c_int]),
@@ -190,6 +194,23 @@ class RefLib:
                                             cell.ctypes.data_as(_f32p), w.shape[1], ctypes.c_float(minR),
                                             ctypes.c_float(maxR), int(maxN))
         return w
+
+    # -- row f-4 -----------------------------------------------------------------------
+    def hb_corr(self, acceptors, donors, hydrogens, cellDims, maxR, minAngle, continuous,
+                maxTime=100, step=1, nbrTimeOri=25):
+        """-> float32 [nFrames] as the reference accumulates it (exact integers below 2**24)"""
+        a = np.ascontiguousarray(acceptors, np.float32)
+        d = np.ascontiguousarray(donors, np.float32)
+        h = np.ascontiguousarray(hydrogens, np.float32)
+        cell = np.ascontiguousarray(cellDims, np.float32)
+        nF = a.shape[1]
+        out = np.zeros(nF, np.float32)
+        with self._quiet():
+            self.fn["getHBCorr"](a.ctypes.data_as(_f32p), a.shape[0], nF, d.ctypes.data_as(_f32p), d.shape[0],
+                                 h.ctypes.data_as(_f32p), h.shape[0], cell.ctypes.data_as(_f32p),
+                                 out.ctypes.data_as(_f32p), int(maxTime), int(step), int(nbrTimeOri),
+                                 ctypes.c_float(maxR), ctypes.c_float(minAngle), int(continuous))
+        return out
 
     # -- raw multi-frame calls, as the reference's callers make them (for timing) ---
     def raw_rdf(self, sel1, sel2, out, cellDims, sameSel, maxR, dr):

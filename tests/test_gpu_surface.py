@@ -79,3 +79,34 @@ def test_surface_argument_errors():
         plf.py_waterOrientAtSurface(w, w.copy(), p, np.zeros((1, 1), np.float32), cell, 0.0, 5.0, 17)
     with pytest.raises(ValueError):
         plf.py_waterOrientAtSurface(w, w[:3].copy(), p, np.zeros((1, 1), np.float32), cell, 0.0, 5.0, 3)
+
+
+# ---------------------------------------------------------------- SURVEY row f-4 (H-bond autocorrelation)
+
+@pytest.mark.parametrize("continuous", [0, 1])
+@pytest.mark.parametrize("n,nF", [(400, 30), (1500, 70), (37, 33)])
+def test_hb_corr(n, nF, continuous):
+    c = synth.hbond_case(n_water=n, n_frames=nF, seed=1006 + n)
+    args = (c["acceptors"], c["donors"], c["hydrogens"], c["cellDims"], c["maxR"], c["minAngle"], continuous)
+    want = port.hb_corr(*args)
+    got = plf.py_getHBCounts(*args)
+    assert np.array_equal(got, want)
+    # the reference-shaped operator accumulates into out (getHydrogenBonds.cpp:73)
+    out = np.full(nF, 2.0, np.float32)
+    plf.py_getHBCorr(c["acceptors"], nF, c["donors"], c["hydrogens"], c["cellDims"], out, 100, 1, 25,
+                     c["maxR"], c["minAngle"], continuous)
+    assert np.array_equal(out, (want + 2).astype(np.float32))
+    assert want[0] > 0 or n < 100
+
+
+def test_hb_corr_different_selections_and_dense_list():
+    """acceptors != donors, and a maxR so large that the frame-0 pair list overflows its first guess"""
+    c = synth.hbond_case(n_water=300, n_frames=12, seed=99)
+    acc = np.ascontiguousarray(c["acceptors"][:170])
+    don = np.ascontiguousarray(c["donors"][40:])
+    hyd = np.ascontiguousarray(c["hydrogens"][40:])
+    for maxR, ang in ((2.8, 130.0), (60.0, 1.0)):
+        for cont in (0, 1):
+            want = port.hb_corr(acc, don, hyd, c["cellDims"], maxR, ang, cont)
+            got = plf.py_getHBCounts(acc, don, hyd, c["cellDims"], maxR, ang, cont)
+            assert np.array_equal(got, want), (maxR, cont)

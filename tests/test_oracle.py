@@ -206,3 +206,18 @@ def test_port_water_orient_equals_reference(maxN):
         want = R.water_orient_at_surface(wO, vec, prot, cell, 0.0, 5.0, maxN)
     assert np.array_equal(got, want, equal_nan=True)
     assert 0 < want[..., 1].sum() < want[..., 1].size          # some waters at the surface, some not
+
+
+# ---------------------------------------------------------------- SURVEY row f-4 (H-bond autocorrelation)
+
+@pytest.mark.skipif(not ref.available("strict"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("continuous", [0, 1])
+def test_port_hb_corr_equals_reference(continuous):
+    R = ref.RefLib("strict")
+    c = synth.hbond_case()
+    got = port.hb_corr(c["acceptors"], c["donors"], c["hydrogens"], c["cellDims"], c["maxR"], c["minAngle"], continuous)
+    want = R.hb_corr(c["acceptors"], c["donors"], c["hydrogens"], c["cellDims"], c["maxR"], c["minAngle"], continuous)
+    assert np.array_equal(got.astype(np.float32), want)
+    assert want[0] > 20 and want[-1] < want[0]               # bonds exist at t = 0 and decay
+    if continuous:
+        assert np.all(np.diff(want) <= 0)                    # an unbroken count can only go down

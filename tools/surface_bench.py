@@ -49,3 +49,18 @@ if ref.available("fast"):
     R.water_orient_at_surface(wO[:, :s], vec[:, :s], prot[:, :s], cell[:s], 0.0, 5.0, 5)
     dt = time.perf_counter() - t0
     print("reference CPU waterOrientAtSurface (%d threads), %d frames: %.3e pairs/s" % (os.cpu_count(), s, 7923.0 * 1231 * s / dt))
+
+# ---- row f-4: H-bond autocorrelation, 4000 water-like triples x 200 frames
+from oracle import port
+hb = synth.hbond_case(n_water=4000, n_frames=200, L=49.0)
+args = (hb["acceptors"], hb["donors"], hb["hydrogens"], hb["cellDims"], hb["maxR"], hb["minAngle"], 1)
+plf.py_getHBCounts(*args)
+t0 = time.perf_counter()
+cnt = plf.py_getHBCounts(*args)
+dt = time.perf_counter() - t0
+st = (ctypes.c_double * 4)()
+lib.nda_last_stats(st)
+print("getHBCorr continuous, 4000 x 4000 / 2 pairs at t0, %d bonded, 200 frames: e2e %.2f ms, walk kernel %.3f ms" % (int(st[1]), dt * 1e3, kms()))
+t0 = time.perf_counter()
+w = port.hb_corr(*args)
+print("  C restatement on the CPU (%d threads): %.1f ms; equal: %s" % (port.num_threads(), (time.perf_counter() - t0) * 1e3, np.array_equal(w, cnt)))
