@@ -128,6 +128,54 @@ def cpu_within_sample(cfg, frames, threads, repeats=1):
     return pairs / dt, dt
 
 
+def legacy_gpu_sample():
+    """The reference's OWN CUDA build (lib/cuda/src/*.cu, unmodified, compiled for sm_100a into
+    oracle/_ref/libref_cuda.so) on bounded samples: the recompiled legacy kernels this repo is meant
+    to beat.  End to end like the reference runs them (cudaMalloc + blocking copies + one launch and
+    device sync per frame + cudaFree).  Not a parity oracle: the two reference builds disagree."""
+    from namdanalyzer_b200 import synth
+    from oracle import ref
+    if not ref.available("cuda"):
+        return {"unavailable": "oracle/_ref/libref_cuda.so not built"}
+    R = ref.RefLib("cuda")
+    out = {}
+    nF = 100
+    c = synth.config2(n_frames=nF)
+    o = np.zeros(c["allAtoms"].shape[:2], np.int32)
+    f32p, i32p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)
+
+    def within():
+        with R._quiet():
+            R.fn["getWithin"](c["allAtoms"].ctypes.data_as(f32p), c["allAtoms"].shape[0], nF,
+                              c["refSel"].ctypes.data_as(i32p), c["refSel"].size,
+                              c["outSel"].ctypes.data_as(i32p), c["outSel"].size,
+                              o.ctypes.data_as(i32p), c["cellDims"].ctypes.data_as(f32p), ctypes.c_float(3.0))
+    within()
+    t0 = time.perf_counter()
+    within()
+    dt = time.perf_counter() - t0
+    out["within_config2"] = {"frames": nF, "pairs_per_s": 1231.0 * 7923 * nF / dt, "ms": dt * 1e3}
+    c5 = synth.config5(n_side=32, n_frames=2)                 # 32 768 atoms: the legacy kernel is O(n^2) global atomics
+    d = np.zeros(149, np.float32)
+    n = c5["sel1"].shape[0]
+
+    def rdf():
+        with R._quiet():
+            R.fn["getRadialNbrDensity"](c5["sel1"].ctypes.data_as(f32p), n, c5["sel1"].ctypes.data_as(f32p), n,
+                                        d.ctypes.data_as(f32p), 149, c5["cellDims"].ctypes.data_as(f32p), 2, 1,
+                                        ctypes.c_float(15.0), ctypes.c_float(0.1))
+    rdf()
+    t0 = time.perf_counter()
+    rdf()
+    dt = time.perf_counter() - t0
+    # the legacy kernel ignores sameSel and evaluates the full n x n matrix (SURVEY B-6)
+    out["rdf_32768_atoms"] = {"frames": 2, "pairs_evaluated_per_s": float(n) * n * 2 / dt,
+                              "unique_pairs_per_s": 0.5 * n * (n - 1.0) * 2 / dt, "ms": dt * 1e3}
+    out["note"] = ("reference CUDA build recompiled for sm_100a, end to end from host arrays "
+                   "(its only mode); semantics differ from the OpenMP oracle (SURVEY Appendix B)")
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -325,6 +373,10 @@ def run_ours(args, rank, world, local_rank):
         while dt < 8.0 and reps < 64:                       # bounded sample: ~10-30 s of CPU work
             reps *= 2
             rate, dt = cpu_within_sample(scfg, range(sample), threads, reps)
+        try:
+            line["legacy_gpu"] = legacy_gpu_sample()
+        except Exception as e:                               # never let the optional arm break the bench line
+            line["legacy_gpu"] = {"unavailable": repr(e)[:200]}
         line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": threads, "kind": "reference",
                                 "sample": "reference OpenMP getWithin (oracle/_ref/libref_fast.so, shipped flags), "
                                           "one frame per call, %d frames x %d repeats of config 2 (%.1f s)"

@@ -53,14 +53,18 @@ def available(kind="strict"):
 
 
 class RefLib:
-    """One compiled build of the reference ('strict' = parity, 'fast' = shipped flags)."""
+    """One compiled build of the reference ('strict' = parity, 'fast' = shipped flags,
+    'cuda' = the reference's legacy CUDA build recompiled for sm_100a, bench comparison only)."""
 
     def __init__(self, kind="strict"):
         self.kind = kind
         self.lib = ctypes.CDLL(lib_path(kind))
         self.fn = {}
         for name, (sym, argtypes) in _SYMS.items():
-            f = getattr(self.lib, sym)
+            try:
+                f = getattr(self.lib, sym)
+            except AttributeError:           # e.g. the legacy CUDA build holds the three hot-path functions only
+                continue
             f.argtypes = argtypes
             f.restype = ctypes.c_int if name == "getParallelBackend" else None
             self.fn[name] = f
