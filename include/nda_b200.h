@@ -138,6 +138,20 @@ int nda_get_hb_counts(const float *acceptors, int size_acceptors, int nbrFrames,
                       const float *donors, int size_donors, const float *hydrogens, int size_hydrogens,
                       const float *cellDims, uint64_t *counts, float maxR, float minAngle, int continuous);
 
+/* ---- DCD ingest (host I/O feeding the path) ---------------------------- */
+
+/* lib/libFunc.h:21-28 getDCDCoor / lib/common/src/dcdReader.cpp:28-98.  Reads the records of the
+ * requested frames / axes and gathers the selected atoms into outArr float32
+ * [selAtomsSize][nbrFrames][nbrDims].  Returns the reference's codes: 0, -1 (cannot open),
+ * -2 (bad index / seek), -3 (short read).  Frames are read by several host threads (pread). */
+int nda_dcd_get_coor(const char *fileName, const int *frames, int nbrFrames, int nbrAtoms,
+                     const int *selAtoms, int selAtomsSize, const int *dims, int nbrDims, int cell,
+                     const long long *startPos, float *outArr, char byteorder);
+/* lib/libFunc.h:30-31 getDCDCell / lib/common/src/dcdCellReader.cpp:26-70: the six unit-cell doubles of
+ * each requested frame into outArr float64 [nbrFrames][6]. */
+int nda_dcd_get_cell(const char *fileName, const int *frames, int nbrFrames, const long long *startPos,
+                     double *outArr, char byteorder);
+
 /* ---- device-pointer entry points (inputs resident in HBM, stream-ordered) ---------- */
 
 /* d_counts uint64 [nGroups][outSize] is ACCUMULATED into (zero it first).

@@ -15,7 +15,7 @@ import types
 __version__ = "0.1.0"
 
 _PAIR_OPS = ("py_getWithin", "py_getDistances", "py_getRadialNbrDensity", "py_getParallelBackend",
-             "py_setWaterDistPBC", "py_waterOrientAtSurface", "py_getHBCorr")
+             "py_setWaterDistPBC", "py_waterOrientAtSurface", "py_getHBCorr", "py_getDCDCoor", "py_getDCDCell")
 
 
 def install():

@@ -43,6 +43,10 @@ SIGNATURES = {
                                 c_float, c_float, c_int]),
     "nda_get_hb_counts": (c_int, [c_f32p, c_int, c_int, c_f32p, c_int, c_f32p, c_int, c_f32p, c_u64p, c_float, c_float,
                                   c_int]),
+    "nda_dcd_get_coor": (c_int, [ctypes.c_char_p, c_i32p, c_int, c_int, c_i32p, c_int, c_i32p, c_int, c_int,
+                                 ctypes.POINTER(ctypes.c_longlong), c_f32p, ctypes.c_char]),
+    "nda_dcd_get_cell": (c_int, [ctypes.c_char_p, c_i32p, c_int, ctypes.POINTER(ctypes.c_longlong), c_f64p,
+                                 ctypes.c_char]),
     "nda_dev_radial_nbr_counts": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                           c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "nda_dev_within": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,

@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <string.h>
 #include <math.h>
 #include <atomic>
@@ -1243,6 +1245,84 @@ int nda_get_hb_corr(const float *acceptors, int nA, int nF, const float *donors,
     if (rc) return rc;
     for (int dt = 0; dt < nF; ++dt) out[dt] += (float)cnt[dt];   // the reference ACCUMULATES into out (:73)
     return NDA_OK;
+}
+
+// ---- DCD ingest ------------------------------------------------------------------
+// Drop-ins for lib/common/src/dcdReader.cpp:28-98 (getDCDCoor) and dcdCellReader.cpp:26-70
+// (getDCDCell), which do not compile outside MSVC (_fseeki64, undeclared lastAtomIdx) and byte-swap
+// nothing.  Same arguments, same error codes (0, -1 open, -2 seek/out of range, -3 short read), same
+// output layout; pread() instead of a shared FILE* so the frames are read by several host threads,
+// and a real byte swap when the file's endianness differs from the host's.
+static inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
+
+int nda_dcd_get_coor(const char *fileName, const int *frames, int nbrFrames, int nbrAtoms,
+                     const int *selAtoms, int selAtomsSize, const int *dims, int nbrDims, int cell,
+                     const long long *startPos, float *outArr, char byteorder)
+{
+    if (!fileName || !frames || !selAtoms || !dims || !startPos || !outArr) return -1;
+    if (nbrAtoms <= 0 || nbrFrames < 0 || selAtomsSize < 0 || nbrDims < 0) return -2;
+    for (int i = 0; i < selAtomsSize; ++i) if (selAtoms[i] < 0 || selAtoms[i] >= nbrAtoms) return -2;
+    for (int d = 0; d < nbrDims; ++d) if (dims[d] < 0 || dims[d] > 2) return -2;
+    const int fd = open(fileName, O_RDONLY);
+    if (fd < 0) return -1;
+    const uint16_t probe = 1;
+    const char sys = *reinterpret_cast<const char *>(&probe) ? '<' : '>';
+    const bool swap = (byteorder == '<' || byteorder == '>') && byteorder != sys;
+    int err = 0;
+    #pragma omp parallel num_threads(g_host_threads > 0 ? g_host_threads : 1)
+    {
+        std::vector<uint32_t> rec((size_t)nbrAtoms);
+        #pragma omp for schedule(dynamic, 1)
+        for (int frameId = 0; frameId < nbrFrames; ++frameId) {
+            const int frame = frames[frameId];
+            for (int dimId = 0; dimId < nbrDims; ++dimId) {
+                // dcdReader.cpp:66-68: record of axis dims[dimId] of this frame
+                const long long pos = startPos[frame] + (long long)dims[dimId] * (4LL * nbrAtoms + 8) + (cell ? 60 : 4);
+                size_t got = 0;
+                const size_t want = 4u * (size_t)nbrAtoms;
+                while (got < want) {
+                    const ssize_t r = pread(fd, reinterpret_cast<char *>(rec.data()) + got, want - got, pos + (long long)got);
+                    if (r <= 0) break;
+                    got += (size_t)r;
+                }
+                if (got < want) {
+                    #pragma omp atomic write
+                    err = (pos < 0) ? -2 : -3;
+                    continue;
+                }
+                for (int a = 0; a < selAtomsSize; ++a) {        // dcdReader.cpp:88-89
+                    uint32_t v = rec[selAtoms[a]];
+                    if (swap) v = bswap32(v);
+                    memcpy(&outArr[(size_t)nbrDims * nbrFrames * a + (size_t)nbrDims * frameId + dimId], &v, 4);
+                }
+            }
+        }
+    }
+    close(fd);
+    return err;
+}
+
+int nda_dcd_get_cell(const char *fileName, const int *frames, int nbrFrames, const long long *startPos,
+                     double *outArr, char byteorder)
+{
+    if (!fileName || !frames || !startPos || !outArr) return -1;
+    const int fd = open(fileName, O_RDONLY);
+    if (fd < 0) return -1;
+    const uint16_t probe = 1;
+    const char sys = *reinterpret_cast<const char *>(&probe) ? '<' : '>';
+    const bool swap = (byteorder == '<' || byteorder == '>') && byteorder != sys;
+    int err = 0;
+    for (int frameId = 0; frameId < nbrFrames; ++frameId) {
+        uint64_t rec[6];
+        const ssize_t r = pread(fd, rec, sizeof rec, startPos[frames[frameId]] + 4);   // dcdCellReader.cpp:44
+        if (r != (ssize_t)sizeof rec) { err = -2; break; }
+        for (int i = 0; i < 6; ++i) {
+            uint64_t v = swap ? __builtin_bswap64(rec[i]) : rec[i];
+            memcpy(&outArr[6 * (size_t)frameId + i], &v, 8);
+        }
+    }
+    close(fd);
+    return err;
 }
 
 // ---- measurement / test support --------------------------------------------------------------

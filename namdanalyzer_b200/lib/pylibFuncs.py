@@ -27,7 +27,7 @@ from .._capi import c_f32p, c_f64p, c_i32p, c_u32p, c_u64p
 __all__ = ["py_getWithin", "py_getDistances", "py_getRadialNbrDensity", "py_getParallelBackend",
            "py_getRadialNbrDensityGrouped", "py_getRadialNbrCounts", "py_getDistancesSum",
            "py_getWithinBits", "py_getWithinLists", "py_setWaterDistPBC", "py_waterOrientAtSurface",
-           "py_getHBCorr", "py_getHBCounts"]
+           "py_getHBCorr", "py_getHBCounts", "py_getDCDCoor", "py_getDCDCell"]
 
 _CNAME = {np.dtype(np.float32): "float", np.dtype(np.float64): "double", np.dtype(np.int32): "int",
           np.dtype(np.int64): "long", np.dtype(np.uint64): "unsigned long", np.dtype(np.uint32): "unsigned int"}
@@ -308,3 +308,51 @@ def py_getHBCounts(acceptors, donors, hydrogens, cellDims, maxR, minAngle, conti
                                     _p(hydrogens, c_f32p), hydrogens.shape[0], _p(cell, c_f32p), _p(counts, c_u64p),
                                     float(maxR), float(minAngle), int(continuous)))
     return counts
+
+
+# ---- DCD ingest ---------------------------------------------------------------------
+
+def _byteorder_char(byteorder):
+    if isinstance(byteorder, int):
+        byteorder = chr(byteorder)
+    if isinstance(byteorder, (bytes, bytearray)):
+        byteorder = byteorder.decode()
+    return byteorder.encode()[:1] or b"<"
+
+
+def py_getDCDCoor(fileName, frames, nbrAtoms, selAtoms, dims, cell, startPos, outArr, byteorder):
+    """Reads DCD coordinate records into ``outArr`` float32 (len(selAtoms), len(frames), len(dims));
+    returns the reference's error code (NAMDAnalyzer/lib/libFunc.pyx:61-75,
+    lib/common/src/dcdReader.cpp:28-98 -- which does not compile on Linux)."""
+    frames = _buf(frames, "frames", np.int32, 1)
+    selAtoms = _buf(selAtoms, "selAtoms", np.int32, 1)
+    dims = _buf(dims, "dims", np.int32, 1)
+    startPos = _buf(startPos, "startPos", np.int64, 1)
+    outArr = _buf(outArr, "outArr", np.float32, 3)
+    if outArr.shape != (selAtoms.size, frames.size, dims.size):
+        raise ValueError("outArr must have shape (len(selAtoms), len(frames), len(dims))")
+    if frames.size and (frames.min() < 0 or frames.max() >= startPos.size):
+        return -2
+    name = bytes(fileName) if isinstance(fileName, (bytes, bytearray)) else str(fileName).encode()
+    L = _capi.load()
+    return int(L.nda_dcd_get_coor(name, _p(frames, c_i32p), frames.size, int(nbrAtoms), _p(selAtoms, c_i32p),
+                                  selAtoms.size, _p(dims, c_i32p), dims.size, int(bool(cell)),
+                                  startPos.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), _p(outArr, c_f32p),
+                                  _byteorder_char(byteorder)))
+
+
+def py_getDCDCell(fileName, frames, startPos, outArr, byteorder):
+    """Reads the six unit-cell doubles of each frame into ``outArr`` float64 (len(frames), 6)
+    (NAMDAnalyzer/lib/libFunc.pyx:82-95, lib/common/src/dcdCellReader.cpp:26-70)."""
+    frames = _buf(frames, "frames", np.int32, 1)
+    startPos = _buf(startPos, "startPos", np.int64, 1)
+    outArr = _buf(outArr, "outArr", np.float64, 2)
+    if outArr.shape != (frames.size, 6):
+        raise ValueError("outArr must have shape (len(frames), 6)")
+    if frames.size and (frames.min() < 0 or frames.max() >= startPos.size):
+        return -2
+    name = bytes(fileName) if isinstance(fileName, (bytes, bytearray)) else str(fileName).encode()
+    L = _capi.load()
+    return int(L.nda_dcd_get_cell(name, _p(frames, c_i32p), frames.size,
+                                  startPos.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)), _p(outArr, c_f64p),
+                                  _byteorder_char(byteorder)))

@@ -183,3 +183,19 @@ def test_resident_trajectory_matches_host_operators():
     ds = T.distances(r[:12])
     assert np.array_equal(ds, ds.T) and np.all(np.diag(ds) == 0)
     assert np.max(np.abs(ds - d[:, :12]) / np.maximum(d[:, :12], 1e-30)) <= 1e-6
+
+
+def test_dcd_file_to_resident_trajectory(tmp_path):
+    """row f-2 end to end: DCD file -> threaded reader -> HBM -> within, against the oracle"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_dcd_cpu import write_dcd
+    from namdanalyzer_b200.dataParsers.dcdReader import DCDFile
+    c = synth.config2(n_frames=4, n_water=500)
+    cell6 = np.zeros((4, 6))
+    cell6[:, [0, 2, 5]] = c["cellDims"]
+    p = str(tmp_path / "traj.dcd")
+    write_dcd(p, c["allAtoms"], cell6, "<")
+    T = DCDFile(p).resident()
+    want = port.within(c["allAtoms"], c["refSel"], c["outSel"], c["cellDims"], 3.0)
+    assert np.array_equal(T.within(c["refSel"], c["outSel"], 3.0), want)
