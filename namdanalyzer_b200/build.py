@@ -11,7 +11,7 @@ SRC_DIR = os.path.join(_HERE, "csrc")
 INC_DIR = os.path.join(os.path.dirname(_HERE), "include")
 OUT = os.path.join(_HERE, "lib", "libnda_b200.so")
 SOURCES = ["nda_b200.cu"]
-DEPS = ["nda_b200.cu", "nda_kernels.cuh", "nda_device.cuh", "nda_surface.cuh"]
+DEPS = ["nda_b200.cu", "nda_kernels.cuh", "nda_device.cuh", "nda_surface.cuh", "nda_tc.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-fopenmp", "-lgomp"]
 

@@ -18,6 +18,7 @@
 
 #include "../../include/nda_b200.h"
 #include "nda_kernels.cuh"
+#include "nda_tc.cuh"
 #include "nda_surface.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -96,11 +97,12 @@ struct Ctx {
     // two LANES = two compute streams with their own pass buffers: consecutive frame chunks of the
     // host entry points run on alternating lanes so the head of chunk k+1's persistent kernel fills
     // the tail of chunk k's.  ctl: [0..1] work counter (u32 x2), stats u64 x2 at +16.
-    struct Lane { DevBuf packA, packB, packAw, packBw, fp, maxAbs, ctl; cudaStream_t stream = nullptr; };
+    struct Lane { DevBuf packA, packB, packAw, packBw, fp, maxAbs, ctl, embA, embB, thrDot; cudaStream_t stream = nullptr; };
     Lane lane[2];
     cudaEvent_t evSetup = nullptr, evLaneJoin = nullptr;
     DevBuf raw[2][2];                             // [array][double buffer] raw coordinate chunks
     DevBuf cell, idx1, idx2, gid, counts, bits, sum;
+    std::vector<float> hostCell;                  // cell edges read back for the filter choice (device API)
     void *stage[2] = {nullptr, nullptr};          // pinned staging for pageable inputs
     size_t stageCap[2] = {0, 0};
     cudaError_t stage_reserve(int b, size_t bytes)
@@ -209,6 +211,43 @@ static int launch_pack(Ctx &c, cudaStream_t st, const float *src, int nFtot, con
     return NDA_OK;
 }
 
+// NDA_FILTER=tc (default): the tensor-core filter (nda_tc.cuh) whenever every frame of the call is
+// eligible, the packed-FP32 fold2 filter otherwise.  NDA_FILTER=rint|fold|fold2|fold2a0..3 forces an
+// FP32 filter.
+static bool filter_tc_requested()
+{
+    const char *e = getenv("NDA_FILTER");
+    return !e || !*e || !strcmp(e, "tc");
+}
+
+// Host-side mirror of prep_tc_kernel with a 10 % margin: true when no frame of [fb, fe) would be
+// sent to the all-exact path by the tensor-core filter.  T = in-range limit on r2.
+static bool tc_frames_eligible(const float *cell, int fb, int fe, double T)
+{
+    const double k = 0.15915494309189535;
+    for (int f = fb; f < fe; ++f) {
+        const double cx = fabs((double)cell[3 * (size_t)f]), cy = fabs((double)cell[3 * (size_t)f + 1]), cz = fabs((double)cell[3 * (size_t)f + 2]);
+        if (!(cx > 0.0 && cy > 0.0 && cz > 0.0) || !(cx < 1.0e30 && cy < 1.0e30 && cz < 1.0e30)) return false;
+        const double P = (cx * cx + cy * cy + cz * cz) * k * k;
+        const double Eb = P * (4.8828125e-04 * 1.01 + 3.814697265625e-06) + 1.0e-6;
+        const double thr = T * 1.001 + 1.0e-6;
+        if (!(2.5 * Eb * 1.1 <= thr && thr * 1.1 <= P)) return false;
+    }
+    return T > 0.0;
+}
+
+// cell edges of frames [fb, fe) on the host: the caller's host array when there is one, else a
+// read-back of the device array (device API; 12 bytes per frame)
+static int host_cell_view(Ctx &c, cudaStream_t st, const float *h_cell, const float *d_cell, int fb, int fe, const float **out)
+{
+    if (h_cell) { *out = h_cell; return NDA_OK; }
+    c.hostCell.resize((size_t)3 * fe);
+    CK(cudaMemcpyAsync(c.hostCell.data() + 3 * (size_t)fb, d_cell + 3 * (size_t)fb, (size_t)(fe - fb) * 12, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *out = c.hostCell.data();
+    return NDA_OK;
+}
+
 // which FP32 filter the pair kernels run (NDA_FILTER=rint|fold|fold2, default fold2)
 static int filter_kind()
 {
@@ -229,15 +268,193 @@ static int frames_per_pass(size_t bytesPerFrame, int nF)
     return (int)f;
 }
 
+// ------------------------------------------------------------------------------------------
+// tensor-core filter drivers (nda_tc.cuh): pack -> embed -> prep -> one persistent kernel per pass
+// ------------------------------------------------------------------------------------------
+static int launch_embed(cudaStream_t st, const float4 *packed, int nPad, int nFc, const float *cell, int f0,
+                        __half *E, int roleA)
+{
+    dim3 grid(nPad / TC_BLK, std::min(nFc, 65535));
+    embed_kernel<<<grid, 128, 0, st>>>(packed, nPad, nFc, cell, f0, E, roleA);
+    LAUNCHED();
+    return NDA_OK;
+}
+
+static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, int n1, const float *d_sel2, int n2,
+                      const int *d_gid, int nGroups, unsigned long long *d_counts, int nBins,
+                      const float *d_cell, int nF, int fb, int fe, int sameSel, float dr,
+                      const int *d_idx1, const int *d_idx2, double T)
+{
+    const bool grouped = d_gid != nullptr;
+    const size_t H = (size_t)nGroups * nBins;
+    const size_t base = tc_smem_base();
+    const size_t budget = c.smemOptin > base ? c.smemOptin - base : 0;
+    int copies = (int)std::min<size_t>(TC_EPI_WARPS, budget / (H * 4));
+    if (copies < 1)
+        return fail(NDA_ERR_ARG, "nGroups*outSize = %zu histogram cells do not fit in shared memory (max %zu)", H, budget / 4);
+    const size_t smem = base + (size_t)copies * H * 4;
+    const int n1Pad = round_up(n1, TC_ATILE);
+    const int n2Pad = sameSel ? n1Pad : round_up(n2, TC_BLK);
+    const size_t bytesPerFrame = (size_t)n1Pad * (16 + 32) + (sameSel ? (size_t)n1Pad * 32 : (size_t)n2Pad * (16 + 32));
+    const int pass = frames_per_pass(bytesPerFrame, fe - fb);
+
+    CK(L.packA.reserve((size_t)n1Pad * pass * sizeof(float4)));
+    if (!sameSel) CK(L.packB.reserve((size_t)n2Pad * pass * sizeof(float4)));
+    CK(L.embA.reserve((size_t)n1Pad * pass * 32));
+    CK(L.embB.reserve((size_t)n2Pad * pass * 32));
+    CK(L.fp.reserve((size_t)pass * sizeof(FrameParams)));
+    CK(L.thrDot.reserve((size_t)pass * sizeof(float)));
+    CK(L.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
+    unsigned long long *stats = reinterpret_cast<unsigned long long *>(L.ctl.as<unsigned char>() + 16);
+
+    RdfTcArgs a;
+    TcGeom &g = a.g;
+    g.n1 = n1; g.n1Pad = n1Pad; g.n2 = n2; g.n2Pad = n2Pad;
+    g.nATiles = n1Pad / TC_ATILE;
+    g.nBBlocks = (n2 + TC_BLK - 1) / TC_BLK;
+    g.sameSel = sameSel ? 1 : 0;
+    g.stats = stats;
+    a.counts = d_counts; a.nBins = nBins; a.nGroups = nGroups; a.histCopies = copies;
+    a.dr = dr;
+    a.fastStrict = getenv("NDA_STRICT_SLOW") ? 0 : 1;
+    {
+        // B blocks per work item: >= 16 items per CTA for the static round-robin to balance the
+        // triangular (sameSel) workload, but an item stays >= 4 blocks (~2.6e5 pairs)
+        const long long target = 16LL * c.numSMs;
+        const long long rows = (long long)pass * g.nATiles;
+        const long long chunksWanted = std::max<long long>(1, (target + rows - 1) / rows);
+        long long cb = (g.nBBlocks + chunksWanted - 1) / chunksWanted;
+        cb = std::max<long long>(4, std::min<long long>(256, cb));
+        g.chunkBlocks = (int)std::min<long long>(cb, g.nBBlocks);
+        g.nBChunks = (g.nBBlocks + g.chunkBlocks - 1) / g.chunkBlocks;
+    }
+    const void *kfn = grouped ? (const void *)rdf_tc_kernel<true> : (const void *)rdf_tc_kernel<false>;
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    for (int f0 = fb; f0 < fe; f0 += pass) {
+        const int nFc = std::min(pass, fe - f0);
+        CK(cudaMemsetAsync(L.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
+        int rc = launch_pack(c, st, d_sel1, nF, d_idx1, n1, n1Pad, f0, nFc, sameSel ? d_gid : nullptr,
+                             L.packA.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, nullptr, 0);
+        if (rc) return rc;
+        if (!sameSel) {
+            rc = launch_pack(c, st, d_sel2, nF, d_idx2, n2, n2Pad, f0, nFc, d_gid,
+                             L.packB.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, nullptr, 0);
+            if (rc) return rc;
+        }
+        g.A = L.packA.as<float4>();
+        g.B = sameSel ? g.A : L.packB.as<float4>();
+        rc = launch_embed(st, g.A, n1Pad, nFc, d_cell, f0, L.embA.as<__half>(), 1);
+        if (rc) return rc;
+        rc = launch_embed(st, g.B, n2Pad, nFc, d_cell, f0, L.embB.as<__half>(), 0);
+        if (rc) return rc;
+        prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
+                                                             L.fp.as<FrameParams>(), stats);
+        LAUNCHED();
+        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.fp.as<FrameParams>(), L.thrDot.as<float>(), stats);
+        LAUNCHED();
+        g.EA = L.embA.as<__half>(); g.EB = L.embB.as<__half>();
+        g.fp = L.fp.as<FrameParams>(); g.thrDot = L.thrDot.as<float>();
+        const unsigned long long items = (unsigned long long)nFc * g.nATiles * g.nBChunks;
+        if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
+        g.nItems = (unsigned)items;
+        const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)c.numSMs);
+        CK(c.kev_record(st));
+        if (grouped) rdf_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
+        else         rdf_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
+        LAUNCHED();
+        CK(c.kev_record(st));
+    }
+    return NDA_OK;
+}
+
+static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all, int nF,
+                         const int *d_refSel, int refSize, const int *d_outSel, int outSize,
+                         unsigned *d_bits, const float *d_cell, float d2, double T, int fb, int fe)
+{
+    const int words = (outSize + 31) / 32;
+    const int nAPad = round_up(outSize, TC_ATILE);
+    const int nBPad = round_up(refSize, TC_BLK);
+    const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * (16 + 32);
+    const int pass = frames_per_pass(bytesPerFrame, fe - fb);
+    CK(L.packA.reserve((size_t)nAPad * pass * sizeof(float4)));
+    CK(L.packB.reserve((size_t)nBPad * pass * sizeof(float4)));
+    CK(L.embA.reserve((size_t)nAPad * pass * 32));
+    CK(L.embB.reserve((size_t)nBPad * pass * 32));
+    CK(L.fp.reserve((size_t)pass * sizeof(FrameParams)));
+    CK(L.thrDot.reserve((size_t)pass * sizeof(float)));
+    CK(L.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
+    unsigned long long *stats = reinterpret_cast<unsigned long long *>(L.ctl.as<unsigned char>() + 16);
+
+    WithinTcArgs a;
+    TcGeom &g = a.g;
+    g.n1 = outSize; g.n1Pad = nAPad; g.n2 = refSize; g.n2Pad = nBPad;
+    g.nATiles = nAPad / TC_ATILE;
+    g.nBBlocks = (refSize + TC_BLK - 1) / TC_BLK;
+    g.chunkBlocks = g.nBBlocks; g.nBChunks = 1;
+    g.sameSel = 0;
+    g.stats = stats;
+    a.wordsPerFrame = words;
+    a.d2 = d2;
+    a.literal = g_within_pure.load() ? 0 : 1;
+    const size_t smem = tc_smem_base();
+    CK(cudaFuncSetAttribute((const void *)within_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    for (int f0 = fb; f0 < fe; f0 += pass) {
+        const int nFc = std::min(pass, fe - f0);
+        CK(cudaMemsetAsync(L.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
+        int rc = launch_pack(c, st, d_all, nF, d_outSel, outSize, nAPad, f0, nFc, nullptr,
+                             L.packA.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, nullptr, 0);
+        if (rc) return rc;
+        rc = launch_pack(c, st, d_all, nF, d_refSel, refSize, nBPad, f0, nFc, nullptr,
+                         L.packB.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, nullptr, 0);
+        if (rc) return rc;
+        g.A = L.packA.as<float4>();
+        g.B = L.packB.as<float4>();
+        rc = launch_embed(st, g.A, nAPad, nFc, d_cell, f0, L.embA.as<__half>(), 1);
+        if (rc) return rc;
+        rc = launch_embed(st, g.B, nBPad, nFc, d_cell, f0, L.embB.as<__half>(), 0);
+        if (rc) return rc;
+        prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
+                                                             L.fp.as<FrameParams>(), stats);
+        LAUNCHED();
+        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.fp.as<FrameParams>(), L.thrDot.as<float>(), stats);
+        LAUNCHED();
+        g.EA = L.embA.as<__half>(); g.EB = L.embB.as<__half>();
+        g.fp = L.fp.as<FrameParams>(); g.thrDot = L.thrDot.as<float>();
+        a.bits = d_bits + (size_t)(f0 - fb) * words;
+        const unsigned long long items = (unsigned long long)nFc * g.nATiles;
+        if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
+        g.nItems = (unsigned)items;
+        const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)c.numSMs);
+        CK(c.kev_record(st));
+        within_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+        LAUNCHED();
+        CK(c.kev_record(st));
+    }
+    return NDA_OK;
+}
+
 static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, int n1, const float *d_sel2, int n2,
                    const int *d_gid, int nGroups, unsigned long long *d_counts, int nBins,
                    const float *d_cell, int nF, int fb, int fe, int sameSel, float dr,
-                   const int *d_idx1 = nullptr, const int *d_idx2 = nullptr)   // optional row indices into d_sel1/2
+                   const int *d_idx1 = nullptr, const int *d_idx2 = nullptr,   // optional row indices into d_sel1/2
+                   const float *h_cell = nullptr)                              // host copy of d_cell, when the caller has one
 {
     if (n1 <= 0 || n2 <= 0 || fe <= fb || nBins <= 0) return NDA_OK;
     if (nGroups < 1) nGroups = 1;
     const bool grouped = d_gid != nullptr;
     if (!grouped) nGroups = 1;
+    if (filter_tc_requested()) {
+        const double lim0 = (double)nBins * fabs((double)dr);
+        const double T0 = lim0 * lim0 * (1.0 + 9.5367431640625e-07);
+        const float *hc = nullptr;
+        int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
+        if (rc0) return rc0;
+        if (tc_frames_eligible(hc, fb, fe, T0))
+            return dev_rdf_tc(c, L, st, d_sel1, n1, d_sel2, n2, d_gid, nGroups, d_counts, nBins, d_cell, nF, fb, fe,
+                              sameSel, dr, d_idx1, d_idx2, T0);
+    }
     const size_t H = (size_t)nGroups * nBins;
     // shared memory: as many warp-private histogram copies as still allow PAIR_MIN_CTAS CTAs per SM
     const size_t perCta = ((size_t)227 * 1024) / PAIR_MIN_CTAS - 1024;
@@ -341,12 +558,27 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
 
 static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all, int nAtoms, int nF,
                       const int *d_refSel, int refSize, const int *d_outSel, int outSize,
-                      unsigned *d_bits, int *d_out, const float *d_cell, float distance, int fb, int fe)
+                      unsigned *d_bits, int *d_out, const float *d_cell, float distance, int fb, int fe,
+                      const float *h_cell = nullptr)
 {
     (void)nAtoms;
     if (outSize <= 0 || fe <= fb) return NDA_OK;
     const int words = (outSize + 31) / 32;
-    if (refSize <= 0) {
+    bool doneTc = false;
+    if (refSize > 0 && filter_tc_requested()) {
+        const float d2t = distance * distance;
+        const double Tt = (double)d2t * (1.0 + 9.5367431640625e-07);
+        const float *hc = nullptr;
+        int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
+        if (rc0) return rc0;
+        if (tc_frames_eligible(hc, fb, fe, Tt)) {
+            rc0 = dev_within_tc(c, L, st, d_all, nF, d_refSel, refSize, d_outSel, outSize, d_bits, d_cell, d2t, Tt, fb, fe);
+            if (rc0) return rc0;
+            doneTc = true;
+        }
+    }
+    if (doneTc) {
+    } else if (refSize <= 0) {
         CK(cudaMemsetAsync(d_bits, 0, (size_t)(fe - fb) * words * sizeof(unsigned), st));
     } else {
         const int nAPad = round_up(outSize, PAIR_ATILE);
@@ -871,7 +1103,8 @@ int nda_get_radial_nbr_counts(const float *sel1, int n1, const float *sel2, int 
             if (rc) return rc;
             rc = dev_rdf(*c, L, L.stream, up.dev(0, k), n1, sameSel ? up.dev(0, k) : up.dev(1, k), n2,
                          groupId ? c->gid.as<int>() : nullptr, nGroups, c->counts.as<unsigned long long>(), outSize,
-                         c->cell.as<float>() + (size_t)up.f0(k) * 3, wc, 0, wc, sameSel, dr);
+                         c->cell.as<float>() + (size_t)up.f0(k) * 3, wc, 0, wc, sameSel, dr, nullptr, nullptr,
+                         cellDims + (size_t)up.f0(k) * 3);
             if (rc) return rc;
             rc = up.release(k, L.stream);
             if (rc) return rc;
@@ -1040,7 +1273,7 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
         if (rc) return rc;
         rc = dev_within(*c, L, ls, up.dev(0, k), nRows, wc, c->idx1.as<int>(), refSize, c->idx2.as<int>(), outSelSize,
                         c->bits.as<unsigned>() + (size_t)(f0 - fb) * words, nullptr,
-                        c->cell.as<float>() + (size_t)f0 * 3, distance, 0, wc);
+                        c->cell.as<float>() + (size_t)f0 * 3, distance, 0, wc, cellDims + (size_t)f0 * 3);
         if (rc) return rc;
         rc = up.release(k, ls);
         if (rc) return rc;

@@ -1,0 +1,616 @@
+// nda_tc.cuh -- the pair filter on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// The minimum-image wrap breaks the ||a||^2 + ||b||^2 - 2ab contraction, but a PERIODIC embedding
+// restores a contraction that is good enough for a FILTER: with theta_k = 2 pi x_k / c_k and
+// rho_k = c_k / (2 pi), phi(x) = (rho_x cos theta_x, rho_x sin theta_x, ..., rho_z sin theta_z) gives
+//
+//     |phi(a) - phi(b)|^2 = sum_k (c_k/pi)^2 sin^2(pi w_k / c_k) =: S  <=  sum_k w_k^2 = r^2
+//
+// (w = exact minimum-image vector; sin^2 is periodic, |sin x| <= |x|), and
+// phi(a).phi(b) = P - S/2 with P = sum_k rho_k^2.  So  r^2 <= thr  =>  phi(a).phi(b) >= P - thr/2:
+// one 6-term dot product per pair decides, conservatively, which pairs can be in range, and a tile
+// of dot products is a GEMM.  The kernels below run that GEMM as tcgen05.mma (kind::f16, M = 128,
+// N = 64, K = 16, fp32 accumulators in TMEM), read the accumulators back with tcgen05.ld, reduce
+// them with a max tree (FMNMX3) and re-evaluate the few survivors with the reference's strict
+// arithmetic on the ORIGINAL coordinates (nda_device.cuh), exactly like the FP32 filters: counts and
+// mask bits stay bit-identical to the reference.  The per-pair cost drops from ~9 issue slots
+// (fold2 filter) to ~0.6.
+//
+// Precision of the filter (all slack goes into the threshold, see prep_tc_kernel): phi is computed
+// in float64 and stored as fp16; K = 16 holds [hi(6) 0 0 | lo(6) 0 0] for the A role and
+// [hi(6) 0 0 | hi(6) 0 0] for the B role, so A's rounding is compensated and only B's 2^-11
+// relative rounding remains: |dot_computed - dot_exact| <= E = P (2^-11 * 1.01 + 2^-18).
+//
+// Operand layout (pinned by tools/tc_probe.cu on a B200): blocks of 128 atoms, 4 KB each,
+// [kchunk(2)][atom(128)][8 halves]: K-major, no swizzle, descriptor LBO = 2048 B, SBO = 128 B.
+//
+// CTA = 16 epilogue warps + 1 control warp, one CTA per SM (all 512 TMEM columns):
+//   control thread : TMA bulk copies (A tile 16 KB once per item, B blocks 4 KB through a 4-stage ring)
+//                    and the MMAs: per B block and half h (64 atoms) 4 MMAs (one per 128-row A block)
+//                    into TMEM columns [256 h + 64 t, +64); tcgen05.commit -> mbarriers
+//   epilogue warp w: TMEM lanes 32 (w % 4) .., A block t = w / 4: one A atom per thread, 64 B atoms
+//                    per tcgen05.ld; TMEM half h is released right after the load, so the MMAs of
+//                    the next block overlap the max tree of this one.
+#pragma once
+#include <cuda_fp16.h>
+#include "nda_kernels.cuh"
+
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS   = (TC_EPI_WARPS + 1) * 32;          // 544
+constexpr int TC_ATILE     = 512;                              // A atoms per work item (4 blocks)
+constexpr int TC_BLK       = 128;                              // atoms per embedding block
+constexpr int TC_BLK_BYTES = 4096;
+constexpr int TC_STAGES    = 4;                                // B blocks in flight
+constexpr int TC_QCAP      = 64;                               // per-warp candidate ring (rdf)
+// instruction descriptor: D = F32 (bit 4), A = B = F16, both K-major, N = 64 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+constexpr uint32_t TC_IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+__host__ __device__ constexpr size_t tc_smem_base()
+{
+    return 2 * (size_t)TC_ATILE * 32            // A embedding, double-buffered
+         + (size_t)TC_STAGES * TC_BLK_BYTES     // B ring
+         + (size_t)TC_ATILE * sizeof(float4)    // original A coordinates (strict re-evaluation)
+         + (size_t)TC_EPI_WARPS * TC_QCAP * 4   // candidate rings
+         + 256;                                 // mbarriers + TMEM base
+}
+
+// ------------------------------------------------------------------------------------------
+// embedding: packed float4 [nFc][nPad] -> fp16 blocks [nFc][nPad/128][2][128][8]
+// grid (nPad/128, min(nFc, 65535)), block 128
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+embed_kernel(const float4 *__restrict__ packed, int nPad, int nFc, const float *__restrict__ cell, int f0,
+             __half *__restrict__ E, int roleA)
+{
+    const int blk = blockIdx.x, tid = threadIdx.x;
+    const int nBlk = nPad / TC_BLK;
+    for (int f = blockIdx.y; f < nFc; f += gridDim.y) {
+        const float4 v = packed[(size_t)f * nPad + (size_t)blk * TC_BLK + tid];
+        const float *cf = cell + 3 * (size_t)(f0 + f);
+        const float x[3] = {v.x, v.y, v.z};
+        __align__(16) __half hi[8], lo[8];
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) { hi[i] = __float2half_rn(0.f); lo[i] = hi[i]; }
+        const bool finite = (fabsf(v.x) <= 3.0e38f) && (fabsf(v.y) <= 3.0e38f) && (fabsf(v.z) <= 3.0e38f);
+        if (finite) {
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double c = fabs((double)cf[k]);
+                if (c > 0.0 && c < 1.0e30) {
+                    const double rho = c * 0.15915494309189535;      // c / (2 pi)
+                    double s, co;
+                    sincospi(2.0 * ((double)x[k] / c), &s, &co);
+                    const double pc = rho * co, ps = rho * s;
+                    hi[2 * k] = __float2half_rn((float)pc);
+                    hi[2 * k + 1] = __float2half_rn((float)ps);
+                    lo[2 * k] = __float2half_rn((float)(pc - (double)__half2float(hi[2 * k])));
+                    lo[2 * k + 1] = __float2half_rn((float)(ps - (double)__half2float(hi[2 * k + 1])));
+                }
+            }
+        }
+        __half *dst = E + ((size_t)f * nBlk + blk) * (TC_BLK_BYTES / 2);
+        *reinterpret_cast<uint4 *>(dst + tid * 8) = *reinterpret_cast<const uint4 *>(hi);
+        *reinterpret_cast<uint4 *>(dst + 1024 + tid * 8) = *reinterpret_cast<const uint4 *>(roleA ? lo : hi);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-frame dot-product threshold.  fp[f].thr already satisfies: strict r2 <= T  =>  exact
+// minimum-image r2 <= thr (guard band of prep_frames_kernel).  S <= r2 and dot = P - S/2, so
+//     strict in range  =>  dot_computed >= P - thr/2 - E.
+// Frames where the slack eats the range (2E > thr) or the chord bound is useless (thr > P) are run
+// all-exact; the host only selects the tensor-core path when no frame of the call should end there.
+// ------------------------------------------------------------------------------------------
+__global__ void prep_tc_kernel(const float *__restrict__ cell, int f0, int nFc, FrameParams *__restrict__ fp,
+                               float *__restrict__ thrDot, unsigned long long *__restrict__ stats)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFc) return;
+    FrameParams p = fp[f];
+    float td = 3.0e38f;
+    if (!p.exact_all) {
+        const double k = 0.15915494309189535;
+        const double rx = fabs((double)p.cx) * k, ry = fabs((double)p.cy) * k, rz = fabs((double)p.cz) * k;
+        const double P = rx * rx + ry * ry + rz * rz;
+        const double Eb = P * (4.8828125e-04 * 1.01 + 3.814697265625e-06) + 1.0e-6;
+        const double thr = (double)p.thr;
+        const double t = P - 0.5 * thr - 1.25 * Eb;
+        if (2.5 * Eb <= thr && thr <= P && t > 0.0 && P < 1.0e30) {
+            td = __double2float_rd(t);
+        } else {
+            p.exact_all = 1;
+            fp[f].exact_all = 1;
+            atomicAdd(&stats[1], 1ull);
+        }
+    }
+    thrDot[f] = td;
+}
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 / mbarrier helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr)
+{
+    // start address >> 4 | LBO (2048 B) >> 4 at bit 16 | SBO (128 B) >> 4 at bit 32 | version 1 at bit 46
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ void tc_mma(uint32_t dTmem, uint64_t descA, uint64_t descB)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(dTmem), "l"(descA), "l"(descB), "r"(TC_IDESC), "r"(0u) : "memory");
+}
+
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// 64 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld64(uint32_t taddr, float (&v)[64])
+{
+    uint32_t r[64];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+                 "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+                 "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+                   "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+                   "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+                   "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+                   "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry shared by the two kernels: work items, cursors, shared-memory carve-up
+// ------------------------------------------------------------------------------------------
+struct TcGeom {
+    const float4 *A, *B;            // packed ORIGINAL coordinates [nFc][n1Pad], [nFc][n2Pad]
+    const __half *EA, *EB;          // embeddings (A role / B role)
+    const FrameParams *fp;
+    const float *thrDot;
+    int n1, n1Pad, n2, n2Pad;
+    int nATiles;                    // n1Pad / 512
+    int nBBlocks;                   // ceil(n2 / 128): blocks that hold real atoms
+    int chunkBlocks, nBChunks;      // B blocks per work item
+    int sameSel;
+    unsigned nItems;                // nFc * nATiles * nBChunks
+    unsigned long long *stats;
+};
+
+struct TcItem { int f, ia, jb0, jb1; bool tc; };
+
+// false: the item has no work at all (chunk entirely below the diagonal)
+__device__ __forceinline__ bool tc_decode(const TcGeom &g, unsigned item, TcItem &it)
+{
+    const unsigned ipf = (unsigned)g.nATiles * (unsigned)g.nBChunks;
+    it.f = (int)(item / ipf);
+    const unsigned rem = item % ipf;
+    it.ia = (int)(rem / (unsigned)g.nBChunks);
+    const int kc = (int)(rem % (unsigned)g.nBChunks);
+    it.jb0 = kc * g.chunkBlocks;
+    it.jb1 = min(g.nBBlocks, it.jb0 + g.chunkBlocks);
+    if (g.sameSel) it.jb0 = max(it.jb0, (it.ia * TC_ATILE + 1) / TC_BLK);      // col > row only
+    if (it.jb0 >= it.jb1) return false;
+    it.tc = g.fp[it.f].exact_all == 0;
+    return true;
+}
+
+// position of the control thread in this CTA's sequence of tensor-core blocks
+struct TcCursor {
+    unsigned item;      // global item id
+    TcItem it;
+    int jb;             // current B block
+    unsigned g;         // tensor-core blocks before this one (this CTA)
+    unsigned kt;        // tensor-core items before this one (this CTA)
+    bool valid;
+    __device__ __forceinline__ void seek(const TcGeom &geo)
+    {
+        while (item < geo.nItems) {
+            if (tc_decode(geo, item, it) && it.tc) { jb = it.jb0; valid = true; return; }
+            item += gridDim.x;
+        }
+        valid = false;
+    }
+    __device__ __forceinline__ void init(const TcGeom &geo) { item = blockIdx.x; g = 0; kt = 0; seek(geo); }
+    __device__ __forceinline__ void advance(const TcGeom &geo)
+    {
+        ++g;
+        if (++jb >= it.jb1) { ++kt; item += gridDim.x; seek(geo); }
+    }
+};
+
+struct TcSmem {
+    unsigned char *sEA;     // [2][16 KB]
+    unsigned char *sEB;     // [TC_STAGES][4 KB]
+    float4   *sA;           // [512]
+    unsigned *sQ;           // [16][TC_QCAP]
+    uint64_t *full, *empty; // [TC_STAGES] B ring
+    uint64_t *tfull, *tempty;   // [2] TMEM halves
+    uint64_t *afull, *aempty;   // [2] A tile buffers
+    uint32_t *tmemPtr;
+    unsigned *extra;        // histograms (rdf)
+};
+
+__device__ __forceinline__ TcSmem tc_carve(unsigned char *raw)
+{
+    TcSmem s;
+    s.sEA = raw;
+    s.sEB = s.sEA + 2 * TC_ATILE * 32;
+    s.sA = reinterpret_cast<float4 *>(s.sEB + TC_STAGES * TC_BLK_BYTES);
+    s.sQ = reinterpret_cast<unsigned *>(s.sA + TC_ATILE);
+    s.full = reinterpret_cast<uint64_t *>(s.sQ + TC_EPI_WARPS * TC_QCAP);
+    s.empty = s.full + TC_STAGES;
+    s.tfull = s.empty + TC_STAGES;
+    s.tempty = s.tfull + 2;
+    s.afull = s.tempty + 2;
+    s.aempty = s.afull + 2;
+    s.tmemPtr = reinterpret_cast<uint32_t *>(s.aempty + 2);
+    s.extra = reinterpret_cast<unsigned *>(raw + tc_smem_base());
+    return s;
+}
+
+// barriers + TMEM allocation (all threads call; returns the TMEM base address)
+__device__ __forceinline__ uint32_t tc_setup(const TcSmem &s)
+{
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s.tfull[i], 1);
+            mbar_init(&s.tempty[i], TC_EPI_WARPS);
+            mbar_init(&s.afull[i], 1);
+            mbar_init(&s.aempty[i], 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == TC_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(s.tmemPtr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *s.tmemPtr;
+}
+
+__device__ __forceinline__ void tc_teardown(uint32_t tmem)
+{
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == TC_EPI_WARPS)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+
+// the control thread: TMA producer and MMA issuer in one instruction stream.  The producer cursor
+// runs at most TC_STAGES blocks and one item ahead of the MMA cursor, so every wait below is on work
+// this thread has already issued (no self-deadlock).
+__device__ __forceinline__ void tc_control(const TcGeom &geo, const TcSmem &s, uint32_t tmem)
+{
+    TcCursor P, C;
+    P.init(geo);
+    C = P;
+    const size_t aBlkPerFrame = (size_t)geo.n1Pad / TC_BLK, bBlkPerFrame = (size_t)geo.n2Pad / TC_BLK;
+    while (C.valid) {
+        while (P.valid && P.g < C.g + TC_STAGES && P.kt <= C.kt + 1) {
+            if (P.jb == P.it.jb0) {                                  // first block of an item: its A tile
+                const unsigned ab = P.kt & 1u, u = P.kt >> 1;
+                mbar_wait(&s.aempty[ab], (u & 1u) ^ 1u);
+                mbar_expect_tx(&s.afull[ab], TC_ATILE * 32);
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(geo.EA) +
+                    ((size_t)P.it.f * aBlkPerFrame + (size_t)P.it.ia * (TC_ATILE / TC_BLK)) * TC_BLK_BYTES;
+                tma_bulk_g2s(s.sEA + ab * (TC_ATILE * 32), src, TC_ATILE * 32, &s.afull[ab]);
+            }
+            const unsigned slot = P.g % TC_STAGES, u = P.g / TC_STAGES;
+            mbar_wait(&s.empty[slot], (u & 1u) ^ 1u);
+            mbar_expect_tx(&s.full[slot], TC_BLK_BYTES);
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(geo.EB) +
+                ((size_t)P.it.f * bBlkPerFrame + (size_t)P.jb) * TC_BLK_BYTES;
+            tma_bulk_g2s(s.sEB + slot * TC_BLK_BYTES, src, TC_BLK_BYTES, &s.full[slot]);
+            P.advance(geo);
+        }
+        const unsigned ab = C.kt & 1u;
+        if (C.jb == C.it.jb0) mbar_wait(&s.afull[ab], (C.kt >> 1) & 1u);
+        const unsigned slot = C.g % TC_STAGES;
+        mbar_wait(&s.full[slot], (C.g / TC_STAGES) & 1u);
+        const uint32_t aBase = smem_u32(s.sEA + ab * (TC_ATILE * 32));
+        const uint32_t bBase = smem_u32(s.sEB + slot * TC_BLK_BYTES);
+        #pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            mbar_wait(&s.tempty[h], (C.g & 1u) ^ 1u);                // epilogue has read the previous block's half
+            tc_fence_after();
+            const uint64_t db = tc_smem_desc(bBase + h * 1024);
+            #pragma unroll
+            for (int t = 0; t < 4; ++t)
+                tc_mma(tmem + (uint32_t)(h * 256 + t * 64), tc_smem_desc(aBase + t * TC_BLK_BYTES), db);
+            tc_commit(&s.tfull[h]);
+        }
+        tc_commit(&s.empty[slot]);
+        const bool lastOfItem = (C.jb + 1 >= C.it.jb1);
+        if (lastOfItem) tc_commit(&s.aempty[ab]);
+        C.advance(geo);
+    }
+}
+
+// max of 8 accumulators (FMNMX3 chain)
+__device__ __forceinline__ float tc_max8(const float *v)
+{
+    float m = fmaxf(fmaxf(v[0], v[1]), v[2]);
+    m = fmaxf(fmaxf(m, v[3]), v[4]);
+    m = fmaxf(fmaxf(m, v[5]), v[6]);
+    return fmaxf(m, v[7]);
+}
+
+// bit k of (lo, hi) = (v[k] >= thr), evaluated only inside the 8-column groups whose maximum passes
+__device__ __forceinline__ void tc_mask64(const float (&v)[64], const float (&mb)[8], float thr, unsigned &lo, unsigned &hi)
+{
+    lo = 0u; hi = 0u;
+    #pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if (__any_sync(NDA_FULL_MASK, mb[b] >= thr)) {
+            unsigned m = 0u;
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) m |= (v[8 * b + k] >= thr) ? (1u << k) : 0u;
+            if (b < 4) lo |= m << (8 * b); else hi |= m << (8 * (b - 4));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// RDF on the tensor-core filter
+// ------------------------------------------------------------------------------------------
+struct RdfTcArgs {
+    TcGeom g;
+    unsigned long long *counts;
+    int nBins, nGroups, histCopies;
+    float dr;
+    int fastStrict;
+};
+
+template <bool kGrouped>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+rdf_tc_kernel(const RdfTcArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TcSmem s = tc_carve(smem_raw);
+    const TcGeom &geo = p.g;
+    unsigned *hist = s.extra;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = p.nGroups * p.nBins;
+
+    for (int i = tid; i < p.histCopies * H; i += TC_THREADS) hist[i] = 0u;
+    const uint32_t tmem = tc_setup(s);
+
+    if (warp == TC_EPI_WARPS) {
+        if (lane == 0) tc_control(geo, s, tmem);
+        __syncwarp();
+    } else {
+        const int q = warp & 3, t = warp >> 2;
+        const int rowInTile = t * TC_BLK + q * 32 + lane;
+        unsigned *myHist = hist + (warp % p.histCopies) * H;
+        unsigned *myQ = s.sQ + warp * TC_QCAP;
+        const unsigned ltmask = lanemask_lt();
+        const uint32_t tLane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 64);
+        unsigned g = 0, nCand = 0;
+        int sinceFlush = 0;
+
+        for (unsigned item = blockIdx.x; item < geo.nItems; item += gridDim.x) {
+            TcItem it;
+            if (!tc_decode(geo, item, it)) continue;
+            if (++sinceFlush > PAIR_FLUSH_ITEMS) {             // u32 safety: spill shared histograms (atomic grab)
+                for (int i = lane; i < H; i += 32) {
+                    const unsigned v = atomicExch(&myHist[i], 0u);
+                    if (v) atomicAdd(&p.counts[i], (unsigned long long)v);
+                }
+                sinceFlush = 1;
+            }
+            const FrameParams fpar = geo.fp[it.f];
+            const float4 *Aorig = geo.A + (size_t)it.f * geo.n1Pad + (size_t)it.ia * TC_ATILE;
+            const float4 *Borig = geo.B + (size_t)it.f * geo.n2Pad;
+            const float4 ao = Aorig[rowInTile];
+            __syncwarp();                                      // previous item's drains are done with sA
+            s.sA[rowInTile] = ao;
+            __syncwarp();
+            const int rowBase = it.ia * TC_ATILE;
+            const int rowWarp = t * TC_BLK + q * 32;           // this warp's first row in the tile
+
+            if (!it.tc) {
+                // all-exact frame: the reference arithmetic on every pair
+                const int j0 = it.jb0 * TC_BLK, j1 = min(geo.n2, it.jb1 * TC_BLK);
+                for (int j = j0; j < j1; ++j) {
+                    const float4 b = __ldg(&Borig[j]);
+                    if (!geo.sameSel || (j > rowBase + rowInTile)) {
+                        const float r2 = strict_r2(ao.x, ao.y, ao.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
+                        const int idx = strict_bin(r2, p.dr, p.nBins);
+                        if (idx >= 0) atomicAdd(&myHist[(kGrouped ? __float_as_int(b.w) : 0) * p.nBins + idx], 1u);
+                    }
+                }
+                continue;
+            }
+
+            const float thrD = geo.thrDot[it.f];
+            int qhead = 0, qcount = 0;
+            // strict re-evaluation of n queued candidates, one per lane; entry = (lane of the A row) << 24 | column
+            auto drain = [&](int n) {
+                __syncwarp();
+                if (lane < n) {
+                    const unsigned e = myQ[(qhead + lane) % TC_QCAP];
+                    const int ai = rowWarp + (int)(e >> 24), bj = (int)(e & 0xffffffu);
+                    if (!geo.sameSel || (bj > rowBase + ai)) {
+                        const float4 a = s.sA[ai];
+                        const float4 b = __ldg(&Borig[bj]);
+                        const float r2 = p.fastStrict ? strict_r2_fastpath(a.x, a.y, a.z, b.x, b.y, b.z, fpar)
+                                                      : strict_r2(a.x, a.y, a.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
+                        const int idx = strict_bin(r2, p.dr, p.nBins);
+                        if (idx >= 0) atomicAdd(&myHist[(kGrouped ? __float_as_int(b.w) : 0) * p.nBins + idx], 1u);
+                    }
+                    ++nCand;
+                }
+                qhead = (qhead + n) % TC_QCAP;
+                qcount -= n;
+                __syncwarp();
+            };
+
+            for (int jb = it.jb0; jb < it.jb1; ++jb, ++g) {
+                #pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(&s.tfull[h], g & 1u);
+                    tc_fence_after();
+                    float v[64];
+                    tc_ld64(tLane + (uint32_t)(h * 256), v);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s.tempty[h]);  // TMEM half free: the next block's MMAs may start
+
+                    float mb[8];
+                    #pragma unroll
+                    for (int b = 0; b < 8; ++b) mb[b] = tc_max8(v + 8 * b);
+                    const float top = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])),
+                                            fmaxf(fmaxf(mb[4], mb[5]), fmaxf(mb[6], mb[7])));
+                    if (__any_sync(NDA_FULL_MASK, top >= thrD)) {
+                        unsigned mlo, mhi;
+                        tc_mask64(v, mb, thrD, mlo, mhi);
+                        const int colBase = jb * TC_BLK + h * 64;
+                        for (;;) {
+                            const bool has = (mlo | mhi) != 0u;
+                            const unsigned bal = __ballot_sync(NDA_FULL_MASK, has);
+                            if (!bal) break;
+                            if (has) {
+                                int k;
+                                if (mlo) { k = __ffs(mlo) - 1; mlo &= mlo - 1; }
+                                else     { k = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
+                                const int pos = (qhead + qcount + __popc(bal & ltmask)) % TC_QCAP;
+                                myQ[pos] = ((unsigned)lane << 24) | (unsigned)(colBase + k);
+                            }
+                            qcount += __popc(bal);
+                            if (qcount >= 32) drain(32);
+                        }
+                    }
+                }
+            }
+            if (qcount > 0) drain(qcount);
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nCand += __shfl_xor_sync(NDA_FULL_MASK, nCand, o);
+        if (lane == 0 && nCand) atomicAdd(&geo.stats[0], (unsigned long long)nCand);
+    }
+
+    tc_teardown(tmem);                                         // includes the CTA-wide barrier
+    for (int i = tid; i < p.histCopies * H; i += TC_THREADS) {
+        const unsigned v = hist[i];
+        if (v) atomicAdd(&p.counts[i % H], (unsigned long long)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// within on the tensor-core filter
+// ------------------------------------------------------------------------------------------
+struct WithinTcArgs {
+    TcGeom g;                   // A = outSel atoms, B = refSel atoms; nBChunks = 1, sameSel = 0
+    unsigned *bits;             // [nFc][wordsPerFrame]
+    int wordsPerFrame;
+    float d2;
+    int literal;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+within_tc_kernel(const WithinTcArgs p)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TcSmem s = tc_carve(smem_raw);
+    const TcGeom &geo = p.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tmem = tc_setup(s);
+
+    if (warp == TC_EPI_WARPS) {
+        if (lane == 0) tc_control(geo, s, tmem);
+        __syncwarp();
+    } else {
+        const int q = warp & 3, t = warp >> 2;
+        const int rowInTile = t * TC_BLK + q * 32 + lane;
+        const uint32_t tLane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 64);
+        unsigned g = 0, nCand = 0;
+
+        for (unsigned item = blockIdx.x; item < geo.nItems; item += gridDim.x) {
+            TcItem it;
+            if (!tc_decode(geo, item, it)) continue;
+            const FrameParams fpar = geo.fp[it.f];
+            const float4 ao = geo.A[(size_t)it.f * geo.n1Pad + (size_t)it.ia * TC_ATILE + rowInTile];
+            const float4 *Borig = geo.B + (size_t)it.f * geo.n2Pad;
+            bool found = false;
+
+            if (!it.tc) {
+                for (int j = 0; j < geo.n2 && !__all_sync(NDA_FULL_MASK, found); ++j) {
+                    const float4 b = __ldg(&Borig[j]);
+                    if (!found && strict_within(ao, b, fpar, p.d2, p.literal)) found = true;
+                }
+            } else {
+                const float thrD = geo.thrDot[it.f];
+                for (int jb = it.jb0; jb < it.jb1; ++jb, ++g) {
+                    #pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        mbar_wait(&s.tfull[h], g & 1u);
+                        tc_fence_after();
+                        float v[64];
+                        tc_ld64(tLane + (uint32_t)(h * 256), v);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&s.tempty[h]);
+
+                        float mb[8];
+                        #pragma unroll
+                        for (int b = 0; b < 8; ++b) mb[b] = tc_max8(v + 8 * b);
+                        float top = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])),
+                                          fmaxf(fmaxf(mb[4], mb[5]), fmaxf(mb[6], mb[7])));
+                        if (found) top = -3.0e38f;             // a found atom needs no further test
+                        if (__any_sync(NDA_FULL_MASK, top >= thrD)) {
+                            // candidates are rare (about one per found atom plus the guard band):
+                            // evaluate them in place with the reference arithmetic
+                            unsigned mlo, mhi;
+                            tc_mask64(v, mb, thrD, mlo, mhi);
+                            if (found) { mlo = 0u; mhi = 0u; }
+                            const int colBase = jb * TC_BLK + h * 64;
+                            while (mlo | mhi) {
+                                int k;
+                                if (mlo) { k = __ffs(mlo) - 1; mlo &= mlo - 1; }
+                                else     { k = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
+                                const float4 b = __ldg(&Borig[colBase + k]);
+                                ++nCand;
+                                if (strict_within(ao, b, fpar, p.d2, p.literal)) { found = true; mlo = 0u; mhi = 0u; }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+            const unsigned w = __ballot_sync(NDA_FULL_MASK, found);
+            if (lane == 0) {
+                const int word = (it.ia * TC_ATILE + t * TC_BLK + q * 32) >> 5;
+                if (word < p.wordsPerFrame) p.bits[(size_t)it.f * p.wordsPerFrame + word] = w;
+            }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nCand += __shfl_xor_sync(NDA_FULL_MASK, nCand, o);
+        if (lane == 0 && nCand) atomicAdd(&geo.stats[0], (unsigned long long)nCand);
+    }
+    tc_teardown(tmem);
+}
