@@ -314,6 +314,7 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
     g.nBBlocks = (n2 + TC_BLK - 1) / TC_BLK;
     g.sameSel = sameSel ? 1 : 0;
     g.stats = stats;
+    g.origInStage = 1; g.itemOrigBytes = 0;
     a.counts = d_counts; a.nBins = nBins; a.nGroups = nGroups; a.histCopies = copies;
     a.dr = dr;
     a.fastStrict = getenv("NDA_STRICT_SLOW") ? 0 : 1;
@@ -394,10 +395,14 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
     g.chunkBlocks = g.nBBlocks; g.nBChunks = 1;
     g.sameSel = 0;
     g.stats = stats;
+    g.origInStage = 0;
+    // the frame's original refSel coordinates ride along with every A tile when two copies fit
+    const size_t origBytes = (size_t)nBPad * sizeof(float4);
+    g.itemOrigBytes = (tc_smem_base() + 2 * origBytes <= c.smemOptin) ? (int)origBytes : 0;
     a.wordsPerFrame = words;
     a.d2 = d2;
     a.literal = g_within_pure.load() ? 0 : 1;
-    const size_t smem = tc_smem_base();
+    const size_t smem = tc_smem_base() + 2 * (size_t)g.itemOrigBytes;
     CK(cudaFuncSetAttribute((const void *)within_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int f0 = fb; f0 < fe; f0 += pass) {

@@ -24,33 +24,41 @@
 // Operand layout (pinned by tools/tc_probe.cu on a B200): blocks of 128 atoms, 4 KB each,
 // [kchunk(2)][atom(128)][8 halves]: K-major, no swizzle, descriptor LBO = 2048 B, SBO = 128 B.
 //
-// CTA = 16 epilogue warps + 1 control warp, one CTA per SM (all 512 TMEM columns):
-//   control thread : TMA bulk copies (A tile 16 KB once per item, B blocks 4 KB through a 4-stage ring)
-//                    and the MMAs: per B block and half h (64 atoms) 4 MMAs (one per 128-row A block)
-//                    into TMEM columns [256 h + 64 t, +64); tcgen05.commit -> mbarriers
-//   epilogue warp w: TMEM lanes 32 (w % 4) .., A block t = w / 4: one A atom per thread, 64 B atoms
-//                    per tcgen05.ld; TMEM half h is released right after the load, so the MMAs of
-//                    the next block overlap the max tree of this one.
+// CTA = 16 epilogue warps + MMA warp + TMA warp, one CTA per SM (all 512 TMEM columns):
+//   TMA warp       : bulk copies: the A tile's embedding (16 KB, double-buffered) once per item; per B
+//                    block one 6 KB stage (4 KB embedding + the block's 2 KB ORIGINAL float4 coordinates)
+//                    through a 6-deep ring
+//   MMA warp       : per stage and half h (64 B atoms) 4 MMAs (one per 128-row A block) into TMEM
+//                    columns [256 h + 64 t, +64); tcgen05.commit -> mbarriers
+//   epilogue warp w: TMEM lanes 32 (w % 4) .., A block t = w / 4: one A atom per thread, 64 B atoms per
+//                    tcgen05.ld; TMEM half h is released right after the load, so the MMAs of the next
+//                    block overlap the max tree of this one.  Candidates are copied (with the B atom's
+//                    original coordinates from the stage) into a per-warp ring and re-evaluated 32 at a
+//                    time, so no warp ever stalls the TMEM hand-over on a global load.
 #pragma once
 #include <cuda_fp16.h>
 #include "nda_kernels.cuh"
 
 constexpr int TC_EPI_WARPS = 16;
-constexpr int TC_THREADS   = (TC_EPI_WARPS + 1) * 32;          // 544
+constexpr int TC_MMA_WARP  = TC_EPI_WARPS;                     // warp 16 issues the MMAs
+constexpr int TC_TMA_WARP  = TC_EPI_WARPS + 1;                 // warp 17 issues the TMA copies
+constexpr int TC_THREADS   = (TC_EPI_WARPS + 2) * 32;          // 576
 constexpr int TC_ATILE     = 512;                              // A atoms per work item (4 blocks)
 constexpr int TC_BLK       = 128;                              // atoms per embedding block
 constexpr int TC_BLK_BYTES = 4096;
-constexpr int TC_STAGES    = 4;                                // B blocks in flight
-constexpr int TC_QCAP      = 64;                               // per-warp candidate ring (rdf)
+constexpr int TC_ORIG_BYTES = TC_BLK * 16;                     // the block's ORIGINAL float4 coordinates
+constexpr int TC_STAGE_BYTES = TC_BLK_BYTES + TC_ORIG_BYTES;   // one B stage: embedding + originals (6 KB)
+constexpr int TC_STAGES    = 6;                                // B blocks in flight
+constexpr int TC_QCAP      = 64;                               // per-warp candidate ring, 16-byte entries
 // instruction descriptor: D = F32 (bit 4), A = B = F16, both K-major, N = 64 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
 constexpr uint32_t TC_IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 __host__ __device__ constexpr size_t tc_smem_base()
 {
     return 2 * (size_t)TC_ATILE * 32            // A embedding, double-buffered
-         + (size_t)TC_STAGES * TC_BLK_BYTES     // B ring
+         + (size_t)TC_STAGES * TC_STAGE_BYTES   // B ring
          + (size_t)TC_ATILE * sizeof(float4)    // original A coordinates (strict re-evaluation)
-         + (size_t)TC_EPI_WARPS * TC_QCAP * 4   // candidate rings
+         + (size_t)TC_EPI_WARPS * TC_QCAP * 16  // candidate rings
          + 256;                                 // mbarriers + TMEM base
 }
 
@@ -149,6 +157,15 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
                  :: "r"(smem_u32(bar)) : "memory");
 }
 
+// one lane of a converged warp (elect.sync): the form the compiler recognises as single-thread code,
+// so uniform-register operands need no per-lane serialisation loop
+__device__ __forceinline__ bool tc_elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p mov.u32 %0, 1;\n\t}" : "+r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -195,60 +212,65 @@ struct TcGeom {
     int sameSel;
     unsigned nItems;                // nFc * nATiles * nBChunks
     unsigned long long *stats;
+    int origInStage;                // 1: every B stage also carries the block's original float4 coordinates (rdf)
+    int itemOrigBytes;              // > 0: the frame's whole original B array travels with the A tile (within)
 };
 
 struct TcItem { int f, ia, jb0, jb1; bool tc; };
 
-// false: the item has no work at all (chunk entirely below the diagonal)
-__device__ __forceinline__ bool tc_decode(const TcGeom &g, unsigned item, TcItem &it)
-{
-    const unsigned ipf = (unsigned)g.nATiles * (unsigned)g.nBChunks;
-    it.f = (int)(item / ipf);
-    const unsigned rem = item % ipf;
-    it.ia = (int)(rem / (unsigned)g.nBChunks);
-    const int kc = (int)(rem % (unsigned)g.nBChunks);
-    it.jb0 = kc * g.chunkBlocks;
-    it.jb1 = min(g.nBBlocks, it.jb0 + g.chunkBlocks);
-    if (g.sameSel) it.jb0 = max(it.jb0, (it.ia * TC_ATILE + 1) / TC_BLK);      // col > row only
-    if (it.jb0 >= it.jb1) return false;
-    it.tc = g.fp[it.f].exact_all == 0;
-    return true;
-}
-
-// position of the control thread in this CTA's sequence of tensor-core blocks
-struct TcCursor {
-    unsigned item;      // global item id
-    TcItem it;
-    int jb;             // current B block
-    unsigned g;         // tensor-core blocks before this one (this CTA)
-    unsigned kt;        // tensor-core items before this one (this CTA)
-    bool valid;
-    __device__ __forceinline__ void seek(const TcGeom &geo)
+// (frame, A tile, B chunk) of the items blockIdx.x + k gridDim.x, advanced without divisions
+struct TcWalk {
+    unsigned item;
+    int f, ia, kc, df, dia, dkc;
+    __device__ __forceinline__ void init(const TcGeom &g)
     {
-        while (item < geo.nItems) {
-            if (tc_decode(geo, item, it) && it.tc) { jb = it.jb0; valid = true; return; }
-            item += gridDim.x;
-        }
-        valid = false;
+        const unsigned ipf = (unsigned)g.nATiles * (unsigned)g.nBChunks;
+        item = blockIdx.x;
+        f = (int)(item / ipf);
+        unsigned rem = item % ipf;
+        ia = (int)(rem / (unsigned)g.nBChunks);
+        kc = (int)(rem % (unsigned)g.nBChunks);
+        df = (int)(gridDim.x / ipf);
+        rem = gridDim.x % ipf;
+        dia = (int)(rem / (unsigned)g.nBChunks);
+        dkc = (int)(rem % (unsigned)g.nBChunks);
     }
-    __device__ __forceinline__ void init(const TcGeom &geo) { item = blockIdx.x; g = 0; kt = 0; seek(geo); }
-    __device__ __forceinline__ void advance(const TcGeom &geo)
+    __device__ __forceinline__ void next(const TcGeom &g)
     {
-        ++g;
-        if (++jb >= it.jb1) { ++kt; item += gridDim.x; seek(geo); }
+        item += gridDim.x;
+        kc += dkc;
+        if (kc >= g.nBChunks) { kc -= g.nBChunks; ++ia; }
+        ia += dia;
+        if (ia >= g.nATiles) { ia -= g.nATiles; ++f; }
+        f += df;
+    }
+    // false: the item has no work at all (chunk entirely below the diagonal)
+    __device__ __forceinline__ bool decode(const TcGeom &g, TcItem &it) const
+    {
+        it.f = f; it.ia = ia;
+        it.jb0 = kc * g.chunkBlocks;
+        it.jb1 = min(g.nBBlocks, it.jb0 + g.chunkBlocks);
+        if (g.sameSel) it.jb0 = max(it.jb0, (ia * TC_ATILE + 1) / TC_BLK);     // col > row only
+        if (it.jb0 >= it.jb1) return false;
+        it.tc = g.fp[f].exact_all == 0;
+        return true;
     }
 };
 
+// per-stage word the TMA warp hands to the MMA warp (written before the arrive on full[slot])
+constexpr unsigned TC_INFO_AB = 1u, TC_INFO_FIRST = 2u, TC_INFO_LAST = 4u, TC_INFO_STOP = 8u;
+
 struct TcSmem {
     unsigned char *sEA;     // [2][16 KB]
-    unsigned char *sEB;     // [TC_STAGES][4 KB]
+    unsigned char *sEB;     // [TC_STAGES][4 KB embedding | 2 KB original float4]
     float4   *sA;           // [512]
-    unsigned *sQ;           // [16][TC_QCAP]
+    float4   *sQ;           // [16][TC_QCAP]: (b.x, b.y, b.z, b.w bits | owner lane << 24)
     uint64_t *full, *empty; // [TC_STAGES] B ring
     uint64_t *tfull, *tempty;   // [2] TMEM halves
     uint64_t *afull, *aempty;   // [2] A tile buffers
     uint32_t *tmemPtr;
-    unsigned *extra;        // histograms (rdf)
+    unsigned *info;         // [TC_STAGES]
+    unsigned *extra;        // histograms (rdf) / per-item original B coordinates, double-buffered (within)
 };
 
 __device__ __forceinline__ TcSmem tc_carve(unsigned char *raw)
@@ -256,8 +278,8 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char *raw)
     TcSmem s;
     s.sEA = raw;
     s.sEB = s.sEA + 2 * TC_ATILE * 32;
-    s.sA = reinterpret_cast<float4 *>(s.sEB + TC_STAGES * TC_BLK_BYTES);
-    s.sQ = reinterpret_cast<unsigned *>(s.sA + TC_ATILE);
+    s.sA = reinterpret_cast<float4 *>(s.sEB + TC_STAGES * TC_STAGE_BYTES);
+    s.sQ = s.sA + TC_ATILE;
     s.full = reinterpret_cast<uint64_t *>(s.sQ + TC_EPI_WARPS * TC_QCAP);
     s.empty = s.full + TC_STAGES;
     s.tfull = s.empty + TC_STAGES;
@@ -265,25 +287,30 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char *raw)
     s.afull = s.tempty + 2;
     s.aempty = s.afull + 2;
     s.tmemPtr = reinterpret_cast<uint32_t *>(s.aempty + 2);
+    s.info = s.tmemPtr + 4;
     s.extra = reinterpret_cast<unsigned *>(raw + tc_smem_base());
     return s;
 }
 
 // barriers + TMEM allocation (all threads call; returns the TMEM base address)
-__device__ __forceinline__ uint32_t tc_setup(const TcSmem &s)
+__device__ __forceinline__ uint32_t tc_setup(const TcSmem &s, int origInStage, int epiHoldsA)
 {
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+        // a stage is free again when its MMAs have completed (tcgen05.commit) AND the 16 epilogue
+        // warps are done with its original coordinates
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], origInStage ? 1 + TC_EPI_WARPS : 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.tfull[i], 1);
             mbar_init(&s.tempty[i], TC_EPI_WARPS);
             mbar_init(&s.afull[i], 1);
-            mbar_init(&s.aempty[i], 1);
+            // A buffer (and the per-item originals next to it) is free when the item's MMAs have
+            // completed and, if the epilogue reads per-item data, when the 16 epilogue warps are done
+            mbar_init(&s.aempty[i], epiHoldsA ? 1 + TC_EPI_WARPS : 1);
         }
         mbar_fence_init();
     }
-    if (warp == TC_EPI_WARPS) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(s.tmemPtr)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -297,57 +324,95 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem)
 {
     tc_fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == TC_EPI_WARPS)
+    if ((threadIdx.x >> 5) == TC_MMA_WARP)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
-// the control thread: TMA producer and MMA issuer in one instruction stream.  The producer cursor
-// runs at most TC_STAGES blocks and one item ahead of the MMA cursor, so every wait below is on work
-// this thread has already issued (no self-deadlock).
-__device__ __forceinline__ void tc_control(const TcGeom &geo, const TcSmem &s, uint32_t tmem)
+// TMA warp (converged, one elected lane issues): streams the A tile of every tensor-core item (16 KB, double-buffered) and its B
+// blocks (4 KB each, TC_STAGES-deep ring), and tells the MMA warp through info[slot] what each
+// stage is.  A final STOP stage ends the MMA warp's loop.
+__device__ __forceinline__ void tc_producer(const TcGeom &geo, const TcSmem &s)
 {
-    TcCursor P, C;
-    P.init(geo);
-    C = P;
     const size_t aBlkPerFrame = (size_t)geo.n1Pad / TC_BLK, bBlkPerFrame = (size_t)geo.n2Pad / TC_BLK;
-    while (C.valid) {
-        while (P.valid && P.g < C.g + TC_STAGES && P.kt <= C.kt + 1) {
-            if (P.jb == P.it.jb0) {                                  // first block of an item: its A tile
-                const unsigned ab = P.kt & 1u, u = P.kt >> 1;
-                mbar_wait(&s.aempty[ab], (u & 1u) ^ 1u);
-                mbar_expect_tx(&s.afull[ab], TC_ATILE * 32);
-                const unsigned char *src = reinterpret_cast<const unsigned char *>(geo.EA) +
-                    ((size_t)P.it.f * aBlkPerFrame + (size_t)P.it.ia * (TC_ATILE / TC_BLK)) * TC_BLK_BYTES;
-                tma_bulk_g2s(s.sEA + ab * (TC_ATILE * 32), src, TC_ATILE * 32, &s.afull[ab]);
-            }
-            const unsigned slot = P.g % TC_STAGES, u = P.g / TC_STAGES;
-            mbar_wait(&s.empty[slot], (u & 1u) ^ 1u);
-            mbar_expect_tx(&s.full[slot], TC_BLK_BYTES);
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(geo.EB) +
-                ((size_t)P.it.f * bBlkPerFrame + (size_t)P.jb) * TC_BLK_BYTES;
-            tma_bulk_g2s(s.sEB + slot * TC_BLK_BYTES, src, TC_BLK_BYTES, &s.full[slot]);
-            P.advance(geo);
+    const unsigned char *EA = reinterpret_cast<const unsigned char *>(geo.EA);
+    const unsigned char *EB = reinterpret_cast<const unsigned char *>(geo.EB);
+    const unsigned char *OB = reinterpret_cast<const unsigned char *>(geo.B);
+    unsigned g = 0, kt = 0;
+    TcWalk w;
+    w.init(geo);
+    for (; w.item < geo.nItems; w.next(geo)) {
+        TcItem it;
+        if (!w.decode(geo, it) || !it.tc) continue;
+        const unsigned ab = kt & 1u;
+        mbar_wait(&s.aempty[ab], ((kt >> 1) & 1u) ^ 1u);         // MMAs of item kt - 2 have read this buffer
+        if (tc_elect_one()) {
+            mbar_expect_tx(&s.afull[ab], TC_ATILE * 32 + geo.itemOrigBytes);
+            tma_bulk_g2s(s.sEA + ab * (TC_ATILE * 32),
+                         EA + ((size_t)it.f * aBlkPerFrame + (size_t)it.ia * (TC_ATILE / TC_BLK)) * TC_BLK_BYTES,
+                         TC_ATILE * 32, &s.afull[ab]);
+            if (geo.itemOrigBytes)
+                tma_bulk_g2s(reinterpret_cast<unsigned char *>(s.extra) + ab * geo.itemOrigBytes,
+                             OB + (size_t)it.f * bBlkPerFrame * TC_ORIG_BYTES, geo.itemOrigBytes, &s.afull[ab]);
         }
-        const unsigned ab = C.kt & 1u;
-        if (C.jb == C.it.jb0) mbar_wait(&s.afull[ab], (C.kt >> 1) & 1u);
-        const unsigned slot = C.g % TC_STAGES;
-        mbar_wait(&s.full[slot], (C.g / TC_STAGES) & 1u);
-        const uint32_t aBase = smem_u32(s.sEA + ab * (TC_ATILE * 32));
-        const uint32_t bBase = smem_u32(s.sEB + slot * TC_BLK_BYTES);
+        __syncwarp();
+        const unsigned char *src = EB + ((size_t)it.f * bBlkPerFrame + (size_t)it.jb0) * TC_BLK_BYTES;
+        const unsigned char *osrc = OB + ((size_t)it.f * bBlkPerFrame + (size_t)it.jb0) * TC_ORIG_BYTES;
+        for (int jb = it.jb0; jb < it.jb1; ++jb, ++g, src += TC_BLK_BYTES, osrc += TC_ORIG_BYTES) {
+            const unsigned slot = g % TC_STAGES;
+            mbar_wait(&s.empty[slot], ((g / TC_STAGES) & 1u) ^ 1u);
+            if (tc_elect_one()) {
+                s.info[slot] = ab | (jb == it.jb0 ? TC_INFO_FIRST : 0u) | (jb + 1 == it.jb1 ? TC_INFO_LAST : 0u);
+                mbar_expect_tx(&s.full[slot], geo.origInStage ? TC_STAGE_BYTES : TC_BLK_BYTES);
+                tma_bulk_g2s(s.sEB + slot * TC_STAGE_BYTES, src, TC_BLK_BYTES, &s.full[slot]);
+                if (geo.origInStage)
+                    tma_bulk_g2s(s.sEB + slot * TC_STAGE_BYTES + TC_BLK_BYTES, osrc, TC_ORIG_BYTES, &s.full[slot]);
+            }
+            __syncwarp();
+        }
+        ++kt;
+    }
+    const unsigned slot = g % TC_STAGES;
+    mbar_wait(&s.empty[slot], ((g / TC_STAGES) & 1u) ^ 1u);
+    if (tc_elect_one()) {
+        s.info[slot] = TC_INFO_STOP;
+        mbar_arrive(&s.full[slot]);
+    }
+    __syncwarp();
+}
+
+// MMA warp: the whole warp runs the loop (warp-uniform values stay in uniform registers), one
+// elected lane issues.  Per stage: 2 halves x 4 MMAs (A blocks) into TMEM columns [256 h + 64 t, +64).
+__device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem)
+{
+    const uint32_t aBase = smem_u32(s.sEA), bBase = smem_u32(s.sEB);
+    unsigned kt = 0;
+    for (unsigned g = 0;; ++g) {
+        const unsigned slot = g % TC_STAGES;
+        mbar_wait(&s.full[slot], (g / TC_STAGES) & 1u);
+        const unsigned info = s.info[slot];
+        if (info & TC_INFO_STOP) break;
+        const unsigned ab = info & TC_INFO_AB;
+        if (info & TC_INFO_FIRST) mbar_wait(&s.afull[ab], (kt >> 1) & 1u);
+        const uint64_t da0 = tc_smem_desc(aBase + ab * (TC_ATILE * 32));
+        const uint64_t db0 = tc_smem_desc(bBase + slot * TC_STAGE_BYTES);
         #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            mbar_wait(&s.tempty[h], (C.g & 1u) ^ 1u);                // epilogue has read the previous block's half
+            mbar_wait(&s.tempty[h], (g & 1u) ^ 1u);              // epilogue has read the previous block's half
             tc_fence_after();
-            const uint64_t db = tc_smem_desc(bBase + h * 1024);
-            #pragma unroll
-            for (int t = 0; t < 4; ++t)
-                tc_mma(tmem + (uint32_t)(h * 256 + t * 64), tc_smem_desc(aBase + t * TC_BLK_BYTES), db);
-            tc_commit(&s.tfull[h]);
+            if (tc_elect_one()) {
+                #pragma unroll
+                for (int t = 0; t < 4; ++t)                      // descriptor address field is in 16-byte units
+                    tc_mma(tmem + (uint32_t)(h * 256 + t * 64), da0 + (uint64_t)(t * (TC_BLK_BYTES >> 4)), db0 + (uint64_t)(h * (1024 >> 4)));
+                tc_commit(&s.tfull[h]);
+            }
+            __syncwarp();
         }
-        tc_commit(&s.empty[slot]);
-        const bool lastOfItem = (C.jb + 1 >= C.it.jb1);
-        if (lastOfItem) tc_commit(&s.aempty[ab]);
-        C.advance(geo);
+        if (tc_elect_one()) {
+            tc_commit(&s.empty[slot]);
+            if (info & TC_INFO_LAST) tc_commit(&s.aempty[ab]);
+        }
+        if (info & TC_INFO_LAST) ++kt;
+        __syncwarp();
     }
 }
 
@@ -376,6 +441,35 @@ __device__ __forceinline__ void tc_mask64(const float (&v)[64], const float (&mb
 }
 
 // ------------------------------------------------------------------------------------------
+// epilogue pieces shared by the two kernels
+// ------------------------------------------------------------------------------------------
+// Candidates of one TMEM half -> the warp's ring.  Every lane pushes its own candidates (bit k of
+// (mlo, mhi) = column k of the half), one per round, together with the ORIGINAL coordinates of the B
+// atom taken from the stage (entry.w = b.w bits | owner lane << 24), so the strict re-evaluation is
+// independent of the stage and can be batched into full warps.  `drain(32)` is called whenever 32
+// entries are queued.
+template <class Drain>
+__device__ __forceinline__ void tc_push(unsigned mlo, unsigned mhi, const float4 *origHalf, float4 *myQ,
+                                        int &qhead, int &qcount, int lane, unsigned ltmask, Drain &&drain)
+{
+    for (;;) {
+        const bool has = (mlo | mhi) != 0u;
+        const unsigned bal = __ballot_sync(NDA_FULL_MASK, has);
+        if (!bal) break;
+        if (has) {
+            int k;
+            if (mlo) { k = __ffs(mlo) - 1; mlo &= mlo - 1; }
+            else     { k = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
+            float4 b = origHalf[k];
+            b.w = __int_as_float((__float_as_int(b.w) & 0xffffff) | (lane << 24));
+            myQ[(qhead + qcount + __popc(bal & ltmask)) % TC_QCAP] = b;
+        }
+        qcount += __popc(bal);
+        if (qcount >= 32) drain(32);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // RDF on the tensor-core filter
 // ------------------------------------------------------------------------------------------
 struct RdfTcArgs {
@@ -398,24 +492,28 @@ rdf_tc_kernel(const RdfTcArgs p)
     const int H = p.nGroups * p.nBins;
 
     for (int i = tid; i < p.histCopies * H; i += TC_THREADS) hist[i] = 0u;
-    const uint32_t tmem = tc_setup(s);
+    const uint32_t tmem = tc_setup(s, 1, 0);
 
-    if (warp == TC_EPI_WARPS) {
-        if (lane == 0) tc_control(geo, s, tmem);
-        __syncwarp();
+    if (warp == TC_TMA_WARP) {
+        tc_producer(geo, s);
+    } else if (warp == TC_MMA_WARP) {
+        tc_mma_warp(s, tmem);
     } else {
         const int q = warp & 3, t = warp >> 2;
-        const int rowInTile = t * TC_BLK + q * 32 + lane;
+        const int rowWarp = t * TC_BLK + q * 32;               // this warp's first row in the A tile
+        const int rowInTile = rowWarp + lane;
         unsigned *myHist = hist + (warp % p.histCopies) * H;
-        unsigned *myQ = s.sQ + warp * TC_QCAP;
+        float4 *myQ = s.sQ + warp * TC_QCAP;
         const unsigned ltmask = lanemask_lt();
         const uint32_t tLane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 64);
         unsigned g = 0, nCand = 0;
         int sinceFlush = 0;
 
-        for (unsigned item = blockIdx.x; item < geo.nItems; item += gridDim.x) {
+        TcWalk walk;
+        walk.init(geo);
+        for (; walk.item < geo.nItems; walk.next(geo)) {
             TcItem it;
-            if (!tc_decode(geo, item, it)) continue;
+            if (!walk.decode(geo, it)) continue;
             if (++sinceFlush > PAIR_FLUSH_ITEMS) {             // u32 safety: spill shared histograms (atomic grab)
                 for (int i = lane; i < H; i += 32) {
                     const unsigned v = atomicExch(&myHist[i], 0u);
@@ -424,45 +522,40 @@ rdf_tc_kernel(const RdfTcArgs p)
                 sinceFlush = 1;
             }
             const FrameParams fpar = geo.fp[it.f];
-            const float4 *Aorig = geo.A + (size_t)it.f * geo.n1Pad + (size_t)it.ia * TC_ATILE;
-            const float4 *Borig = geo.B + (size_t)it.f * geo.n2Pad;
-            const float4 ao = Aorig[rowInTile];
-            __syncwarp();                                      // previous item's drains are done with sA
-            s.sA[rowInTile] = ao;
+            const float4 ao = geo.A[(size_t)it.f * geo.n1Pad + (size_t)it.ia * TC_ATILE + rowInTile];
+            s.sA[rowInTile] = ao;                              // read back by this warp only (drain)
             __syncwarp();
-            const int rowBase = it.ia * TC_ATILE;
-            const int rowWarp = t * TC_BLK + q * 32;           // this warp's first row in the tile
+            const int rowGlobal = it.ia * TC_ATILE + rowInTile;
 
             if (!it.tc) {
                 // all-exact frame: the reference arithmetic on every pair
+                const float4 *Borig = geo.B + (size_t)it.f * geo.n2Pad;
                 const int j0 = it.jb0 * TC_BLK, j1 = min(geo.n2, it.jb1 * TC_BLK);
                 for (int j = j0; j < j1; ++j) {
                     const float4 b = __ldg(&Borig[j]);
-                    if (!geo.sameSel || (j > rowBase + rowInTile)) {
+                    if (!geo.sameSel || (j > rowGlobal)) {
                         const float r2 = strict_r2(ao.x, ao.y, ao.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
                         const int idx = strict_bin(r2, p.dr, p.nBins);
                         if (idx >= 0) atomicAdd(&myHist[(kGrouped ? __float_as_int(b.w) : 0) * p.nBins + idx], 1u);
                     }
                 }
+                __syncwarp();
                 continue;
             }
 
             const float thrD = geo.thrDot[it.f];
             int qhead = 0, qcount = 0;
-            // strict re-evaluation of n queued candidates, one per lane; entry = (lane of the A row) << 24 | column
+            // strict re-evaluation of n queued candidates, one per lane
             auto drain = [&](int n) {
                 __syncwarp();
                 if (lane < n) {
-                    const unsigned e = myQ[(qhead + lane) % TC_QCAP];
-                    const int ai = rowWarp + (int)(e >> 24), bj = (int)(e & 0xffffffu);
-                    if (!geo.sameSel || (bj > rowBase + ai)) {
-                        const float4 a = s.sA[ai];
-                        const float4 b = __ldg(&Borig[bj]);
-                        const float r2 = p.fastStrict ? strict_r2_fastpath(a.x, a.y, a.z, b.x, b.y, b.z, fpar)
-                                                      : strict_r2(a.x, a.y, a.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
-                        const int idx = strict_bin(r2, p.dr, p.nBins);
-                        if (idx >= 0) atomicAdd(&myHist[(kGrouped ? __float_as_int(b.w) : 0) * p.nBins + idx], 1u);
-                    }
+                    const float4 b = myQ[(qhead + lane) % TC_QCAP];
+                    const int wb = __float_as_int(b.w);
+                    const float4 a = s.sA[rowWarp + ((wb >> 24) & 31)];
+                    const float r2 = p.fastStrict ? strict_r2_fastpath(a.x, a.y, a.z, b.x, b.y, b.z, fpar)
+                                                  : strict_r2(a.x, a.y, a.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
+                    const int idx = strict_bin(r2, p.dr, p.nBins);
+                    if (idx >= 0) atomicAdd(&myHist[(kGrouped ? (wb & 0xffffff) : 0) * p.nBins + idx], 1u);
                     ++nCand;
                 }
                 qhead = (qhead + n) % TC_QCAP;
@@ -471,6 +564,8 @@ rdf_tc_kernel(const RdfTcArgs p)
             };
 
             for (int jb = it.jb0; jb < it.jb1; ++jb, ++g) {
+                const unsigned slot = g % TC_STAGES;
+                const float4 *orig = reinterpret_cast<const float4 *>(s.sEB + slot * TC_STAGE_BYTES + TC_BLK_BYTES);
                 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
                     mbar_wait(&s.tfull[h], g & 1u);
@@ -489,23 +584,17 @@ rdf_tc_kernel(const RdfTcArgs p)
                     if (__any_sync(NDA_FULL_MASK, top >= thrD)) {
                         unsigned mlo, mhi;
                         tc_mask64(v, mb, thrD, mlo, mhi);
-                        const int colBase = jb * TC_BLK + h * 64;
-                        for (;;) {
-                            const bool has = (mlo | mhi) != 0u;
-                            const unsigned bal = __ballot_sync(NDA_FULL_MASK, has);
-                            if (!bal) break;
-                            if (has) {
-                                int k;
-                                if (mlo) { k = __ffs(mlo) - 1; mlo &= mlo - 1; }
-                                else     { k = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
-                                const int pos = (qhead + qcount + __popc(bal & ltmask)) % TC_QCAP;
-                                myQ[pos] = ((unsigned)lane << 24) | (unsigned)(colBase + k);
-                            }
-                            qcount += __popc(bal);
-                            if (qcount >= 32) drain(32);
+                        if (geo.sameSel) {                      // col > row only (getRadialNbrDensity.cpp:27)
+                            const int d = rowGlobal - (jb * TC_BLK + h * 64);     // columns k <= d are dropped
+                            const unsigned long long keep = d < 0 ? ~0ull : (d >= 63 ? 0ull : ~((2ull << d) - 1ull));
+                            mlo &= (unsigned)keep;
+                            mhi &= (unsigned)(keep >> 32);
                         }
+                        tc_push(mlo, mhi, orig + h * 64, myQ, qhead, qcount, lane, ltmask, drain);
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.empty[slot]);    // done with this stage's original coordinates
             }
             if (qcount > 0) drain(qcount);
         }
@@ -539,32 +628,75 @@ within_tc_kernel(const WithinTcArgs p)
     const TcSmem s = tc_carve(smem_raw);
     const TcGeom &geo = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tmem = tc_setup(s);
+    const uint32_t tmem = tc_setup(s, 0, 1);
 
-    if (warp == TC_EPI_WARPS) {
-        if (lane == 0) tc_control(geo, s, tmem);
-        __syncwarp();
+    if (warp == TC_TMA_WARP) {
+        tc_producer(geo, s);
+    } else if (warp == TC_MMA_WARP) {
+        tc_mma_warp(s, tmem);
     } else {
         const int q = warp & 3, t = warp >> 2;
-        const int rowInTile = t * TC_BLK + q * 32 + lane;
+        const int rowWarp = t * TC_BLK + q * 32;
+        const int rowInTile = rowWarp + lane;
+        // The main loop only RECORDS which (half, lane) saw a dot product above the threshold: one
+        // ballot per half, no data-dependent work, so the 16 warps that share a TMEM half stay in
+        // step.  The flagged halves are resolved at the end of the item (resolve()).
+        constexpr int kFlagCap = TC_QCAP * 2;                  // (half index, ballot) pairs in this warp's ring space
+        uint2 *flags = reinterpret_cast<uint2 *>(s.sQ + warp * TC_QCAP);
         const uint32_t tLane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 64);
-        unsigned g = 0, nCand = 0;
+        unsigned g = 0, kt = 0, nCand = 0;
 
-        for (unsigned item = blockIdx.x; item < geo.nItems; item += gridDim.x) {
+        TcWalk walk;
+        walk.init(geo);
+        for (; walk.item < geo.nItems; walk.next(geo)) {
             TcItem it;
-            if (!tc_decode(geo, item, it)) continue;
+            if (!walk.decode(geo, it)) continue;
             const FrameParams fpar = geo.fp[it.f];
             const float4 ao = geo.A[(size_t)it.f * geo.n1Pad + (size_t)it.ia * TC_ATILE + rowInTile];
-            const float4 *Borig = geo.B + (size_t)it.f * geo.n2Pad;
-            bool found = false;
+            const float4 *Bglob = geo.B + (size_t)it.f * geo.n2Pad;
+            unsigned foundMask = 0u;                           // warp-uniform: bit l = lane l's atom is within
 
             if (!it.tc) {
+                bool found = false;
                 for (int j = 0; j < geo.n2 && !__all_sync(NDA_FULL_MASK, found); ++j) {
-                    const float4 b = __ldg(&Borig[j]);
+                    const float4 b = __ldg(&Bglob[j]);
                     if (!found && strict_within(ao, b, fpar, p.d2, p.literal)) found = true;
                 }
+                foundMask = __ballot_sync(NDA_FULL_MASK, found);
             } else {
                 const float thrD = geo.thrDot[it.f];
+                // the frame's original refSel coordinates: shared memory (came with the A tile) or L2
+                const float4 *Bsrc = geo.itemOrigBytes
+                    ? reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(s.extra) + (kt & 1u) * geo.itemOrigBytes)
+                    : Bglob;
+                int nf = 0;
+                // Flagged (half, lane): the 64 columns of the half are re-evaluated with the reference
+                // arithmetic, two per lane, for the flagged lane's atom; atoms already found are skipped,
+                // so the count of strict evaluations stays ~ one half per found atom.
+                auto resolve = [&]() {
+                    __syncwarp();
+                    for (int i = 0; i < nf; ++i) {
+                        const uint2 fl = flags[i];
+                        unsigned owners = fl.y & ~foundMask;
+                        const float4 b0 = Bsrc[fl.x * 64 + lane];
+                        const float4 b1 = Bsrc[fl.x * 64 + 32 + lane];
+                        while (owners) {
+                            const int o = __ffs(owners) - 1;
+                            owners &= owners - 1;
+                            float4 a;
+                            a.x = __shfl_sync(NDA_FULL_MASK, ao.x, o);
+                            a.y = __shfl_sync(NDA_FULL_MASK, ao.y, o);
+                            a.z = __shfl_sync(NDA_FULL_MASK, ao.z, o);
+                            a.w = 0.f;
+                            const bool hit = strict_within(a, b0, fpar, p.d2, p.literal) || strict_within(a, b1, fpar, p.d2, p.literal);
+                            if (__any_sync(NDA_FULL_MASK, hit)) foundMask |= 1u << o;
+                            nCand += 2;
+                        }
+                    }
+                    nf = 0;
+                    __syncwarp();
+                };
+                if (geo.itemOrigBytes) mbar_wait(&s.afull[kt & 1u], (kt >> 1) & 1u);   // originals have landed
                 for (int jb = it.jb0; jb < it.jb1; ++jb, ++g) {
                     #pragma unroll 1
                     for (int h = 0; h < 2; ++h) {
@@ -579,33 +711,23 @@ within_tc_kernel(const WithinTcArgs p)
                         float mb[8];
                         #pragma unroll
                         for (int b = 0; b < 8; ++b) mb[b] = tc_max8(v + 8 * b);
-                        float top = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])),
-                                          fmaxf(fmaxf(mb[4], mb[5]), fmaxf(mb[6], mb[7])));
-                        if (found) top = -3.0e38f;             // a found atom needs no further test
-                        if (__any_sync(NDA_FULL_MASK, top >= thrD)) {
-                            // candidates are rare (about one per found atom plus the guard band):
-                            // evaluate them in place with the reference arithmetic
-                            unsigned mlo, mhi;
-                            tc_mask64(v, mb, thrD, mlo, mhi);
-                            if (found) { mlo = 0u; mhi = 0u; }
-                            const int colBase = jb * TC_BLK + h * 64;
-                            while (mlo | mhi) {
-                                int k;
-                                if (mlo) { k = __ffs(mlo) - 1; mlo &= mlo - 1; }
-                                else     { k = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
-                                const float4 b = __ldg(&Borig[colBase + k]);
-                                ++nCand;
-                                if (strict_within(ao, b, fpar, p.d2, p.literal)) { found = true; mlo = 0u; mhi = 0u; }
-                            }
-                            __syncwarp();
+                        const float top = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])),
+                                                fmaxf(fmaxf(mb[4], mb[5]), fmaxf(mb[6], mb[7])));
+                        const unsigned bal = __ballot_sync(NDA_FULL_MASK, top >= thrD) & ~foundMask;
+                        if (bal) {
+                            if (lane == 0) flags[nf] = make_uint2((unsigned)(jb * 2 + h), bal);
+                            if (++nf == kFlagCap) resolve();
                         }
                     }
                 }
+                if (nf) resolve();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.aempty[kt & 1u]);   // done with this item's original coordinates
+                ++kt;
             }
-            const unsigned w = __ballot_sync(NDA_FULL_MASK, found);
             if (lane == 0) {
-                const int word = (it.ia * TC_ATILE + t * TC_BLK + q * 32) >> 5;
-                if (word < p.wordsPerFrame) p.bits[(size_t)it.f * p.wordsPerFrame + word] = w;
+                const int word = (it.ia * TC_ATILE + rowWarp) >> 5;
+                if (word < p.wordsPerFrame) p.bits[(size_t)it.f * p.wordsPerFrame + word] = foundMask;
             }
         }
         #pragma unroll
