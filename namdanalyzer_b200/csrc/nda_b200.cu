@@ -231,7 +231,7 @@ static bool tc_frames_eligible(const float *cell, int fb, int fe, double T)
         const double P = (cx * cx + cy * cy + cz * cz) * k * k;
         const double Eb = P * (4.8828125e-04 * 1.01 + 3.814697265625e-06) + 1.0e-6;
         const double thr = T * 1.001 + 1.0e-6;
-        if (!(2.5 * Eb * 1.1 <= thr && thr * 1.1 <= P)) return false;
+        if (!(2.5 * Eb * 1.1 <= thr && thr * 1.1 <= P && P < 5.0e4)) return false;
     }
     return T > 0.0;
 }
@@ -272,10 +272,10 @@ static int frames_per_pass(size_t bytesPerFrame, int nF)
 // tensor-core filter drivers (nda_tc.cuh): pack -> embed -> prep -> one persistent kernel per pass
 // ------------------------------------------------------------------------------------------
 static int launch_embed(cudaStream_t st, const float4 *packed, int nPad, int nFc, const float *cell, int f0,
-                        __half *E, int roleA)
+                        const TcFrame *tf, __half *E, int roleA)
 {
     dim3 grid(nPad / TC_BLK, std::min(nFc, 65535));
-    embed_kernel<<<grid, 128, 0, st>>>(packed, nPad, nFc, cell, f0, E, roleA);
+    embed_kernel<<<grid, 128, 0, st>>>(packed, nPad, nFc, cell, f0, tf, E, roleA);
     LAUNCHED();
     return NDA_OK;
 }
@@ -303,7 +303,7 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
     CK(L.embA.reserve((size_t)n1Pad * pass * 32));
     CK(L.embB.reserve((size_t)n2Pad * pass * 32));
     CK(L.fp.reserve((size_t)pass * sizeof(FrameParams)));
-    CK(L.thrDot.reserve((size_t)pass * sizeof(float)));
+    CK(L.thrDot.reserve((size_t)pass * sizeof(TcFrame)));
     CK(L.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
     unsigned long long *stats = reinterpret_cast<unsigned long long *>(L.ctl.as<unsigned char>() + 16);
 
@@ -345,17 +345,17 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
         }
         g.A = L.packA.as<float4>();
         g.B = sameSel ? g.A : L.packB.as<float4>();
-        rc = launch_embed(st, g.A, n1Pad, nFc, d_cell, f0, L.embA.as<__half>(), 1);
-        if (rc) return rc;
-        rc = launch_embed(st, g.B, n2Pad, nFc, d_cell, f0, L.embB.as<__half>(), 0);
-        if (rc) return rc;
         prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
                                                              L.fp.as<FrameParams>(), stats);
         LAUNCHED();
-        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.fp.as<FrameParams>(), L.thrDot.as<float>(), stats);
+        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
+        rc = launch_embed(st, g.A, n1Pad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embA.as<__half>(), 1);
+        if (rc) return rc;
+        rc = launch_embed(st, g.B, n2Pad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embB.as<__half>(), 0);
+        if (rc) return rc;
         g.EA = L.embA.as<__half>(); g.EB = L.embB.as<__half>();
-        g.fp = L.fp.as<FrameParams>(); g.thrDot = L.thrDot.as<float>();
+        g.tf = L.thrDot.as<TcFrame>();
         const unsigned long long items = (unsigned long long)nFc * g.nATiles * g.nBChunks;
         if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
         g.nItems = (unsigned)items;
@@ -383,7 +383,7 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
     CK(L.embA.reserve((size_t)nAPad * pass * 32));
     CK(L.embB.reserve((size_t)nBPad * pass * 32));
     CK(L.fp.reserve((size_t)pass * sizeof(FrameParams)));
-    CK(L.thrDot.reserve((size_t)pass * sizeof(float)));
+    CK(L.thrDot.reserve((size_t)pass * sizeof(TcFrame)));
     CK(L.maxAbs.reserve((size_t)pass * sizeof(unsigned)));
     unsigned long long *stats = reinterpret_cast<unsigned long long *>(L.ctl.as<unsigned char>() + 16);
 
@@ -416,17 +416,17 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
         if (rc) return rc;
         g.A = L.packA.as<float4>();
         g.B = L.packB.as<float4>();
-        rc = launch_embed(st, g.A, nAPad, nFc, d_cell, f0, L.embA.as<__half>(), 1);
-        if (rc) return rc;
-        rc = launch_embed(st, g.B, nBPad, nFc, d_cell, f0, L.embB.as<__half>(), 0);
-        if (rc) return rc;
         prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
                                                              L.fp.as<FrameParams>(), stats);
         LAUNCHED();
-        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.fp.as<FrameParams>(), L.thrDot.as<float>(), stats);
+        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
+        rc = launch_embed(st, g.A, nAPad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embA.as<__half>(), 1);
+        if (rc) return rc;
+        rc = launch_embed(st, g.B, nBPad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embB.as<__half>(), 0);
+        if (rc) return rc;
         g.EA = L.embA.as<__half>(); g.EB = L.embB.as<__half>();
-        g.fp = L.fp.as<FrameParams>(); g.thrDot = L.thrDot.as<float>();
+        g.tf = L.thrDot.as<TcFrame>();
         a.bits = d_bits + (size_t)(f0 - fb) * words;
         const unsigned long long items = (unsigned long long)nFc * g.nATiles;
         if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");

@@ -50,8 +50,8 @@ constexpr int TC_ORIG_BYTES = TC_BLK * 16;                     // the block's OR
 constexpr int TC_STAGE_BYTES = TC_BLK_BYTES + TC_ORIG_BYTES;   // one B stage: embedding + originals (6 KB)
 constexpr int TC_STAGES    = 6;                                // B blocks in flight
 constexpr int TC_QCAP      = 64;                               // per-warp candidate ring, 16-byte entries
-// instruction descriptor: D = F32 (bit 4), A = B = F16, both K-major, N = 64 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
-constexpr uint32_t TC_IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D = F16 (bits 4-5 = 0), A = B = F16, both K-major, N = 64 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+constexpr uint32_t TC_IDESC = (0u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 __host__ __device__ constexpr size_t tc_smem_base()
 {
@@ -59,16 +59,61 @@ __host__ __device__ constexpr size_t tc_smem_base()
          + (size_t)TC_STAGES * TC_STAGE_BYTES   // B ring
          + (size_t)TC_ATILE * sizeof(float4)    // original A coordinates (strict re-evaluation)
          + (size_t)TC_EPI_WARPS * TC_QCAP * 16  // candidate rings
-         + 256;                                 // mbarriers + TMEM base
+         + 512;                                 // mbarriers, TMEM base, stage info, per-item frame parameters
+}
+
+// ------------------------------------------------------------------------------------------
+// per-frame parameters of the tensor-core path: the FrameParams of prep_frames_kernel plus the
+// dot-product threshold.  fp.thr already satisfies: strict r2 <= T  =>  exact minimum-image
+// r2 <= thr (guard band of prep_frames_kernel).  S <= r2 and dot = P - S/2, so
+//     strict in range  =>  dot_computed >= P - thr/2 - E.
+// Frames where the slack eats the range (2.5 E > thr) or the chord bound is useless (thr > P) are
+// run all-exact; the host only selects the tensor-core path when no frame of the call should end
+// there.  48 bytes so that the TMA warp can ship it next to the A tile.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) TcFrame {
+    FrameParams fp;
+    float thrDot;
+    float pad[3];
+};
+
+__global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, TcFrame *__restrict__ tf,
+                               unsigned long long *__restrict__ stats)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFc) return;
+    TcFrame o;
+    o.fp = fp[f];
+    o.thrDot = 3.0e38f;
+    o.pad[0] = o.pad[1] = o.pad[2] = 0.f;
+    if (!o.fp.exact_all) {
+        const double k = 0.15915494309189535;
+        const double rx = fabs((double)o.fp.cx) * k, ry = fabs((double)o.fp.cy) * k, rz = fabs((double)o.fp.cz) * k;
+        const double P = rx * rx + ry * ry + rz * rz;
+        const double Eb = P * (4.8828125e-04 * 1.01 + 3.814697265625e-06) + 1.0e-6;
+        const double thr = (double)o.fp.thr;
+        const double t = P - 0.5 * thr - 1.25 * Eb;
+        if (2.5 * Eb <= thr && thr <= P && t > 0.0 && P < 6.0e4) {      // P < 6e4: thrDot and every D fit fp16
+            o.thrDot = __double2float_rd(t);
+        } else {
+            o.fp.exact_all = 1;
+            atomicAdd(&stats[1], 1ull);
+        }
+    }
+    tf[f] = o;
 }
 
 // ------------------------------------------------------------------------------------------
 // embedding: packed float4 [nFc][nPad] -> fp16 blocks [nFc][nPad/128][2][128][8]
+//   A role: [hi(6), 1, 1 | lo(6), 0, 0]      B role: [hi(6), -t_hi, -t_lo | hi(6), 0, 0]
+// with t_hi + t_lo <= thrDot of the frame, so that the MMA delivers D = dot - thrDot and the SIGN of
+// D is the filter decision.  Padding and non-finite atoms get a zero embedding but keep slots 6/7:
+// their D is -thrDot < 0, never a candidate.
 // grid (nPad/128, min(nFc, 65535)), block 128
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 embed_kernel(const float4 *__restrict__ packed, int nPad, int nFc, const float *__restrict__ cell, int f0,
-             __half *__restrict__ E, int roleA)
+             const TcFrame *__restrict__ tf, __half *__restrict__ E, int roleA)
 {
     const int blk = blockIdx.x, tid = threadIdx.x;
     const int nBlk = nPad / TC_BLK;
@@ -96,46 +141,27 @@ embed_kernel(const float4 *__restrict__ packed, int nPad, int nFc, const float *
                 }
             }
         }
+        __align__(16) __half c1[8];
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) c1[i] = roleA ? lo[i] : hi[i];
+        if (roleA) {
+            hi[6] = __float2half_rn(1.f);
+            hi[7] = hi[6];
+        } else {
+            const float t = tf[f].thrDot;                       // 3e38 (-> inf) on all-exact frames: unused there
+            const __half th = __float2half_rd(t);
+            const __half tl = __float2half_rd(t - __half2float(th));
+            hi[6] = __hneg(th);
+            hi[7] = __hneg(tl);
+        }
         __half *dst = E + ((size_t)f * nBlk + blk) * (TC_BLK_BYTES / 2);
         *reinterpret_cast<uint4 *>(dst + tid * 8) = *reinterpret_cast<const uint4 *>(hi);
-        *reinterpret_cast<uint4 *>(dst + 1024 + tid * 8) = *reinterpret_cast<const uint4 *>(roleA ? lo : hi);
+        *reinterpret_cast<uint4 *>(dst + 1024 + tid * 8) = *reinterpret_cast<const uint4 *>(c1);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// per-frame dot-product threshold.  fp[f].thr already satisfies: strict r2 <= T  =>  exact
-// minimum-image r2 <= thr (guard band of prep_frames_kernel).  S <= r2 and dot = P - S/2, so
-//     strict in range  =>  dot_computed >= P - thr/2 - E.
-// Frames where the slack eats the range (2E > thr) or the chord bound is useless (thr > P) are run
-// all-exact; the host only selects the tensor-core path when no frame of the call should end there.
-// ------------------------------------------------------------------------------------------
-__global__ void prep_tc_kernel(const float *__restrict__ cell, int f0, int nFc, FrameParams *__restrict__ fp,
-                               float *__restrict__ thrDot, unsigned long long *__restrict__ stats)
-{
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nFc) return;
-    FrameParams p = fp[f];
-    float td = 3.0e38f;
-    if (!p.exact_all) {
-        const double k = 0.15915494309189535;
-        const double rx = fabs((double)p.cx) * k, ry = fabs((double)p.cy) * k, rz = fabs((double)p.cz) * k;
-        const double P = rx * rx + ry * ry + rz * rz;
-        const double Eb = P * (4.8828125e-04 * 1.01 + 3.814697265625e-06) + 1.0e-6;
-        const double thr = (double)p.thr;
-        const double t = P - 0.5 * thr - 1.25 * Eb;
-        if (2.5 * Eb <= thr && thr <= P && t > 0.0 && P < 1.0e30) {
-            td = __double2float_rd(t);
-        } else {
-            p.exact_all = 1;
-            fp[f].exact_all = 1;
-            atomicAdd(&stats[1], 1ull);
-        }
-    }
-    thrDot[f] = td;
-}
-
-// ------------------------------------------------------------------------------------------
-// tcgen05 / mbarrier helpers
+// tcgen05 / mbarrier helpers (shared-memory addresses as 32-bit values, computed once)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr)
 {
@@ -151,10 +177,9 @@ __device__ __forceinline__ void tc_mma(uint32_t dTmem, uint64_t descA, uint64_t 
                  :: "r"(dTmem), "l"(descA), "l"(descB), "r"(TC_IDESC), "r"(0u) : "memory");
 }
 
-__device__ __forceinline__ void tc_commit(uint64_t *bar)
+__device__ __forceinline__ void tc_commit(uint32_t bar)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                 :: "r"(smem_u32(bar)) : "memory");
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
 }
 
 // one lane of a converged warp (elect.sync): the form the compiler recognises as single-thread code,
@@ -169,42 +194,53 @@ __device__ __forceinline__ bool tc_elect_one()
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+__device__ __forceinline__ void bar_arrive(uint32_t bar)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
-// 64 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tc_ld64(uint32_t taddr, float (&v)[64])
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    uint32_t r[64];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ void tma_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// 64 consecutive fp16 accumulators of this thread's TMEM lane, two per register (.pack::16b:
+// register n = column 2n in the low half, column 2n + 1 in the high half; pinned by tools/tc_probe16.cu)
+__device__ __forceinline__ void tc_ld64p(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
-                 "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
-                 "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
-                   "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
-                   "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
-                   "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
-                   "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    #pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // ------------------------------------------------------------------------------------------
-// geometry shared by the two kernels: work items, cursors, shared-memory carve-up
+// geometry shared by the two kernels: work items, shared-memory carve-up
 // ------------------------------------------------------------------------------------------
 struct TcGeom {
     const float4 *A, *B;            // packed ORIGINAL coordinates [nFc][n1Pad], [nFc][n2Pad]
     const __half *EA, *EB;          // embeddings (A role / B role)
-    const FrameParams *fp;
-    const float *thrDot;
+    const TcFrame *tf;              // [nFc]
     int n1, n1Pad, n2, n2Pad;
     int nATiles;                    // n1Pad / 512
     int nBBlocks;                   // ceil(n2 / 128): blocks that hold real atoms
@@ -216,12 +252,15 @@ struct TcGeom {
     int itemOrigBytes;              // > 0: the frame's whole original B array travels with the A tile (within)
 };
 
-struct TcItem { int f, ia, jb0, jb1; bool tc; };
+struct TcItem { int f, ia, jb0, jb1; };
 
-// (frame, A tile, B chunk) of the items blockIdx.x + k gridDim.x, advanced without divisions
+// (frame, A tile, B chunk) of the items blockIdx.x + k gridDim.x, advanced without divisions; the
+// all-exact flag of the NEXT item's frame is fetched one item ahead so that no role ever waits for
+// L2 between two items
 struct TcWalk {
     unsigned item;
     int f, ia, kc, df, dia, dkc;
+    int exact;                      // tf[f].fp.exact_all of the current item
     __device__ __forceinline__ void init(const TcGeom &g)
     {
         const unsigned ipf = (unsigned)g.nATiles * (unsigned)g.nBChunks;
@@ -234,15 +273,18 @@ struct TcWalk {
         rem = gridDim.x % ipf;
         dia = (int)(rem / (unsigned)g.nBChunks);
         dkc = (int)(rem % (unsigned)g.nBChunks);
+        exact = (item < g.nItems) ? g.tf[f].fp.exact_all : 0;
     }
-    __device__ __forceinline__ void next(const TcGeom &g)
+    __device__ __forceinline__ TcWalk peek(const TcGeom &g) const
     {
-        item += gridDim.x;
-        kc += dkc;
-        if (kc >= g.nBChunks) { kc -= g.nBChunks; ++ia; }
-        ia += dia;
-        if (ia >= g.nATiles) { ia -= g.nATiles; ++f; }
-        f += df;
+        TcWalk n = *this;
+        n.item += gridDim.x;
+        n.kc += dkc;
+        if (n.kc >= g.nBChunks) { n.kc -= g.nBChunks; ++n.ia; }
+        n.ia += dia;
+        if (n.ia >= g.nATiles) { n.ia -= g.nATiles; ++n.f; }
+        n.f += df;
+        return n;
     }
     // false: the item has no work at all (chunk entirely below the diagonal)
     __device__ __forceinline__ bool decode(const TcGeom &g, TcItem &it) const
@@ -251,11 +293,22 @@ struct TcWalk {
         it.jb0 = kc * g.chunkBlocks;
         it.jb1 = min(g.nBBlocks, it.jb0 + g.chunkBlocks);
         if (g.sameSel) it.jb0 = max(it.jb0, (ia * TC_ATILE + 1) / TC_BLK);     // col > row only
-        if (it.jb0 >= it.jb1) return false;
-        it.tc = g.fp[f].exact_all == 0;
-        return true;
+        return it.jb0 < it.jb1;
     }
 };
+
+// for (w over this CTA's items): the next item's all-exact flag is requested before the body runs
+#define TC_FOR_ITEMS(w, geo)                                                                        \
+    for (TcWalk w = tc_walk_first(geo), w##_n = w; w.item < (geo).nItems; w = w##_n)                \
+        if ((w##_n = w.peek(geo)),                                                                  \
+            (w##_n.exact = (w##_n.item < (geo).nItems) ? (geo).tf[w##_n.f].fp.exact_all : 0), true)
+
+__device__ __forceinline__ TcWalk tc_walk_first(const TcGeom &g)
+{
+    TcWalk w;
+    w.init(g);
+    return w;
+}
 
 // per-stage word the TMA warp hands to the MMA warp (written before the arrive on full[slot])
 constexpr unsigned TC_INFO_AB = 1u, TC_INFO_FIRST = 2u, TC_INFO_LAST = 4u, TC_INFO_STOP = 8u;
@@ -270,6 +323,7 @@ struct TcSmem {
     uint64_t *afull, *aempty;   // [2] A tile buffers
     uint32_t *tmemPtr;
     unsigned *info;         // [TC_STAGES]
+    TcFrame  *sItem;        // [2]: frame parameters of the item in A buffer 0 / 1
     unsigned *extra;        // histograms (rdf) / per-item original B coordinates, double-buffered (within)
 };
 
@@ -288,25 +342,26 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char *raw)
     s.aempty = s.afull + 2;
     s.tmemPtr = reinterpret_cast<uint32_t *>(s.aempty + 2);
     s.info = s.tmemPtr + 4;
+    s.sItem = reinterpret_cast<TcFrame *>(reinterpret_cast<unsigned char *>(s.full) + 256);
     s.extra = reinterpret_cast<unsigned *>(raw + tc_smem_base());
     return s;
 }
 
 // barriers + TMEM allocation (all threads call; returns the TMEM base address)
-__device__ __forceinline__ uint32_t tc_setup(const TcSmem &s, int origInStage, int epiHoldsA)
+__device__ __forceinline__ uint32_t tc_setup(const TcSmem &s, int origInStage)
 {
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        // a stage is free again when its MMAs have completed (tcgen05.commit) AND the 16 epilogue
-        // warps are done with its original coordinates
+        // a stage is free again when its MMAs have completed (tcgen05.commit) and, if it carries
+        // original coordinates, when the 16 epilogue warps are done with them
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], origInStage ? 1 + TC_EPI_WARPS : 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.tfull[i], 1);
             mbar_init(&s.tempty[i], TC_EPI_WARPS);
             mbar_init(&s.afull[i], 1);
-            // A buffer (and the per-item originals next to it) is free when the item's MMAs have
-            // completed and, if the epilogue reads per-item data, when the 16 epilogue warps are done
-            mbar_init(&s.aempty[i], epiHoldsA ? 1 + TC_EPI_WARPS : 1);
+            // an A buffer (with the frame parameters and per-item originals next to it) is free when
+            // the item's MMAs have completed and the 16 epilogue warps have left the item
+            mbar_init(&s.aempty[i], 1 + TC_EPI_WARPS);
         }
         mbar_fence_init();
     }
@@ -328,54 +383,56 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
-// TMA warp (converged, one elected lane issues): streams the A tile of every tensor-core item (16 KB, double-buffered) and its B
-// blocks (4 KB each, TC_STAGES-deep ring), and tells the MMA warp through info[slot] what each
-// stage is.  A final STOP stage ends the MMA warp's loop.
+// TMA warp (converged, one elected lane issues): per tensor-core item the A tile's embedding (16 KB),
+// the frame parameters (48 B) and -- within -- the frame's original B coordinates, double-buffered;
+// per B block one stage of a TC_STAGES-deep ring.  info[slot] tells the MMA warp what each stage is;
+// a final STOP stage ends its loop.
 __device__ __forceinline__ void tc_producer(const TcGeom &geo, const TcSmem &s)
 {
     const size_t aBlkPerFrame = (size_t)geo.n1Pad / TC_BLK, bBlkPerFrame = (size_t)geo.n2Pad / TC_BLK;
     const unsigned char *EA = reinterpret_cast<const unsigned char *>(geo.EA);
     const unsigned char *EB = reinterpret_cast<const unsigned char *>(geo.EB);
     const unsigned char *OB = reinterpret_cast<const unsigned char *>(geo.B);
-    unsigned g = 0, kt = 0;
-    TcWalk w;
-    w.init(geo);
-    for (; w.item < geo.nItems; w.next(geo)) {
+    const uint32_t sEA = smem_u32(s.sEA), sEB = smem_u32(s.sEB), sItem = smem_u32(s.sItem), sExtra = smem_u32(s.extra);
+    const uint32_t full0 = smem_u32(s.full), empty0 = smem_u32(s.empty), afull0 = smem_u32(s.afull), aempty0 = smem_u32(s.aempty);
+    const uint32_t stageTx = geo.origInStage ? TC_STAGE_BYTES : TC_BLK_BYTES;
+    unsigned g = 0, kt = 0, slot = 0, sphase = 0;
+    TC_FOR_ITEMS(w, geo) {
         TcItem it;
-        if (!w.decode(geo, it) || !it.tc) continue;
+        if (!w.decode(geo, it) || w.exact) continue;
         const unsigned ab = kt & 1u;
-        mbar_wait(&s.aempty[ab], ((kt >> 1) & 1u) ^ 1u);         // MMAs of item kt - 2 have read this buffer
+        bar_wait(aempty0 + ab * 8, ((kt >> 1) & 1u) ^ 1u);       // item kt - 2 has left this buffer
         if (tc_elect_one()) {
-            mbar_expect_tx(&s.afull[ab], TC_ATILE * 32 + geo.itemOrigBytes);
-            tma_bulk_g2s(s.sEA + ab * (TC_ATILE * 32),
-                         EA + ((size_t)it.f * aBlkPerFrame + (size_t)it.ia * (TC_ATILE / TC_BLK)) * TC_BLK_BYTES,
-                         TC_ATILE * 32, &s.afull[ab]);
+            bar_expect_tx(afull0 + ab * 8, TC_ATILE * 32 + (uint32_t)sizeof(TcFrame) + geo.itemOrigBytes);
+            tma_g2s(sEA + ab * (TC_ATILE * 32),
+                    EA + ((size_t)it.f * aBlkPerFrame + (size_t)it.ia * (TC_ATILE / TC_BLK)) * TC_BLK_BYTES,
+                    TC_ATILE * 32, afull0 + ab * 8);
+            tma_g2s(sItem + ab * (uint32_t)sizeof(TcFrame), geo.tf + it.f, (uint32_t)sizeof(TcFrame), afull0 + ab * 8);
             if (geo.itemOrigBytes)
-                tma_bulk_g2s(reinterpret_cast<unsigned char *>(s.extra) + ab * geo.itemOrigBytes,
-                             OB + (size_t)it.f * bBlkPerFrame * TC_ORIG_BYTES, geo.itemOrigBytes, &s.afull[ab]);
+                tma_g2s(sExtra + ab * geo.itemOrigBytes, OB + (size_t)it.f * bBlkPerFrame * TC_ORIG_BYTES,
+                        geo.itemOrigBytes, afull0 + ab * 8);
         }
         __syncwarp();
         const unsigned char *src = EB + ((size_t)it.f * bBlkPerFrame + (size_t)it.jb0) * TC_BLK_BYTES;
         const unsigned char *osrc = OB + ((size_t)it.f * bBlkPerFrame + (size_t)it.jb0) * TC_ORIG_BYTES;
         for (int jb = it.jb0; jb < it.jb1; ++jb, ++g, src += TC_BLK_BYTES, osrc += TC_ORIG_BYTES) {
-            const unsigned slot = g % TC_STAGES;
-            mbar_wait(&s.empty[slot], ((g / TC_STAGES) & 1u) ^ 1u);
+            bar_wait(empty0 + slot * 8, sphase ^ 1u);
             if (tc_elect_one()) {
                 s.info[slot] = ab | (jb == it.jb0 ? TC_INFO_FIRST : 0u) | (jb + 1 == it.jb1 ? TC_INFO_LAST : 0u);
-                mbar_expect_tx(&s.full[slot], geo.origInStage ? TC_STAGE_BYTES : TC_BLK_BYTES);
-                tma_bulk_g2s(s.sEB + slot * TC_STAGE_BYTES, src, TC_BLK_BYTES, &s.full[slot]);
+                bar_expect_tx(full0 + slot * 8, stageTx);
+                tma_g2s(sEB + slot * TC_STAGE_BYTES, src, TC_BLK_BYTES, full0 + slot * 8);
                 if (geo.origInStage)
-                    tma_bulk_g2s(s.sEB + slot * TC_STAGE_BYTES + TC_BLK_BYTES, osrc, TC_ORIG_BYTES, &s.full[slot]);
+                    tma_g2s(sEB + slot * TC_STAGE_BYTES + TC_BLK_BYTES, osrc, TC_ORIG_BYTES, full0 + slot * 8);
             }
             __syncwarp();
+            if (++slot == TC_STAGES) { slot = 0; sphase ^= 1u; }
         }
         ++kt;
     }
-    const unsigned slot = g % TC_STAGES;
-    mbar_wait(&s.empty[slot], ((g / TC_STAGES) & 1u) ^ 1u);
+    bar_wait(empty0 + slot * 8, sphase ^ 1u);
     if (tc_elect_one()) {
         s.info[slot] = TC_INFO_STOP;
-        mbar_arrive(&s.full[slot]);
+        bar_arrive(full0 + slot * 8);
     }
     __syncwarp();
 }
@@ -385,64 +442,102 @@ __device__ __forceinline__ void tc_producer(const TcGeom &geo, const TcSmem &s)
 __device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem)
 {
     const uint32_t aBase = smem_u32(s.sEA), bBase = smem_u32(s.sEB);
-    unsigned kt = 0;
+    const uint32_t full0 = smem_u32(s.full), empty0 = smem_u32(s.empty), afull0 = smem_u32(s.afull), aempty0 = smem_u32(s.aempty);
+    const uint32_t tfull0 = smem_u32(s.tfull), tempty0 = smem_u32(s.tempty);
+    unsigned kt = 0, slot = 0, sphase = 0;
     for (unsigned g = 0;; ++g) {
-        const unsigned slot = g % TC_STAGES;
-        mbar_wait(&s.full[slot], (g / TC_STAGES) & 1u);
+        bar_wait(full0 + slot * 8, sphase);
         const unsigned info = s.info[slot];
         if (info & TC_INFO_STOP) break;
         const unsigned ab = info & TC_INFO_AB;
-        if (info & TC_INFO_FIRST) mbar_wait(&s.afull[ab], (kt >> 1) & 1u);
+        if (info & TC_INFO_FIRST) bar_wait(afull0 + ab * 8, (kt >> 1) & 1u);
         const uint64_t da0 = tc_smem_desc(aBase + ab * (TC_ATILE * 32));
         const uint64_t db0 = tc_smem_desc(bBase + slot * TC_STAGE_BYTES);
         #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            mbar_wait(&s.tempty[h], (g & 1u) ^ 1u);              // epilogue has read the previous block's half
+            bar_wait(tempty0 + h * 8, (g & 1u) ^ 1u);            // epilogue has read the previous block's half
             tc_fence_after();
             if (tc_elect_one()) {
                 #pragma unroll
                 for (int t = 0; t < 4; ++t)                      // descriptor address field is in 16-byte units
                     tc_mma(tmem + (uint32_t)(h * 256 + t * 64), da0 + (uint64_t)(t * (TC_BLK_BYTES >> 4)), db0 + (uint64_t)(h * (1024 >> 4)));
-                tc_commit(&s.tfull[h]);
+                tc_commit(tfull0 + h * 8);
             }
             __syncwarp();
         }
         if (tc_elect_one()) {
-            tc_commit(&s.empty[slot]);
-            if (info & TC_INFO_LAST) tc_commit(&s.aempty[ab]);
+            tc_commit(empty0 + slot * 8);
+            if (info & TC_INFO_LAST) tc_commit(aempty0 + ab * 8);
         }
         if (info & TC_INFO_LAST) ++kt;
         __syncwarp();
-    }
-}
-
-// max of 8 accumulators (FMNMX3 chain)
-__device__ __forceinline__ float tc_max8(const float *v)
-{
-    float m = fmaxf(fmaxf(v[0], v[1]), v[2]);
-    m = fmaxf(fmaxf(m, v[3]), v[4]);
-    m = fmaxf(fmaxf(m, v[5]), v[6]);
-    return fmaxf(m, v[7]);
-}
-
-// bit k of (lo, hi) = (v[k] >= thr), evaluated only inside the 8-column groups whose maximum passes
-__device__ __forceinline__ void tc_mask64(const float (&v)[64], const float (&mb)[8], float thr, unsigned &lo, unsigned &hi)
-{
-    lo = 0u; hi = 0u;
-    #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        if (__any_sync(NDA_FULL_MASK, mb[b] >= thr)) {
-            unsigned m = 0u;
-            #pragma unroll
-            for (int k = 0; k < 8; ++k) m |= (v[8 * b + k] >= thr) ? (1u << k) : 0u;
-            if (b < 4) lo |= m << (8 * b); else hi |= m << (8 * (b - 4));
-        }
+        if (++slot == TC_STAGES) { slot = 0; sphase ^= 1u; }
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // epilogue pieces shared by the two kernels
 // ------------------------------------------------------------------------------------------
+// D = dot - thrDot as packed fp16: a pair is a candidate iff its SIGN bit is clear.  AND-ing registers
+// keeps bit 15 / 31 set only if every column folded in is negative, so one LOP3 tests four columns.
+constexpr unsigned TC_SIGNS = 0x80008000u;
+
+// bit k of (lo, hi) = column k is a candidate, evaluated only inside the 8-column groups (4 registers)
+// whose AND shows a clear sign bit
+__device__ __forceinline__ void tc_mask64(const uint32_t (&r)[32], const uint32_t (&gb)[8], unsigned &lo, unsigned &hi)
+{
+    lo = 0u; hi = 0u;
+    #pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if (__any_sync(NDA_FULL_MASK, (gb[b] & TC_SIGNS) != TC_SIGNS)) {
+            unsigned m = 0u;
+            #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned c = ~r[4 * b + i];
+                m |= ((c >> 15) & 1u) << (2 * i);
+                m |= (c >> 31) << (2 * i + 1);
+            }
+            if (b < 4) lo |= m << (8 * b); else hi |= m << (8 * (b - 4));
+        }
+    }
+}
+
+// per-warp constants of the epilogue loop
+struct TcEpi {
+    uint32_t tfull[2], tempty[2], tm[2];     // barrier addresses and TMEM addresses of the two halves
+    uint32_t empty0, afull0, aempty0;
+    int q, t, lane, rowWarp;
+    __device__ __forceinline__ void init(const TcSmem &s, uint32_t tmem)
+    {
+        const int warp = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        q = warp & 3; t = warp >> 2;
+        rowWarp = t * TC_BLK + q * 32;
+        #pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            tfull[h] = smem_u32(&s.tfull[h]);
+            tempty[h] = smem_u32(&s.tempty[h]);
+            tm[h] = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + t * 64);
+        }
+        empty0 = smem_u32(s.empty); afull0 = smem_u32(s.afull); aempty0 = smem_u32(s.aempty);
+    }
+    // one TMEM half: wait, load 64 accumulators, hand the half back to the MMA warp, reduce.
+    // cand = this lane's atom has at least one candidate among the 64 columns
+    __device__ __forceinline__ void load_half(int h, unsigned parity, uint32_t (&r)[32], uint32_t (&gb)[8], bool &cand) const
+    {
+        bar_wait(tfull[h], parity);
+        tc_fence_after();
+        tc_ld64p(tm[h], r);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(tempty[h]);                  // the next block's MMAs into this half may start
+        #pragma unroll
+        for (int b = 0; b < 8; ++b) gb[b] = r[4 * b] & r[4 * b + 1] & r[4 * b + 2] & r[4 * b + 3];
+        const uint32_t top = (gb[0] & gb[1] & gb[2]) & (gb[3] & gb[4] & gb[5]) & (gb[6] & gb[7]);
+        cand = (top & TC_SIGNS) != TC_SIGNS;
+    }
+};
+
 // Candidates of one TMEM half -> the warp's ring.  Every lane pushes its own candidates (bit k of
 // (mlo, mhi) = column k of the half), one per round, together with the ORIGINAL coordinates of the B
 // atom taken from the stage (entry.w = b.w bits | owner lane << 24), so the strict re-evaluation is
@@ -492,28 +587,25 @@ rdf_tc_kernel(const RdfTcArgs p)
     const int H = p.nGroups * p.nBins;
 
     for (int i = tid; i < p.histCopies * H; i += TC_THREADS) hist[i] = 0u;
-    const uint32_t tmem = tc_setup(s, 1, 0);
+    const uint32_t tmem = tc_setup(s, 1);
 
     if (warp == TC_TMA_WARP) {
         tc_producer(geo, s);
     } else if (warp == TC_MMA_WARP) {
         tc_mma_warp(s, tmem);
     } else {
-        const int q = warp & 3, t = warp >> 2;
-        const int rowWarp = t * TC_BLK + q * 32;               // this warp's first row in the A tile
-        const int rowInTile = rowWarp + lane;
+        TcEpi ep;
+        ep.init(s, tmem);
+        const int rowWarp = ep.rowWarp, rowInTile = rowWarp + lane;
         unsigned *myHist = hist + (warp % p.histCopies) * H;
         float4 *myQ = s.sQ + warp * TC_QCAP;
         const unsigned ltmask = lanemask_lt();
-        const uint32_t tLane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 64);
-        unsigned g = 0, nCand = 0;
+        unsigned g = 0, kt = 0, nCand = 0, slot = 0;
         int sinceFlush = 0;
 
-        TcWalk walk;
-        walk.init(geo);
-        for (; walk.item < geo.nItems; walk.next(geo)) {
+        TC_FOR_ITEMS(w, geo) {
             TcItem it;
-            if (!walk.decode(geo, it)) continue;
+            if (!w.decode(geo, it)) continue;
             if (++sinceFlush > PAIR_FLUSH_ITEMS) {             // u32 safety: spill shared histograms (atomic grab)
                 for (int i = lane; i < H; i += 32) {
                     const unsigned v = atomicExch(&myHist[i], 0u);
@@ -521,14 +613,14 @@ rdf_tc_kernel(const RdfTcArgs p)
                 }
                 sinceFlush = 1;
             }
-            const FrameParams fpar = geo.fp[it.f];
             const float4 ao = geo.A[(size_t)it.f * geo.n1Pad + (size_t)it.ia * TC_ATILE + rowInTile];
             s.sA[rowInTile] = ao;                              // read back by this warp only (drain)
             __syncwarp();
             const int rowGlobal = it.ia * TC_ATILE + rowInTile;
 
-            if (!it.tc) {
+            if (w.exact) {
                 // all-exact frame: the reference arithmetic on every pair
+                const FrameParams fpar = geo.tf[it.f].fp;
                 const float4 *Borig = geo.B + (size_t)it.f * geo.n2Pad;
                 const int j0 = it.jb0 * TC_BLK, j1 = min(geo.n2, it.jb1 * TC_BLK);
                 for (int j = j0; j < j1; ++j) {
@@ -543,7 +635,9 @@ rdf_tc_kernel(const RdfTcArgs p)
                 continue;
             }
 
-            const float thrD = geo.thrDot[it.f];
+            const unsigned ab = kt & 1u;
+            bar_wait(ep.afull0 + ab * 8, (kt >> 1) & 1u);      // frame parameters have landed next to the A tile
+            const TcFrame *tfS = &s.sItem[ab];
             int qhead = 0, qcount = 0;
             // strict re-evaluation of n queued candidates, one per lane
             auto drain = [&](int n) {
@@ -552,6 +646,7 @@ rdf_tc_kernel(const RdfTcArgs p)
                     const float4 b = myQ[(qhead + lane) % TC_QCAP];
                     const int wb = __float_as_int(b.w);
                     const float4 a = s.sA[rowWarp + ((wb >> 24) & 31)];
+                    const FrameParams fpar = tfS->fp;
                     const float r2 = p.fastStrict ? strict_r2_fastpath(a.x, a.y, a.z, b.x, b.y, b.z, fpar)
                                                   : strict_r2(a.x, a.y, a.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
                     const int idx = strict_bin(r2, p.dr, p.nBins);
@@ -564,26 +659,15 @@ rdf_tc_kernel(const RdfTcArgs p)
             };
 
             for (int jb = it.jb0; jb < it.jb1; ++jb, ++g) {
-                const unsigned slot = g % TC_STAGES;
                 const float4 *orig = reinterpret_cast<const float4 *>(s.sEB + slot * TC_STAGE_BYTES + TC_BLK_BYTES);
-                #pragma unroll 1
+                #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    mbar_wait(&s.tfull[h], g & 1u);
-                    tc_fence_after();
-                    float v[64];
-                    tc_ld64(tLane + (uint32_t)(h * 256), v);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s.tempty[h]);  // TMEM half free: the next block's MMAs may start
-
-                    float mb[8];
-                    #pragma unroll
-                    for (int b = 0; b < 8; ++b) mb[b] = tc_max8(v + 8 * b);
-                    const float top = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])),
-                                            fmaxf(fmaxf(mb[4], mb[5]), fmaxf(mb[6], mb[7])));
-                    if (__any_sync(NDA_FULL_MASK, top >= thrD)) {
+                    uint32_t r[32], gb[8];
+                    bool cand;
+                    ep.load_half(h, g & 1u, r, gb, cand);
+                    if (__any_sync(NDA_FULL_MASK, cand)) {
                         unsigned mlo, mhi;
-                        tc_mask64(v, mb, thrD, mlo, mhi);
+                        tc_mask64(r, gb, mlo, mhi);
                         if (geo.sameSel) {                      // col > row only (getRadialNbrDensity.cpp:27)
                             const int d = rowGlobal - (jb * TC_BLK + h * 64);     // columns k <= d are dropped
                             const unsigned long long keep = d < 0 ? ~0ull : (d >= 63 ? 0ull : ~((2ull << d) - 1ull));
@@ -594,9 +678,13 @@ rdf_tc_kernel(const RdfTcArgs p)
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s.empty[slot]);    // done with this stage's original coordinates
+                if (lane == 0) bar_arrive(ep.empty0 + slot * 8);   // done with this stage's original coordinates
+                if (++slot == TC_STAGES) slot = 0;
             }
             if (qcount > 0) drain(qcount);
+            __syncwarp();
+            if (lane == 0) bar_arrive(ep.aempty0 + ab * 8);    // done with this item's frame parameters
+            ++kt;
         }
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nCand += __shfl_xor_sync(NDA_FULL_MASK, nCand, o);
@@ -628,35 +716,33 @@ within_tc_kernel(const WithinTcArgs p)
     const TcSmem s = tc_carve(smem_raw);
     const TcGeom &geo = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tmem = tc_setup(s, 0, 1);
+    const uint32_t tmem = tc_setup(s, 0);
 
     if (warp == TC_TMA_WARP) {
         tc_producer(geo, s);
     } else if (warp == TC_MMA_WARP) {
         tc_mma_warp(s, tmem);
     } else {
-        const int q = warp & 3, t = warp >> 2;
-        const int rowWarp = t * TC_BLK + q * 32;
-        const int rowInTile = rowWarp + lane;
+        TcEpi ep;
+        ep.init(s, tmem);
+        const int rowWarp = ep.rowWarp, rowInTile = rowWarp + lane;
         // The main loop only RECORDS which (half, lane) saw a dot product above the threshold: one
         // ballot per half, no data-dependent work, so the 16 warps that share a TMEM half stay in
         // step.  The flagged halves are resolved at the end of the item (resolve()).
         constexpr int kFlagCap = TC_QCAP * 2;                  // (half index, ballot) pairs in this warp's ring space
         uint2 *flags = reinterpret_cast<uint2 *>(s.sQ + warp * TC_QCAP);
-        const uint32_t tLane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 64);
         unsigned g = 0, kt = 0, nCand = 0;
 
-        TcWalk walk;
-        walk.init(geo);
-        for (; walk.item < geo.nItems; walk.next(geo)) {
+        TC_FOR_ITEMS(w, geo) {
             TcItem it;
-            if (!walk.decode(geo, it)) continue;
-            const FrameParams fpar = geo.fp[it.f];
-            const float4 ao = geo.A[(size_t)it.f * geo.n1Pad + (size_t)it.ia * TC_ATILE + rowInTile];
+            if (!w.decode(geo, it)) continue;
             const float4 *Bglob = geo.B + (size_t)it.f * geo.n2Pad;
+            const float4 *Aglob = geo.A + (size_t)it.f * geo.n1Pad + (size_t)it.ia * TC_ATILE;
             unsigned foundMask = 0u;                           // warp-uniform: bit l = lane l's atom is within
 
-            if (!it.tc) {
+            if (w.exact) {
+                const FrameParams fpar = geo.tf[it.f].fp;
+                const float4 ao = Aglob[rowInTile];
                 bool found = false;
                 for (int j = 0; j < geo.n2 && !__all_sync(NDA_FULL_MASK, found); ++j) {
                     const float4 b = __ldg(&Bglob[j]);
@@ -664,10 +750,12 @@ within_tc_kernel(const WithinTcArgs p)
                 }
                 foundMask = __ballot_sync(NDA_FULL_MASK, found);
             } else {
-                const float thrD = geo.thrDot[it.f];
+                const unsigned ab = kt & 1u;
+                bar_wait(ep.afull0 + ab * 8, (kt >> 1) & 1u);  // frame parameters (and originals) have landed
+                const TcFrame *tfS = &s.sItem[ab];
                 // the frame's original refSel coordinates: shared memory (came with the A tile) or L2
                 const float4 *Bsrc = geo.itemOrigBytes
-                    ? reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(s.extra) + (kt & 1u) * geo.itemOrigBytes)
+                    ? reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(s.extra) + ab * geo.itemOrigBytes)
                     : Bglob;
                 int nf = 0;
                 // Flagged (half, lane): the 64 columns of the half are re-evaluated with the reference
@@ -675,9 +763,12 @@ within_tc_kernel(const WithinTcArgs p)
                 // so the count of strict evaluations stays ~ one half per found atom.
                 auto resolve = [&]() {
                     __syncwarp();
+                    const FrameParams fpar = tfS->fp;
+                    const float4 ao = Aglob[rowInTile];
                     for (int i = 0; i < nf; ++i) {
                         const uint2 fl = flags[i];
                         unsigned owners = fl.y & ~foundMask;
+                        if (!owners) continue;
                         const float4 b0 = Bsrc[fl.x * 64 + lane];
                         const float4 b1 = Bsrc[fl.x * 64 + 32 + lane];
                         while (owners) {
@@ -696,24 +787,13 @@ within_tc_kernel(const WithinTcArgs p)
                     nf = 0;
                     __syncwarp();
                 };
-                if (geo.itemOrigBytes) mbar_wait(&s.afull[kt & 1u], (kt >> 1) & 1u);   // originals have landed
                 for (int jb = it.jb0; jb < it.jb1; ++jb, ++g) {
-                    #pragma unroll 1
+                    #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        mbar_wait(&s.tfull[h], g & 1u);
-                        tc_fence_after();
-                        float v[64];
-                        tc_ld64(tLane + (uint32_t)(h * 256), v);
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&s.tempty[h]);
-
-                        float mb[8];
-                        #pragma unroll
-                        for (int b = 0; b < 8; ++b) mb[b] = tc_max8(v + 8 * b);
-                        const float top = fmaxf(fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])),
-                                                fmaxf(fmaxf(mb[4], mb[5]), fmaxf(mb[6], mb[7])));
-                        const unsigned bal = __ballot_sync(NDA_FULL_MASK, top >= thrD) & ~foundMask;
+                        uint32_t r[32], gb[8];
+                        bool cand;
+                        ep.load_half(h, g & 1u, r, gb, cand);
+                        const unsigned bal = __ballot_sync(NDA_FULL_MASK, cand) & ~foundMask;
                         if (bal) {
                             if (lane == 0) flags[nf] = make_uint2((unsigned)(jb * 2 + h), bal);
                             if (++nf == kFlagCap) resolve();
@@ -722,7 +802,7 @@ within_tc_kernel(const WithinTcArgs p)
                 }
                 if (nf) resolve();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s.aempty[kt & 1u]);   // done with this item's original coordinates
+                if (lane == 0) bar_arrive(ep.aempty0 + ab * 8);   // done with this item's shared-memory data
                 ++kt;
             }
             if (lane == 0) {
