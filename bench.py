@@ -319,29 +319,72 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
 
-    # ---- roofline of the dominant kernel (within_kernel), FP32 pipe
+    # ---- roofline of the dominant kernel
     peak0, peak1 = ctypes.c_double(0), ctypes.c_double(0)
     _capi.check(lib.nda_measure_fp32_peak(0, ctypes.byref(peak0)))
     _capi.check(lib.nda_measure_fp32_peak(1, ctypes.byref(peak1)))
     peak = max(peak0.value, peak1.value)
     k_ms = float(np.mean(kern_ms))
     achieved = pairs_step * FLOP_WITHIN / (k_ms * 1e-3) / 1e12
+    filt = int(lib.nda_last_filter())
+    tensor_path = filt == 100
+    kname = "within_tc_kernel" if tensor_path else "within_kernel"
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic_latest.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("within_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get(kname + "_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp32", "kernel": "within_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": traffic,
-                "peak_source": "FFMA loop measured live on this GPU (scalar %.1f, f32x2 %.1f TFLOP/s); "
-                               "MEASURED_PEAKS.json has no FP32 figure; nominal 2*128*148*1.965 GHz = %.1f"
-                               % (peak0.value, peak1.value, FP32_NOMINAL_TFLOPS),
-                "frac_of_nominal": achieved / FP32_NOMINAL_TFLOPS,
-                "flop_per_pair": FLOP_WITHIN, "pairs_per_launch": pairs_step,
-                "kernel_ms": k_ms, "kernel_share_of_step": k_ms * args.steps / ms_total if world == 1 else None,
-                "kernel_pairs_per_s": pairs_step / (k_ms * 1e-3)}
+    fp32_view = {"achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                 "frac_of_nominal": achieved / FP32_NOMINAL_TFLOPS, "flop_per_pair": FLOP_WITHIN,
+                 "peak_source": "FFMA loop measured live on this GPU (scalar %.1f, f32x2 %.1f TFLOP/s); "
+                                "MEASURED_PEAKS.json has no FP32 figure; nominal 2*128*148*1.965 GHz = %.1f"
+                                % (peak0.value, peak1.value, FP32_NOMINAL_TFLOPS),
+                 "note": "algorithmic flops of the REFERENCE arithmetic (SURVEY 8d: 21 per within pair) over the FP32 "
+                         "peak; above 1 when the filter runs on the tensor cores"}
+    common = {"kernel": kname, "pairs_per_launch": pairs_step, "kernel_ms": k_ms,
+              "kernel_share_of_step": k_ms * args.steps / ms_total if world == 1 else None,
+              "kernel_pairs_per_s": pairs_step / (k_ms * 1e-3), "traffic": traffic}
+    if tensor_path:
+        # executed tensor flops: one tcgen05.mma (kind::f16, K = 16) row x column = 2 * 16 flop per pair
+        tpeak, tsrc = 1590.0, "fallback of B200_PROFILING.md"
+        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(mp):
+            try:
+                tpeak, tsrc = float(json.load(open(mp))["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)"
+            except Exception:
+                pass
+        t_ach = pairs_step * 32.0 / (k_ms * 1e-3) / 1e12
+        roofline = dict(common, bound="tensor", achieved=t_ach, peak=tpeak, unit="TFLOP/s", frac=t_ach / tpeak,
+                        flop_per_pair=32.0, peak_source=tsrc,
+                        note="tcgen05.mma M=128 N=64 K=16 (6 of 16 K slots carry the embedding, 2 the threshold): the MMAs are "
+                             "operand-fetch bound and the kernel is bound by the TMEM hand-over and the epilogue, see DESIGN.md 5.7",
+                        fp32_equivalent=fp32_view)
+    else:
+        roofline = dict(common, bound="fp32", **{k: fp32_view[k] for k in ("achieved", "peak", "unit", "frac", "frac_of_nominal",
+                                                                           "flop_per_pair", "peak_source")})
+
+    # ---- the same resident step with the packed-FP32 filter (the round-1 kernel), for comparison
+    fp32_arm = None
+    if tensor_path and not args.no_extras and world == 1:
+        os.environ["NDA_FILTER"] = "fold2a1"
+        try:
+            for _ in range(2):
+                step_resident()
+            ks = []
+            for _ in range(3):
+                step_resident()
+                ms = ctypes.c_double(0.0)
+                _capi.check(lib.nda_last_kernel_ms(ctypes.byref(ms), None))
+                ks.append(ms.value)
+            fk = float(np.mean(ks))
+            fp32_arm = {"filter": "fold2a1 (packed FP32, FFMA2/FADD2)", "kernel": "within_kernel", "kernel_ms": fk,
+                        "kernel_pairs_per_s": pairs_step / (fk * 1e-3),
+                        "frac_of_fp32_peak": pairs_step * FLOP_WITHIN / (fk * 1e-3) / 1e12 / peak if peak else None,
+                        "hits": int(d_out.sum().item())}
+        finally:
+            del os.environ["NDA_FILTER"]
 
     line = {
         "metric": "min-image pair evals/sec (within, config 2)", "value": value, "unit": "pairs/s",
@@ -358,7 +401,11 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": roofline,
         "check": {"hits_resident": hits_dev, "hits_e2e": hits_e2e},
+        "filter": "tensor-core (tcgen05) periodic-embedding filter + strict FP32 re-evaluation" if tensor_path
+                  else "packed-FP32 filter %d + strict FP32 re-evaluation" % filt,
     }
+    if fp32_arm is not None:
+        line["fp32_filter_arm"] = fp32_arm
 
     if rdf_sharded is not None:
         line["rdf_sharded"] = rdf_sharded
@@ -417,9 +464,12 @@ def rdf_extra(lib, _capi, torch, dev, st, peak):
     return {"workload": "config-5 shape: %d O atoms, %d frames, 149 bins, sameSel (device-generated)" % (n, nF),
             "pairs_per_launch": pairs, "kernel_ms": k_ms, "kernel_pairs_per_s": pairs / (k_ms * 1e-3),
             "step_pairs_per_s": pairs / wall,
-            "roofline": {"bound": "fp32", "kernel": "rdf_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp32", "kernel": "rdf_tc_kernel" if int(lib.nda_last_filter()) == 100 else "rdf_kernel",
+                         "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                          "frac": ach / peak if peak else None, "frac_of_nominal": ach / FP32_NOMINAL_TFLOPS,
-                         "flop_per_pair": FLOP_RDF},
+                         "flop_per_pair": FLOP_RDF,
+                         "note": "algorithmic flops of the reference arithmetic over the FP32 peak; above 1 when the "
+                                 "filter runs on the tensor cores"},
             "counts_total": int(counts.sum().item())}
 
 

@@ -52,6 +52,14 @@ uint64_t nda_launch_count(void);
 void     nda_launch_count_reset(void);
 /* 0 (default): literal getWithin.cpp:64-71 per-axis early-outs; 1: pure r2 <= d^2 */
 int  nda_set_within_pure_predicate(int on);
+/* filter the last within / RDF call ran: 100 = tensor-core filter (csrc/nda_tc.cuh), 0 = rint,
+ * 1 = fold, 2..5 = packed-FP32 fold2 variants (csrc/nda_device.cuh); -1 before the first call.
+ * NDA_FILTER=tc|rint|fold|fold2|fold2a0..3 selects; tc (default) falls back to fold2 when a frame
+ * of the call is not eligible (cut-off too close to the cell size, no unit cell, dense ranges) */
+int  nda_last_filter(void);
+/* debugging aid: with NDA_TC_TRACE=1 the last tensor-core within call recorded clock64 stamps of
+ * CTA 0's pipeline (256 blocks x 12 stamps, see csrc/nda_tc.cuh: tc_stamp); copies them out */
+int  nda_debug_tc_trace(long long *out);
 
 /* ---- drop-in host entry points (reference signatures) --------------------------- */
 

@@ -27,6 +27,8 @@ SIGNATURES = {
     "nda_launch_count": (ctypes.c_uint64, []),
     "nda_launch_count_reset": (None, []),
     "nda_set_within_pure_predicate": (c_int, [c_int]),
+    "nda_debug_tc_trace": (c_int, [ctypes.POINTER(ctypes.c_longlong)]),
+    "nda_last_filter": (c_int, []),
     "nda_get_within": (c_int, [c_f32p, c_int, c_int, c_i32p, c_int, c_i32p, c_int, c_i32p, c_f32p, c_float]),
     "nda_get_distances": (c_int, [c_f32p, c_int, c_f32p, c_int, c_f32p, c_f32p, c_int, c_int]),
     "nda_get_radial_nbr_density": (c_int, [c_f32p, c_int, c_f32p, c_int, c_f32p, c_int, c_f32p, c_int, c_int,

@@ -27,6 +27,7 @@
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_within_pure{0};
+static std::atomic<int> g_last_filter{-1};          // filter of the last pair-kernel launch: 0..5 FP32 filters, 100 tensor core
 static std::mutex g_mutex;
 static int g_host_threads = 4;          // host threads gathering pageable rows into pinned staging
 
@@ -222,9 +223,15 @@ static bool filter_tc_requested()
 
 // Host-side mirror of prep_tc_kernel with a 10 % margin: true when no frame of [fb, fe) would be
 // sent to the all-exact path by the tensor-core filter.  T = in-range limit on r2.
-static bool tc_frames_eligible(const float *cell, int fb, int fe, double T)
+// maxFraction: the tensor-core filter pays per CANDIDATE (mask + queue + strict re-evaluation on 16
+// warps per SM), the packed-FP32 filter per PAIR; measured on a B200 the cross-over is where about
+// 0.6 % of the pairs are in range (config 3, 2.3 %: fold2 0.96e12 vs tensor 0.42e12 pairs/s;
+// config 5, 0.14 %: fold2 2.7e12 vs tensor 6.0e12), estimated here from the cut-off sphere volume
+// over the cell volume.
+static bool tc_frames_eligible(const float *cell, int fb, int fe, double T, double maxFraction)
 {
     const double k = 0.15915494309189535;
+    if (const char *e = getenv("NDA_TC_MAX_FRACTION")) { const double v = atof(e); if (v > 0.0) maxFraction = v; }
     for (int f = fb; f < fe; ++f) {
         const double cx = fabs((double)cell[3 * (size_t)f]), cy = fabs((double)cell[3 * (size_t)f + 1]), cz = fabs((double)cell[3 * (size_t)f + 2]);
         if (!(cx > 0.0 && cy > 0.0 && cz > 0.0) || !(cx < 1.0e30 && cy < 1.0e30 && cz < 1.0e30)) return false;
@@ -232,6 +239,8 @@ static bool tc_frames_eligible(const float *cell, int fb, int fe, double T)
         const double Eb = P * (4.8828125e-04 * 1.01 + 3.814697265625e-06) + 1.0e-6;
         const double thr = T * 1.001 + 1.0e-6;
         if (!(2.5 * Eb * 1.1 <= thr && thr * 1.1 <= P && P < 5.0e4)) return false;
+        const double sphere = 4.1887902047863905 * T * sqrt(T);
+        if (sphere > maxFraction * cx * cy * cz) return false;
     }
     return T > 0.0;
 }
@@ -315,6 +324,7 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
     g.sameSel = sameSel ? 1 : 0;
     g.stats = stats;
     g.origInStage = 1; g.itemOrigBytes = 0;
+    g.trace = nullptr;
     a.counts = d_counts; a.nBins = nBins; a.nGroups = nGroups; a.histCopies = copies;
     a.dr = dr;
     a.fastStrict = getenv("NDA_STRICT_SLOW") ? 0 : 1;
@@ -396,6 +406,14 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
     g.sameSel = 0;
     g.stats = stats;
     g.origInStage = 0;
+    g.trace = nullptr;
+    if (const char *e = getenv("NDA_TC_TRACE")) {              // debugging aid: clock64 trace of CTA 0 (tools/tc_trace.py)
+        if (atoi(e) == 1) {
+            CK(c.sum.reserve(256 * 12 * 8));
+            CK(cudaMemsetAsync(c.sum.p, 0, 256 * 12 * 8, st));
+            g.trace = c.sum.as<long long>();
+        }
+    }
     // the frame's original refSel coordinates ride along with every A tile when two copies fit
     const size_t origBytes = (size_t)nBPad * sizeof(float4);
     g.itemOrigBytes = (tc_smem_base() + 2 * origBytes <= c.smemOptin) ? (int)origBytes : 0;
@@ -456,9 +474,11 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
         const float *hc = nullptr;
         int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
         if (rc0) return rc0;
-        if (tc_frames_eligible(hc, fb, fe, T0))
+        if (tc_frames_eligible(hc, fb, fe, T0, 0.006)) {
+            g_last_filter.store(100);
             return dev_rdf_tc(c, L, st, d_sel1, n1, d_sel2, n2, d_gid, nGroups, d_counts, nBins, d_cell, nF, fb, fe,
                               sameSel, dr, d_idx1, d_idx2, T0);
+        }
     }
     const size_t H = (size_t)nGroups * nBins;
     // shared memory: as many warp-private histogram copies as still allow PAIR_MIN_CTAS CTAs per SM
@@ -475,6 +495,7 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
     const int n1Pad = sameSel ? round_up(n1, PAIR_BTILE) : round_up(n1, PAIR_ATILE);
     const int n2Pad = sameSel ? n1Pad : round_up(n2, PAIR_BTILE);
     const int filter = filter_kind();
+    g_last_filter.store(filter);
     const bool fold = filter != kFilterRint;                 // wrapped copies needed
     const int pairLayout = is_fold2(filter) ? 1 : 0;
     const size_t bytesPerFrame = ((size_t)n1Pad + (sameSel ? 0 : (size_t)n2Pad)) * sizeof(float4) * (fold ? 2 : 1);
@@ -576,10 +597,11 @@ static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all,
         const float *hc = nullptr;
         int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
         if (rc0) return rc0;
-        if (tc_frames_eligible(hc, fb, fe, Tt)) {
+        if (tc_frames_eligible(hc, fb, fe, Tt, 0.02)) {
             rc0 = dev_within_tc(c, L, st, d_all, nF, d_refSel, refSize, d_outSel, outSize, d_bits, d_cell, d2t, Tt, fb, fe);
             if (rc0) return rc0;
             doneTc = true;
+            g_last_filter.store(100);
         }
     }
     if (doneTc) {
@@ -589,6 +611,7 @@ static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all,
         const int nAPad = round_up(outSize, PAIR_ATILE);
         const int nBPad = round_up(refSize, PAIR_BTILE);
         const int filter = filter_kind();
+        g_last_filter.store(filter);
         const bool fold = filter != kFilterRint;             // wrapped copies needed
         const int pairLayout = is_fold2(filter) ? 1 : 0;
         const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * sizeof(float4) * (fold ? 2 : 1);
@@ -938,6 +961,19 @@ int nda_set_device(int device)
 }
 
 int nda_get_device(void) { return g_dev; }
+int nda_last_filter(void) { return g_last_filter.load(); }
+
+// debugging aid (NDA_TC_TRACE=1): copies the clock64 trace of the last within call, 256 x 12 values
+int nda_debug_tc_trace(long long *out)
+{
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    if (!c->sum.p || c->sum.cap < 256 * 12 * 8) return fail(NDA_ERR_ARG, "no trace recorded");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, c->sum.p, 256 * 12 * 8, cudaMemcpyDeviceToHost));
+    return NDA_OK;
+}
 uint64_t nda_launch_count(void) { return g_launches.load(); }
 void nda_launch_count_reset(void) { g_launches.store(0); }
 int nda_set_within_pure_predicate(int on) { g_within_pure.store(on ? 1 : 0); return NDA_OK; }

@@ -24,11 +24,11 @@
 // Operand layout (pinned by tools/tc_probe.cu on a B200): blocks of 128 atoms, 4 KB each,
 // [kchunk(2)][atom(128)][8 halves]: K-major, no swizzle, descriptor LBO = 2048 B, SBO = 128 B.
 //
-// CTA = 16 epilogue warps + MMA warp + TMA warp, one CTA per SM (all 512 TMEM columns):
+// CTA = 16 epilogue warps + 2 MMA warps + TMA warp, one CTA per SM (all 512 TMEM columns):
 //   TMA warp       : bulk copies: the A tile's embedding (16 KB, double-buffered) once per item; per B
 //                    block one 6 KB stage (4 KB embedding + the block's 2 KB ORIGINAL float4 coordinates)
 //                    through a 6-deep ring
-//   MMA warp       : per stage and half h (64 B atoms) 4 MMAs (one per 128-row A block) into TMEM
+//   MMA warp h     : per stage 4 MMAs of the B atoms [64 h, 64 h + 64) (one per 128-row A block) into TMEM
 //                    columns [256 h + 64 t, +64); tcgen05.commit -> mbarriers
 //   epilogue warp w: TMEM lanes 32 (w % 4) .., A block t = w / 4: one A atom per thread, 64 B atoms per
 //                    tcgen05.ld; TMEM half h is released right after the load, so the MMAs of the next
@@ -40,9 +40,9 @@
 #include "nda_kernels.cuh"
 
 constexpr int TC_EPI_WARPS = 16;
-constexpr int TC_MMA_WARP  = TC_EPI_WARPS;                     // warp 16 issues the MMAs
-constexpr int TC_TMA_WARP  = TC_EPI_WARPS + 1;                 // warp 17 issues the TMA copies
-constexpr int TC_THREADS   = (TC_EPI_WARPS + 2) * 32;          // 576
+constexpr int TC_MMA_WARP  = TC_EPI_WARPS;                     // warps 16, 17 issue the MMAs of TMEM half 0, 1
+constexpr int TC_TMA_WARP  = TC_EPI_WARPS + 2;                 // warp 18 issues the TMA copies
+constexpr int TC_THREADS   = (TC_EPI_WARPS + 3) * 32;          // 608
 constexpr int TC_ATILE     = 512;                              // A atoms per work item (4 blocks)
 constexpr int TC_BLK       = 128;                              // atoms per embedding block
 constexpr int TC_BLK_BYTES = 4096;
@@ -250,7 +250,16 @@ struct TcGeom {
     unsigned long long *stats;
     int origInStage;                // 1: every B stage also carries the block's original float4 coordinates (rdf)
     int itemOrigBytes;              // > 0: the frame's whole original B array travels with the A tile (within)
+    long long *trace;               // optional clock64 trace of CTA 0 (tools/tc_trace.py); nullptr in production
 };
+
+// clock64 stamp k of block g (CTA 0, first 256 blocks): 0/1 MMA warp 0 passed tempty / committed, 2/3 MMA
+// warp 1, 4..7 epilogue warp 0 (tfull h0 passed, h0 loaded, tfull h1 passed, h1 loaded), 8..11 epilogue warp 15
+__device__ __forceinline__ void tc_stamp(const long long *tracePtr, unsigned g, int k)
+{
+    if (tracePtr && blockIdx.x == 0 && g < 256u && (threadIdx.x & 31) == 0)
+        const_cast<long long *>(tracePtr)[g * 12 + k] = clock64();
+}
 
 struct TcItem { int f, ia, jb0, jb1; };
 
@@ -352,16 +361,16 @@ __device__ __forceinline__ uint32_t tc_setup(const TcSmem &s, int origInStage)
 {
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        // a stage is free again when its MMAs have completed (tcgen05.commit) and, if it carries
+        // a stage is free again when its MMAs have completed (one tcgen05.commit per MMA warp) and, if it carries
         // original coordinates, when the 16 epilogue warps are done with them
-        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], origInStage ? 1 + TC_EPI_WARPS : 1); }
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], origInStage ? 2 + TC_EPI_WARPS : 2); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.tfull[i], 1);
             mbar_init(&s.tempty[i], TC_EPI_WARPS);
             mbar_init(&s.afull[i], 1);
             // an A buffer (with the frame parameters and per-item originals next to it) is free when
             // the item's MMAs have completed and the 16 epilogue warps have left the item
-            mbar_init(&s.aempty[i], 1 + TC_EPI_WARPS);
+            mbar_init(&s.aempty[i], 2 + TC_EPI_WARPS);
         }
         mbar_fence_init();
     }
@@ -437,13 +446,17 @@ __device__ __forceinline__ void tc_producer(const TcGeom &geo, const TcSmem &s)
     __syncwarp();
 }
 
-// MMA warp: the whole warp runs the loop (warp-uniform values stay in uniform registers), one
-// elected lane issues.  Per stage: 2 halves x 4 MMAs (A blocks) into TMEM columns [256 h + 64 t, +64).
-__device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem)
+// MMA warp h (h = 0, 1): owns TMEM half h.  The whole warp runs the loop (warp-uniform values stay in
+// uniform registers), one elected lane issues.  Per stage: 4 MMAs (A blocks) of the stage's B atoms
+// [64 h, 64 h + 64) into TMEM columns [256 h + 64 t, +64).  Two issuing warps because the serial
+// instruction stream of ONE warp per stage (waits, descriptor set-up, 8 MMAs, commits) was the
+// critical path of the whole CTA.
+__device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem, int h, const long long *trace)
 {
-    const uint32_t aBase = smem_u32(s.sEA), bBase = smem_u32(s.sEB);
+    const uint32_t aBase = smem_u32(s.sEA), bBase = smem_u32(s.sEB) + (uint32_t)h * 1024u;
     const uint32_t full0 = smem_u32(s.full), empty0 = smem_u32(s.empty), afull0 = smem_u32(s.afull), aempty0 = smem_u32(s.aempty);
-    const uint32_t tfull0 = smem_u32(s.tfull), tempty0 = smem_u32(s.tempty);
+    const uint32_t tfull = smem_u32(&s.tfull[h]), tempty = smem_u32(&s.tempty[h]);
+    const uint32_t d0 = tmem + (uint32_t)(h * 256);
     unsigned kt = 0, slot = 0, sphase = 0;
     for (unsigned g = 0;; ++g) {
         bar_wait(full0 + slot * 8, sphase);
@@ -452,25 +465,21 @@ __device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem)
         const unsigned ab = info & TC_INFO_AB;
         if (info & TC_INFO_FIRST) bar_wait(afull0 + ab * 8, (kt >> 1) & 1u);
         const uint64_t da0 = tc_smem_desc(aBase + ab * (TC_ATILE * 32));
-        const uint64_t db0 = tc_smem_desc(bBase + slot * TC_STAGE_BYTES);
-        #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            bar_wait(tempty0 + h * 8, (g & 1u) ^ 1u);            // epilogue has read the previous block's half
-            tc_fence_after();
-            if (tc_elect_one()) {
-                #pragma unroll
-                for (int t = 0; t < 4; ++t)                      // descriptor address field is in 16-byte units
-                    tc_mma(tmem + (uint32_t)(h * 256 + t * 64), da0 + (uint64_t)(t * (TC_BLK_BYTES >> 4)), db0 + (uint64_t)(h * (1024 >> 4)));
-                tc_commit(tfull0 + h * 8);
-            }
-            __syncwarp();
-        }
+        const uint64_t db = tc_smem_desc(bBase + slot * TC_STAGE_BYTES);
+        bar_wait(tempty, (g & 1u) ^ 1u);                         // epilogue has read the previous block's half
+        tc_fence_after();
+        tc_stamp(trace, g, 2 * h);
         if (tc_elect_one()) {
+            #pragma unroll
+            for (int t = 0; t < 4; ++t)                          // descriptor address field is in 16-byte units
+                tc_mma(d0 + (uint32_t)(t * 64), da0 + (uint64_t)(t * (TC_BLK_BYTES >> 4)), db);
+            tc_commit(tfull);
             tc_commit(empty0 + slot * 8);
             if (info & TC_INFO_LAST) tc_commit(aempty0 + ab * 8);
         }
         if (info & TC_INFO_LAST) ++kt;
         __syncwarp();
+        tc_stamp(trace, g, 2 * h + 1);
         if (++slot == TC_STAGES) { slot = 0; sphase ^= 1u; }
     }
 }
@@ -523,11 +532,14 @@ struct TcEpi {
     }
     // one TMEM half: wait, load 64 accumulators, hand the half back to the MMA warp, reduce.
     // cand = this lane's atom has at least one candidate among the 64 columns
-    __device__ __forceinline__ void load_half(int h, unsigned parity, uint32_t (&r)[32], uint32_t (&gb)[8], bool &cand) const
+    __device__ __forceinline__ void load_half(int h, unsigned parity, uint32_t (&r)[32], uint32_t (&gb)[8], bool &cand,
+                                              const long long *trace = nullptr, unsigned g = 0) const
     {
         bar_wait(tfull[h], parity);
         tc_fence_after();
+        if (trace && (t * 4 + q == 0 || t * 4 + q == 15)) tc_stamp(trace, g, (t * 4 + q == 0 ? 4 : 8) + 2 * h);
         tc_ld64p(tm[h], r);
+        if (trace && (t * 4 + q == 0 || t * 4 + q == 15)) tc_stamp(trace, g, (t * 4 + q == 0 ? 4 : 8) + 2 * h + 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(tempty[h]);                  // the next block's MMAs into this half may start
@@ -591,8 +603,8 @@ rdf_tc_kernel(const RdfTcArgs p)
 
     if (warp == TC_TMA_WARP) {
         tc_producer(geo, s);
-    } else if (warp == TC_MMA_WARP) {
-        tc_mma_warp(s, tmem);
+    } else if (warp >= TC_MMA_WARP) {
+        tc_mma_warp(s, tmem, warp - TC_MMA_WARP, geo.trace);
     } else {
         TcEpi ep;
         ep.init(s, tmem);
@@ -720,8 +732,8 @@ within_tc_kernel(const WithinTcArgs p)
 
     if (warp == TC_TMA_WARP) {
         tc_producer(geo, s);
-    } else if (warp == TC_MMA_WARP) {
-        tc_mma_warp(s, tmem);
+    } else if (warp >= TC_MMA_WARP) {
+        tc_mma_warp(s, tmem, warp - TC_MMA_WARP, geo.trace);
     } else {
         TcEpi ep;
         ep.init(s, tmem);
@@ -792,7 +804,7 @@ within_tc_kernel(const WithinTcArgs p)
                     for (int h = 0; h < 2; ++h) {
                         uint32_t r[32], gb[8];
                         bool cand;
-                        ep.load_half(h, g & 1u, r, gb, cand);
+                        ep.load_half(h, g & 1u, r, gb, cand, geo.trace, g);
                         const unsigned bal = __ballot_sync(NDA_FULL_MASK, cand) & ~foundMask;
                         if (bal) {
                             if (lane == 0) flags[nf] = make_uint2((unsigned)(jb * 2 + h), bal);
