@@ -358,7 +358,8 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
         prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
                                                              L.fp.as<FrameParams>(), stats);
         LAUNCHED();
-        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.thrDot.as<TcFrame>(), stats);
+        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.maxAbs.as<unsigned>(), -1.0,
+                                                          L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
         rc = launch_embed(st, g.A, n1Pad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embA.as<__half>(), 1);
         if (rc) return rc;
@@ -437,7 +438,11 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
         prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
                                                              L.fp.as<FrameParams>(), stats);
         LAUNCHED();
-        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.thrDot.as<TcFrame>(), stats);
+        // the "sure" shortcut needs the pure predicate to be what the reference computes: with the literal
+        // per-axis early-outs (getWithin.cpp:64-71) that holds for distance >= 1 (SURVEY B-2)
+        const double sureD2 = (!a.literal || d2 >= 1.0f) && !getenv("NDA_TC_NO_SURE") ? (double)d2 : -1.0;
+        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.maxAbs.as<unsigned>(), sureD2,
+                                                          L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
         rc = launch_embed(st, g.A, nAPad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embA.as<__half>(), 1);
         if (rc) return rc;

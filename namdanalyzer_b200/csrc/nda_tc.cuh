@@ -71,21 +71,32 @@ __host__ __device__ constexpr size_t tc_smem_base()
 // run all-exact; the host only selects the tensor-core path when no frame of the call should end
 // there.  48 bytes so that the TMA warp can ship it next to the A tile.
 // ------------------------------------------------------------------------------------------
+//
+// within only -- the SURE threshold.  The chord sum also bounds r2 from above: if S <= rs^2 / kappa with
+// kappa = max_k (asin(u_k) / u_k)^2, u_k = pi rs / c_k, then every |w_k| <= (c_k/pi) asin(u_k), hence
+// w_k^2 <= kappa S_k and r2_exact <= kappa S <= rs^2.  With rs = sqrt(d2) minus the strict-vs-exact slack
+// (2 sqrt(3) Delta, Delta = 2^-24 (4M + 5c) as in prep_frames_kernel, and 2^-20 relative for the norm)
+// the reference's own float32 r2 is <= d2 as well: such a pair IS within, no re-evaluation needed.  In
+// dot-product terms: dot_computed >= P - rs^2/(2 kappa) + E, i.e. D = dot - thrDot >= sureDelta.
+// About 9 of 10 found atoms are decided this way (nearest neighbour closer than ~0.98 d).
+// ------------------------------------------------------------------------------------------
 struct __align__(16) TcFrame {
     FrameParams fp;
     float thrDot;
-    float pad[3];
+    float sureDelta;        // D >= sureDelta  =>  the pair is within for sure; +inf when the shortcut is off
+    float pad[2];
 };
 
-__global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, TcFrame *__restrict__ tf,
-                               unsigned long long *__restrict__ stats)
+__global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, const unsigned *__restrict__ maxAbs,
+                               double sureD2, TcFrame *__restrict__ tf, unsigned long long *__restrict__ stats)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nFc) return;
     TcFrame o;
     o.fp = fp[f];
     o.thrDot = 3.0e38f;
-    o.pad[0] = o.pad[1] = o.pad[2] = 0.f;
+    o.sureDelta = __int_as_float(0x7f800000);
+    o.pad[0] = o.pad[1] = 0.f;
     if (!o.fp.exact_all) {
         const double k = 0.15915494309189535;
         const double rx = fabs((double)o.fp.cx) * k, ry = fabs((double)o.fp.cy) * k, rz = fabs((double)o.fp.cz) * k;
@@ -95,6 +106,25 @@ __global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, TcFr
         const double t = P - 0.5 * thr - 1.25 * Eb;
         if (2.5 * Eb <= thr && thr <= P && t > 0.0 && P < 6.0e4) {      // P < 6e4: thrDot and every D fit fp16
             o.thrDot = __double2float_rd(t);
+            if (sureD2 > 0.0) {
+                const double cmax = fmax(fabs((double)o.fp.cx), fmax(fabs((double)o.fp.cy), fabs((double)o.fp.cz)));
+                const double cmin = fmin(fabs((double)o.fp.cx), fmin(fabs((double)o.fp.cy), fabs((double)o.fp.cz)));
+                const double M = (double)__uint_as_float(maxAbs[f]);
+                const double Delta = 5.9604644775390625e-08 * (4.0 * M + 5.0 * cmax);
+                const double rs = sqrt(sureD2 / (1.0 + 4.0 * 9.5367431640625e-07)) - 8.0 * Delta;
+                const double u = 3.141592653589793 * rs / cmin;          // largest u_k
+                if (rs > 0.0 && u < 0.9) {
+                    const double q = asin(u) / u;
+                    const double Ssure = rs * rs / (q * q);
+                    const double tSure = P - 0.5 * Ssure + 1.25 * Eb;
+                    // D is the fp16 rounding of (dot - t_used); t_used = the two fp16 pieces embed_kernel stores
+                    const __half th = __float2half_rd(o.thrDot);
+                    const __half tl = __float2half_rd(o.thrDot - __half2float(th));
+                    const double tUsed = (double)__half2float(th) + (double)__half2float(tl);
+                    const double delta = (tSure - tUsed) * (1.0 + 1.953125e-03) + 1.0e-6;
+                    if (delta > 0.0 && delta < 6.0e4) o.sureDelta = __double2float_ru(delta);
+                }
+            }
         } else {
             o.fp.exact_all = 1;
             atomicAdd(&stats[1], 1ull);
@@ -743,7 +773,7 @@ within_tc_kernel(const WithinTcArgs p)
         // step.  The flagged halves are resolved at the end of the item (resolve()).
         constexpr int kFlagCap = TC_QCAP * 2;                  // (half index, ballot) pairs in this warp's ring space
         uint2 *flags = reinterpret_cast<uint2 *>(s.sQ + warp * TC_QCAP);
-        unsigned g = 0, kt = 0, nCand = 0;
+        unsigned g = 0, kt = 0, nCand = 0, nSure = 0;
 
         TC_FOR_ITEMS(w, geo) {
             TcItem it;
@@ -765,6 +795,7 @@ within_tc_kernel(const WithinTcArgs p)
                 const unsigned ab = kt & 1u;
                 bar_wait(ep.afull0 + ab * 8, (kt >> 1) & 1u);  // frame parameters (and originals) have landed
                 const TcFrame *tfS = &s.sItem[ab];
+                const __half sureH = __float2half_ru(tfS->sureDelta);
                 // the frame's original refSel coordinates: shared memory (came with the A tile) or L2
                 const float4 *Bsrc = geo.itemOrigBytes
                     ? reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(s.extra) + ab * geo.itemOrigBytes)
@@ -805,10 +836,22 @@ within_tc_kernel(const WithinTcArgs p)
                         uint32_t r[32], gb[8];
                         bool cand;
                         ep.load_half(h, g & 1u, r, gb, cand, geo.trace, g);
-                        const unsigned bal = __ballot_sync(NDA_FULL_MASK, cand) & ~foundMask;
+                        unsigned bal = __ballot_sync(NDA_FULL_MASK, cand) & ~foundMask;
                         if (bal) {
-                            if (lane == 0) flags[nf] = make_uint2((unsigned)(jb * 2 + h), bal);
-                            if (++nf == kFlagCap) resolve();
+                            // flagged half: is the largest D of a flagged lane above the SURE threshold?  Then the
+                            // atom is within, no strict re-evaluation (and it is switched off right away)
+                            __half2 m = __hmax2(*reinterpret_cast<const __half2 *>(&r[0]), *reinterpret_cast<const __half2 *>(&r[1]));
+                            #pragma unroll
+                            for (int i = 2; i < 32; ++i) m = __hmax2(m, *reinterpret_cast<const __half2 *>(&r[i]));
+                            const bool sure = __hge(__hmax(__low2half(m), __high2half(m)), sureH);
+                            const unsigned sb = __ballot_sync(NDA_FULL_MASK, sure) & bal;
+                            foundMask |= sb;
+                            nSure += __popc(sb);
+                            bal &= ~sb;
+                            if (bal) {
+                                if (lane == 0) flags[nf] = make_uint2((unsigned)(jb * 2 + h), bal);
+                                if (++nf == kFlagCap) resolve();
+                            }
                         }
                     }
                 }
@@ -825,6 +868,7 @@ within_tc_kernel(const WithinTcArgs p)
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nCand += __shfl_xor_sync(NDA_FULL_MASK, nCand, o);
         if (lane == 0 && nCand) atomicAdd(&geo.stats[0], (unsigned long long)nCand);
+        (void)nSure;
     }
     tc_teardown(tmem);
 }
