@@ -283,10 +283,23 @@ static int frames_per_pass(size_t bytesPerFrame, int nF)
 static int launch_embed(cudaStream_t st, const float4 *packed, int nPad, int nFc, const float *cell, int f0,
                         const TcFrame *tf, __half *E, int roleA)
 {
-    dim3 grid(nPad / TC_BLK, std::min(nFc, 65535));
+    dim3 grid(nPad / 128, std::min(nFc, 65535));
     embed_kernel<<<grid, 128, 0, st>>>(packed, nPad, nFc, cell, f0, tf, E, roleA);
     LAUNCHED();
     return NDA_OK;
+}
+
+// streamed blocks per work item: >= 16 items per CTA for the static round-robin to balance (the sameSel
+// workload is triangular), but an item stays >= minBlocks steps so that the resident chunk is amortised
+static void tc_chunking(TcGeom &g, int numSMs, long long framesInPass, int minBlocks)
+{
+    const long long target = 16LL * numSMs;
+    const long long rows = std::max<long long>(1, framesInPass * g.nRChunks);
+    const long long chunksWanted = std::max<long long>(1, (target + rows - 1) / rows);
+    long long cs = (g.nSBlocks + chunksWanted - 1) / chunksWanted;
+    cs = std::max<long long>(minBlocks, std::min<long long>(1024, cs));
+    g.chunkS = (int)std::min<long long>(cs, std::max(1, g.nSBlocks));
+    g.nSChunks = (g.nSBlocks + g.chunkS - 1) / g.chunkS;
 }
 
 static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, int n1, const float *d_sel2, int n2,
@@ -302,8 +315,9 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
     if (copies < 1)
         return fail(NDA_ERR_ARG, "nGroups*outSize = %zu histogram cells do not fit in shared memory (max %zu)", H, budget / 4);
     const size_t smem = base + (size_t)copies * H * 4;
-    const int n1Pad = round_up(n1, TC_ATILE);
-    const int n2Pad = sameSel ? n1Pad : round_up(n2, TC_BLK);
+    // sel1 is streamed in 128-atom blocks (TMEM lanes), sel2 is resident in 256-atom chunks (columns)
+    const int n1Pad = round_up(n1, sameSel ? TC_RBLK : TC_SBLK);
+    const int n2Pad = sameSel ? n1Pad : round_up(n2, TC_RBLK);
     const size_t bytesPerFrame = (size_t)n1Pad * (16 + 32) + (sameSel ? (size_t)n1Pad * 32 : (size_t)n2Pad * (16 + 32));
     const int pass = frames_per_pass(bytesPerFrame, fe - fb);
 
@@ -319,26 +333,16 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
     RdfTcArgs a;
     TcGeom &g = a.g;
     g.n1 = n1; g.n1Pad = n1Pad; g.n2 = n2; g.n2Pad = n2Pad;
-    g.nATiles = n1Pad / TC_ATILE;
-    g.nBBlocks = (n2 + TC_BLK - 1) / TC_BLK;
+    g.nRChunks = (n2 + TC_RBLK - 1) / TC_RBLK;
+    g.nSBlocks = (n1 + TC_SBLK - 1) / TC_SBLK;
     g.sameSel = sameSel ? 1 : 0;
     g.stats = stats;
-    g.origInStage = 1; g.itemOrigBytes = 0;
+    g.origInStage = 1;
     g.trace = nullptr;
     a.counts = d_counts; a.nBins = nBins; a.nGroups = nGroups; a.histCopies = copies;
     a.dr = dr;
     a.fastStrict = getenv("NDA_STRICT_SLOW") ? 0 : 1;
-    {
-        // B blocks per work item: >= 16 items per CTA for the static round-robin to balance the
-        // triangular (sameSel) workload, but an item stays >= 4 blocks (~2.6e5 pairs)
-        const long long target = 16LL * c.numSMs;
-        const long long rows = (long long)pass * g.nATiles;
-        const long long chunksWanted = std::max<long long>(1, (target + rows - 1) / rows);
-        long long cb = (g.nBBlocks + chunksWanted - 1) / chunksWanted;
-        cb = std::max<long long>(4, std::min<long long>(256, cb));
-        g.chunkBlocks = (int)std::min<long long>(cb, g.nBBlocks);
-        g.nBChunks = (g.nBBlocks + g.chunkBlocks - 1) / g.chunkBlocks;
-    }
+    tc_chunking(g, c.numSMs, pass, 8);
     const void *kfn = grouped ? (const void *)rdf_tc_kernel<true> : (const void *)rdf_tc_kernel<false>;
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
@@ -367,7 +371,7 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
         if (rc) return rc;
         g.EA = L.embA.as<__half>(); g.EB = L.embB.as<__half>();
         g.tf = L.thrDot.as<TcFrame>();
-        const unsigned long long items = (unsigned long long)nFc * g.nATiles * g.nBChunks;
+        const unsigned long long items = (unsigned long long)nFc * g.nRChunks * g.nSChunks;
         if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
         g.nItems = (unsigned)items;
         const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)c.numSMs);
@@ -385,8 +389,9 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
                          unsigned *d_bits, const float *d_cell, float d2, double T, int fb, int fe)
 {
     const int words = (outSize + 31) / 32;
-    const int nAPad = round_up(outSize, TC_ATILE);
-    const int nBPad = round_up(refSize, TC_BLK);
+    // outSel is streamed in 128-atom blocks (TMEM lanes), refSel is resident in 256-atom chunks (columns)
+    const int nAPad = round_up(outSize, TC_SBLK);
+    const int nBPad = round_up(refSize, TC_RBLK);
     const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * (16 + 32);
     const int pass = frames_per_pass(bytesPerFrame, fe - fb);
     CK(L.packA.reserve((size_t)nAPad * pass * sizeof(float4)));
@@ -401,9 +406,8 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
     WithinTcArgs a;
     TcGeom &g = a.g;
     g.n1 = outSize; g.n1Pad = nAPad; g.n2 = refSize; g.n2Pad = nBPad;
-    g.nATiles = nAPad / TC_ATILE;
-    g.nBBlocks = (refSize + TC_BLK - 1) / TC_BLK;
-    g.chunkBlocks = g.nBBlocks; g.nBChunks = 1;
+    g.nRChunks = (refSize + TC_RBLK - 1) / TC_RBLK;
+    g.nSBlocks = (outSize + TC_SBLK - 1) / TC_SBLK;
     g.sameSel = 0;
     g.stats = stats;
     g.origInStage = 0;
@@ -415,18 +419,18 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
             g.trace = c.sum.as<long long>();
         }
     }
-    // the frame's original refSel coordinates ride along with every A tile when two copies fit
-    const size_t origBytes = (size_t)nBPad * sizeof(float4);
-    g.itemOrigBytes = (tc_smem_base() + 2 * origBytes <= c.smemOptin) ? (int)origBytes : 0;
+    tc_chunking(g, c.numSMs, pass, 16);
     a.wordsPerFrame = words;
     a.d2 = d2;
     a.literal = g_within_pure.load() ? 0 : 1;
-    const size_t smem = tc_smem_base() + 2 * (size_t)g.itemOrigBytes;
+    const size_t smem = tc_smem_base();
     CK(cudaFuncSetAttribute((const void *)within_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int f0 = fb; f0 < fe; f0 += pass) {
         const int nFc = std::min(pass, fe - f0);
         CK(cudaMemsetAsync(L.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
+        a.bits = d_bits + (size_t)(f0 - fb) * words;
+        CK(cudaMemsetAsync(a.bits, 0, (size_t)nFc * words * sizeof(unsigned), st));   // found atoms are OR-ed in
         int rc = launch_pack(c, st, d_all, nF, d_outSel, outSize, nAPad, f0, nFc, nullptr,
                              L.packA.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, nullptr, 0);
         if (rc) return rc;
@@ -450,8 +454,7 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
         if (rc) return rc;
         g.EA = L.embA.as<__half>(); g.EB = L.embB.as<__half>();
         g.tf = L.thrDot.as<TcFrame>();
-        a.bits = d_bits + (size_t)(f0 - fb) * words;
-        const unsigned long long items = (unsigned long long)nFc * g.nATiles;
+        const unsigned long long items = (unsigned long long)nFc * g.nRChunks * g.nSChunks;
         if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
         g.nItems = (unsigned)items;
         const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)c.numSMs);

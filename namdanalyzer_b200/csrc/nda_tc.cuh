@@ -10,55 +10,64 @@
 // phi(a).phi(b) = P - S/2 with P = sum_k rho_k^2.  So  r^2 <= thr  =>  phi(a).phi(b) >= P - thr/2:
 // one 6-term dot product per pair decides, conservatively, which pairs can be in range, and a tile
 // of dot products is a GEMM.  The kernels below run that GEMM as tcgen05.mma (kind::f16, M = 128,
-// N = 64, K = 16, fp32 accumulators in TMEM), read the accumulators back with tcgen05.ld, reduce
-// them with a max tree (FMNMX3) and re-evaluate the few survivors with the reference's strict
-// arithmetic on the ORIGINAL coordinates (nda_device.cuh), exactly like the FP32 filters: counts and
-// mask bits stay bit-identical to the reference.  The per-pair cost drops from ~9 issue slots
-// (fold2 filter) to ~0.6.
+// N = 256, K = 16).  Two of the spare K slots carry (1, 1) x (-t_hi, -t_lo), so the MMA itself
+// subtracts the threshold: D = dot - thrDot, delivered as fp16 accumulators (correctly rounded from the
+// exact sum, pinned by tools/tc_probe16.cu) and read back two per register with tcgen05.ld.pack::16b.
+// A pair is a candidate iff the SIGN bit of D is clear; one LOP3 (AND) tests four pairs.  The few
+// survivors are re-evaluated with the reference's strict arithmetic on the ORIGINAL coordinates
+// (nda_device.cuh), exactly like the FP32 filters: counts and mask bits stay bit-identical to the
+// reference.  The per-pair cost drops from ~9 issue slots (fold2 filter) to ~0.4.
 //
 // Precision of the filter (all slack goes into the threshold, see prep_tc_kernel): phi is computed
-// in float64 and stored as fp16; K = 16 holds [hi(6) 0 0 | lo(6) 0 0] for the A role and
-// [hi(6) 0 0 | hi(6) 0 0] for the B role, so A's rounding is compensated and only B's 2^-11
+// in float64 and stored as fp16; K = 16 holds [hi(6) 1 1 | lo(6) 0 0] for the A role and
+// [hi(6) -t_hi -t_lo | hi(6) 0 0] for the B role, so A's rounding is compensated and only B's 2^-11
 // relative rounding remains: |dot_computed - dot_exact| <= E = P (2^-11 * 1.01 + 2^-18).
 //
-// Operand layout (pinned by tools/tc_probe.cu on a B200): blocks of 128 atoms, 4 KB each,
-// [kchunk(2)][atom(128)][8 halves]: K-major, no swizzle, descriptor LBO = 2048 B, SBO = 128 B.
+// Operand layout (pinned by tools/tc_probe.cu on a B200): K-major, no swizzle, blocks of R rows stored
+// [kchunk(2)][row(R)][8 halves]; descriptor LBO = 16 R bytes (k-chunk stride), SBO = 128 B.
 //
-// CTA = 16 epilogue warps + 2 MMA warps + TMA warp, one CTA per SM (all 512 TMEM columns):
-//   TMA warp       : bulk copies: the A tile's embedding (16 KB, double-buffered) once per item; per B
-//                    block one 6 KB stage (4 KB embedding + the block's 2 KB ORIGINAL float4 coordinates)
-//                    through a 6-deep ring
-//   MMA warp h     : per stage 4 MMAs of the B atoms [64 h, 64 h + 64) (one per 128-row A block) into TMEM
-//                    columns [256 h + 64 t, +64); tcgen05.commit -> mbarriers
-//   epilogue warp w: TMEM lanes 32 (w % 4) .., A block t = w / 4: one A atom per thread, 64 B atoms per
-//                    tcgen05.ld; TMEM half h is released right after the load, so the MMAs of the next
-//                    block overlap the max tree of this one.  Candidates are copied (with the B atom's
-//                    original coordinates from the stage) into a per-warp ring and re-evaluated 32 at a
-//                    time, so no warp ever stalls the TMEM hand-over on a global load.
+// Work decomposition.  One tcgen05.mma per step: M = 128 STREAMED atoms (selection A: outSel / sel1,
+// one 4 KB block per step, TMEM lanes) x N = 256 RESIDENT atoms (selection B: refSel / sel2, one 8 KB
+// chunk per work item, TMEM columns) -- the largest N, because a K = 16 MMA costs ~65 clocks of issue
+// whatever its N and 128 clocks of tensor pipe at N = 256 (tools/tc_rate.cu); N = 64 tiles were bound by
+// exactly that.  Work item = (frame, resident chunk, range of streamed blocks).
+//
+// CTA = 16 epilogue warps + MMA warp + TMA warp, one CTA per SM (2 TMEM buffers x 256 columns):
+//   TMA warp       : per item the resident chunk (8 KB embedding + 4 KB ORIGINAL float4 coordinates +
+//                    48 B frame parameters), double-buffered; per step one stage of a 6-deep ring (4 KB
+//                    embedding of the streamed block, + its 2 KB original coordinates for the RDF)
+//   MMA warp       : per step one MMA into TMEM buffer g & 1; tcgen05.commit -> mbarriers
+//   epilogue warp w: TMEM lanes 32 (w % 4) .. (its streamed atoms), columns 64 (w / 4) .. of the buffer
+//                    (its 64 resident atoms): one tcgen05.ld (.pack::16b) per step, the buffer is released
+//                    right after the load so the next MMA overlaps the reduction.
 #pragma once
 #include <cuda_fp16.h>
 #include "nda_kernels.cuh"
 
 constexpr int TC_EPI_WARPS = 16;
-constexpr int TC_MMA_WARP  = TC_EPI_WARPS;                     // warps 16, 17 issue the MMAs of TMEM half 0, 1
-constexpr int TC_TMA_WARP  = TC_EPI_WARPS + 2;                 // warp 18 issues the TMA copies
-constexpr int TC_THREADS   = (TC_EPI_WARPS + 3) * 32;          // 608
-constexpr int TC_ATILE     = 512;                              // A atoms per work item (4 blocks)
-constexpr int TC_BLK       = 128;                              // atoms per embedding block
-constexpr int TC_BLK_BYTES = 4096;
-constexpr int TC_ORIG_BYTES = TC_BLK * 16;                     // the block's ORIGINAL float4 coordinates
-constexpr int TC_STAGE_BYTES = TC_BLK_BYTES + TC_ORIG_BYTES;   // one B stage: embedding + originals (6 KB)
-constexpr int TC_STAGES    = 6;                                // B blocks in flight
+constexpr int TC_MMA_WARP  = TC_EPI_WARPS;                     // warp 16 issues the MMAs
+constexpr int TC_TMA_WARP  = TC_EPI_WARPS + 1;                 // warp 17 issues the TMA copies
+constexpr int TC_THREADS   = (TC_EPI_WARPS + 2) * 32;          // 576
+constexpr int TC_SBLK      = 128;                              // streamed atoms per step (MMA M)
+constexpr int TC_RBLK      = 256;                              // resident atoms per work item (MMA N)
+constexpr int TC_SEMB_BYTES = TC_SBLK * 32;                    // 4 KB
+constexpr int TC_SORIG_BYTES = TC_SBLK * 16;                   // 2 KB
+constexpr int TC_SPS       = 2;                                // streamed blocks (steps) per stage: halves the per-step
+                                                               // work of the two single-lane control warps
+constexpr int TC_STAGE_BYTES = TC_SPS * (TC_SEMB_BYTES + TC_SORIG_BYTES);   // [emb x SPS | originals x SPS] (12 KB)
+constexpr int TC_REMB_BYTES = TC_RBLK * 32;                    // 8 KB
+constexpr int TC_RORIG_BYTES = TC_RBLK * 16;                   // 4 KB
+constexpr int TC_RBUF_BYTES = TC_REMB_BYTES + TC_RORIG_BYTES;  // resident chunk buffer (12 KB)
+constexpr int TC_STAGES    = 4;                                // stages in flight (8 streamed blocks)
 constexpr int TC_QCAP      = 64;                               // per-warp candidate ring, 16-byte entries
-// instruction descriptor: D = F16 (bits 4-5 = 0), A = B = F16, both K-major, N = 64 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
-constexpr uint32_t TC_IDESC = (0u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D = F16 (bits 4-5 = 0), A = B = F16, both K-major, N = 256 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+constexpr uint32_t TC_IDESC = (0u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
 __host__ __device__ constexpr size_t tc_smem_base()
 {
-    return 2 * (size_t)TC_ATILE * 32            // A embedding, double-buffered
-         + (size_t)TC_STAGES * TC_STAGE_BYTES   // B ring
-         + (size_t)TC_ATILE * sizeof(float4)    // original A coordinates (strict re-evaluation)
-         + (size_t)TC_EPI_WARPS * TC_QCAP * 16  // candidate rings
+    return 2 * (size_t)TC_RBUF_BYTES            // resident chunk, double-buffered
+         + (size_t)TC_STAGES * TC_STAGE_BYTES   // streamed ring
+         + (size_t)TC_EPI_WARPS * TC_QCAP * 16  // candidate rings / flag lists
          + 512;                                 // mbarriers, TMEM base, stage info, per-item frame parameters
 }
 
@@ -134,8 +143,8 @@ __global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// embedding: packed float4 [nFc][nPad] -> fp16 blocks [nFc][nPad/128][2][128][8]
-//   A role: [hi(6), 1, 1 | lo(6), 0, 0]      B role: [hi(6), -t_hi, -t_lo | hi(6), 0, 0]
+// embedding: packed float4 [nFc][nPad] -> fp16 blocks [nFc][nPad/rows][2][rows][8]
+//   A role (rows = 128): [hi(6), 1, 1 | lo(6), 0, 0]      B role (rows = 256): [hi(6), -t_hi, -t_lo | hi(6), 0, 0]
 // with t_hi + t_lo <= thrDot of the frame, so that the MMA delivers D = dot - thrDot and the SIGN of
 // D is the filter decision.  Padding and non-finite atoms get a zero embedding but keep slots 6/7:
 // their D is -thrDot < 0, never a candidate.
@@ -145,10 +154,13 @@ __global__ void __launch_bounds__(128)
 embed_kernel(const float4 *__restrict__ packed, int nPad, int nFc, const float *__restrict__ cell, int f0,
              const TcFrame *__restrict__ tf, __half *__restrict__ E, int roleA)
 {
-    const int blk = blockIdx.x, tid = threadIdx.x;
-    const int nBlk = nPad / TC_BLK;
+    const int tid = threadIdx.x;
+    const int atom = blockIdx.x * 128 + tid;
+    const int rows = roleA ? TC_SBLK : TC_RBLK;
+    const int blk = atom / rows, r = atom % rows;
+    const int nBlk = nPad / rows;
     for (int f = blockIdx.y; f < nFc; f += gridDim.y) {
-        const float4 v = packed[(size_t)f * nPad + (size_t)blk * TC_BLK + tid];
+        const float4 v = packed[(size_t)f * nPad + atom];
         const float *cf = cell + 3 * (size_t)(f0 + f);
         const float x[3] = {v.x, v.y, v.z};
         __align__(16) __half hi[8], lo[8];
@@ -184,19 +196,19 @@ embed_kernel(const float4 *__restrict__ packed, int nPad, int nFc, const float *
             hi[6] = __hneg(th);
             hi[7] = __hneg(tl);
         }
-        __half *dst = E + ((size_t)f * nBlk + blk) * (TC_BLK_BYTES / 2);
-        *reinterpret_cast<uint4 *>(dst + tid * 8) = *reinterpret_cast<const uint4 *>(hi);
-        *reinterpret_cast<uint4 *>(dst + 1024 + tid * 8) = *reinterpret_cast<const uint4 *>(c1);
+        __half *dst = E + ((size_t)f * nBlk + blk) * (size_t)(rows * 16);
+        *reinterpret_cast<uint4 *>(dst + r * 8) = *reinterpret_cast<const uint4 *>(hi);
+        *reinterpret_cast<uint4 *>(dst + rows * 8 + r * 8) = *reinterpret_cast<const uint4 *>(c1);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // tcgen05 / mbarrier helpers (shared-memory addresses as 32-bit values, computed once)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lboBytes)
 {
-    // start address >> 4 | LBO (2048 B) >> 4 at bit 16 | SBO (128 B) >> 4 at bit 32 | version 1 at bit 46
-    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
+    // start address >> 4 | LBO >> 4 at bit 16 | SBO (128 B) >> 4 at bit 32 | version 1 at bit 46
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(lboBytes >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
            ((uint64_t)1 << 46);
 }
 
@@ -268,79 +280,72 @@ __device__ __forceinline__ void tc_ld64p(uint32_t taddr, uint32_t (&r)[32])
 // geometry shared by the two kernels: work items, shared-memory carve-up
 // ------------------------------------------------------------------------------------------
 struct TcGeom {
-    const float4 *A, *B;            // packed ORIGINAL coordinates [nFc][n1Pad], [nFc][n2Pad]
-    const __half *EA, *EB;          // embeddings (A role / B role)
+    const float4 *A, *B;            // packed ORIGINAL coordinates [nFc][n1Pad] (streamed), [nFc][n2Pad] (resident)
+    const __half *EA, *EB;          // embeddings: A role in 128-row blocks, B role in 256-row blocks
     const TcFrame *tf;              // [nFc]
-    int n1, n1Pad, n2, n2Pad;
-    int nATiles;                    // n1Pad / 512
-    int nBBlocks;                   // ceil(n2 / 128): blocks that hold real atoms
-    int chunkBlocks, nBChunks;      // B blocks per work item
+    int n1, n1Pad, n2, n2Pad;       // n1Pad % 128 == 0, n2Pad % 256 == 0
+    int nRChunks;                   // ceil(n2 / 256): resident chunks that hold real atoms
+    int nSBlocks;                   // ceil(n1 / 128): streamed blocks that hold real atoms
+    int chunkS, nSChunks;           // streamed blocks per work item
     int sameSel;
-    unsigned nItems;                // nFc * nATiles * nBChunks
+    unsigned nItems;                // nFc * nRChunks * nSChunks
     unsigned long long *stats;
-    int origInStage;                // 1: every B stage also carries the block's original float4 coordinates (rdf)
-    int itemOrigBytes;              // > 0: the frame's whole original B array travels with the A tile (within)
+    int origInStage;                // 1: every stage also carries the streamed block's original coordinates (rdf)
     long long *trace;               // optional clock64 trace of CTA 0 (tools/tc_trace.py); nullptr in production
 };
 
-// clock64 stamp k of block g (CTA 0, first 256 blocks): 0/1 MMA warp 0 passed tempty / committed, 2/3 MMA
-// warp 1, 4..7 epilogue warp 0 (tfull h0 passed, h0 loaded, tfull h1 passed, h1 loaded), 8..11 epilogue warp 15
+// clock64 stamp k of step g (CTA 0, first 256 steps): 0/1 MMA warp got its TMEM buffer back / committed,
+// 4/5 epilogue warp 0 saw the buffer / had loaded it, 8/9 epilogue warp 15
 __device__ __forceinline__ void tc_stamp(const long long *tracePtr, unsigned g, int k)
 {
     if (tracePtr && blockIdx.x == 0 && g < 256u && (threadIdx.x & 31) == 0)
         const_cast<long long *>(tracePtr)[g * 12 + k] = clock64();
 }
 
-struct TcItem { int f, ia, jb0, jb1; };
+struct TcItem { int f, c, sb0, sb1; };
 
-// (frame, A tile, B chunk) of the items blockIdx.x + k gridDim.x, advanced without divisions; the
-// all-exact flag of the NEXT item's frame is fetched one item ahead so that no role ever waits for
-// L2 between two items
+// (frame, resident chunk, streamed range) of the items blockIdx.x + k gridDim.x, advanced without
+// divisions; the all-exact flag of the NEXT item's frame is fetched one item ahead so that no role ever
+// waits for L2 between two items
 struct TcWalk {
     unsigned item;
-    int f, ia, kc, df, dia, dkc;
+    int f, c, ks, df, dc, dks;
     int exact;                      // tf[f].fp.exact_all of the current item
     __device__ __forceinline__ void init(const TcGeom &g)
     {
-        const unsigned ipf = (unsigned)g.nATiles * (unsigned)g.nBChunks;
+        const unsigned ipf = (unsigned)g.nRChunks * (unsigned)g.nSChunks;
         item = blockIdx.x;
         f = (int)(item / ipf);
         unsigned rem = item % ipf;
-        ia = (int)(rem / (unsigned)g.nBChunks);
-        kc = (int)(rem % (unsigned)g.nBChunks);
+        c = (int)(rem / (unsigned)g.nSChunks);
+        ks = (int)(rem % (unsigned)g.nSChunks);
         df = (int)(gridDim.x / ipf);
         rem = gridDim.x % ipf;
-        dia = (int)(rem / (unsigned)g.nBChunks);
-        dkc = (int)(rem % (unsigned)g.nBChunks);
+        dc = (int)(rem / (unsigned)g.nSChunks);
+        dks = (int)(rem % (unsigned)g.nSChunks);
         exact = (item < g.nItems) ? g.tf[f].fp.exact_all : 0;
     }
     __device__ __forceinline__ TcWalk peek(const TcGeom &g) const
     {
         TcWalk n = *this;
         n.item += gridDim.x;
-        n.kc += dkc;
-        if (n.kc >= g.nBChunks) { n.kc -= g.nBChunks; ++n.ia; }
-        n.ia += dia;
-        if (n.ia >= g.nATiles) { n.ia -= g.nATiles; ++n.f; }
+        n.ks += dks;
+        if (n.ks >= g.nSChunks) { n.ks -= g.nSChunks; ++n.c; }
+        n.c += dc;
+        if (n.c >= g.nRChunks) { n.c -= g.nRChunks; ++n.f; }
         n.f += df;
         return n;
     }
-    // false: the item has no work at all (chunk entirely below the diagonal)
+    // false: the item has no work at all (streamed range entirely on the wrong side of the diagonal)
     __device__ __forceinline__ bool decode(const TcGeom &g, TcItem &it) const
     {
-        it.f = f; it.ia = ia;
-        it.jb0 = kc * g.chunkBlocks;
-        it.jb1 = min(g.nBBlocks, it.jb0 + g.chunkBlocks);
-        if (g.sameSel) it.jb0 = max(it.jb0, (ia * TC_ATILE + 1) / TC_BLK);     // col > row only
-        return it.jb0 < it.jb1;
+        it.f = f; it.c = c;
+        it.sb0 = ks * g.chunkS;
+        it.sb1 = min(g.nSBlocks, it.sb0 + g.chunkS);
+        if (g.sameSel) it.sb0 = max(it.sb0, 2 * c);            // streamed index > resident index only
+        return it.sb0 < it.sb1;
     }
 };
-
-// for (w over this CTA's items): the next item's all-exact flag is requested before the body runs
-#define TC_FOR_ITEMS(w, geo)                                                                        \
-    for (TcWalk w = tc_walk_first(geo), w##_n = w; w.item < (geo).nItems; w = w##_n)                \
-        if ((w##_n = w.peek(geo)),                                                                  \
-            (w##_n.exact = (w##_n.item < (geo).nItems) ? (geo).tf[w##_n.f].fp.exact_all : 0), true)
 
 __device__ __forceinline__ TcWalk tc_walk_first(const TcGeom &g)
 {
@@ -349,37 +354,41 @@ __device__ __forceinline__ TcWalk tc_walk_first(const TcGeom &g)
     return w;
 }
 
+// for (w over this CTA's items): the next item's all-exact flag is requested before the body runs
+#define TC_FOR_ITEMS(w, geo)                                                                        \
+    for (TcWalk w = tc_walk_first(geo), w##_n = w; w.item < (geo).nItems; w = w##_n)                \
+        if ((w##_n = w.peek(geo)),                                                                  \
+            (w##_n.exact = (w##_n.item < (geo).nItems) ? (geo).tf[w##_n.f].fp.exact_all : 0), true)
+
 // per-stage word the TMA warp hands to the MMA warp (written before the arrive on full[slot])
-constexpr unsigned TC_INFO_AB = 1u, TC_INFO_FIRST = 2u, TC_INFO_LAST = 4u, TC_INFO_STOP = 8u;
+constexpr unsigned TC_INFO_AB = 1u, TC_INFO_FIRST = 2u, TC_INFO_LAST = 4u, TC_INFO_STOP = 8u, TC_INFO_CNT_SHIFT = 4;
 
 struct TcSmem {
-    unsigned char *sEA;     // [2][16 KB]
-    unsigned char *sEB;     // [TC_STAGES][4 KB embedding | 2 KB original float4]
-    float4   *sA;           // [512]
-    float4   *sQ;           // [16][TC_QCAP]: (b.x, b.y, b.z, b.w bits | owner lane << 24)
-    uint64_t *full, *empty; // [TC_STAGES] B ring
-    uint64_t *tfull, *tempty;   // [2] TMEM halves
-    uint64_t *afull, *aempty;   // [2] A tile buffers
+    unsigned char *sR;      // [2][8 KB embedding | 4 KB original float4] resident chunk
+    unsigned char *sS;      // [TC_STAGES][SPS x 4 KB embedding | SPS x 2 KB original float4] streamed blocks
+    float4   *sQ;           // [16][TC_QCAP]
+    uint64_t *full, *empty; // [TC_STAGES] streamed ring
+    uint64_t *tfull, *tempty;   // [2] TMEM buffers
+    uint64_t *rfull, *rempty;   // [2] resident buffers
     uint32_t *tmemPtr;
     unsigned *info;         // [TC_STAGES]
-    TcFrame  *sItem;        // [2]: frame parameters of the item in A buffer 0 / 1
-    unsigned *extra;        // histograms (rdf) / per-item original B coordinates, double-buffered (within)
+    TcFrame  *sItem;        // [2]: frame parameters of the item in resident buffer 0 / 1
+    unsigned *extra;        // histograms (rdf)
 };
 
 __device__ __forceinline__ TcSmem tc_carve(unsigned char *raw)
 {
     TcSmem s;
-    s.sEA = raw;
-    s.sEB = s.sEA + 2 * TC_ATILE * 32;
-    s.sA = reinterpret_cast<float4 *>(s.sEB + TC_STAGES * TC_STAGE_BYTES);
-    s.sQ = s.sA + TC_ATILE;
+    s.sR = raw;
+    s.sS = s.sR + 2 * TC_RBUF_BYTES;
+    s.sQ = reinterpret_cast<float4 *>(s.sS + TC_STAGES * TC_STAGE_BYTES);
     s.full = reinterpret_cast<uint64_t *>(s.sQ + TC_EPI_WARPS * TC_QCAP);
     s.empty = s.full + TC_STAGES;
     s.tfull = s.empty + TC_STAGES;
     s.tempty = s.tfull + 2;
-    s.afull = s.tempty + 2;
-    s.aempty = s.afull + 2;
-    s.tmemPtr = reinterpret_cast<uint32_t *>(s.aempty + 2);
+    s.rfull = s.tempty + 2;
+    s.rempty = s.rfull + 2;
+    s.tmemPtr = reinterpret_cast<uint32_t *>(s.rempty + 2);
     s.info = s.tmemPtr + 4;
     s.sItem = reinterpret_cast<TcFrame *>(reinterpret_cast<unsigned char *>(s.full) + 256);
     s.extra = reinterpret_cast<unsigned *>(raw + tc_smem_base());
@@ -391,16 +400,16 @@ __device__ __forceinline__ uint32_t tc_setup(const TcSmem &s, int origInStage)
 {
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        // a stage is free again when its MMAs have completed (one tcgen05.commit per MMA warp) and, if it carries
+        // a stage is free again when its MMA has completed (tcgen05.commit) and, if it carries
         // original coordinates, when the 16 epilogue warps are done with them
-        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], origInStage ? 2 + TC_EPI_WARPS : 2); }
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], origInStage ? 1 + TC_EPI_WARPS : 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.tfull[i], 1);
             mbar_init(&s.tempty[i], TC_EPI_WARPS);
-            mbar_init(&s.afull[i], 1);
-            // an A buffer (with the frame parameters and per-item originals next to it) is free when
-            // the item's MMAs have completed and the 16 epilogue warps have left the item
-            mbar_init(&s.aempty[i], 2 + TC_EPI_WARPS);
+            mbar_init(&s.rfull[i], 1);
+            // a resident buffer (embedding, originals, frame parameters) is free when the item's MMAs
+            // have completed and the 16 epilogue warps have left the item
+            mbar_init(&s.rempty[i], 1 + TC_EPI_WARPS);
         }
         mbar_fence_init();
     }
@@ -422,46 +431,44 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
-// TMA warp (converged, one elected lane issues): per tensor-core item the A tile's embedding (16 KB),
-// the frame parameters (48 B) and -- within -- the frame's original B coordinates, double-buffered;
-// per B block one stage of a TC_STAGES-deep ring.  info[slot] tells the MMA warp what each stage is;
-// a final STOP stage ends its loop.
+// TMA warp (converged, one elected lane issues): per tensor-core item the resident chunk (embedding,
+// original coordinates, frame parameters), double-buffered; per streamed block one stage of the ring.
+// info[slot] tells the MMA warp what each stage is; a final STOP stage ends its loop.
 __device__ __forceinline__ void tc_producer(const TcGeom &geo, const TcSmem &s)
 {
-    const size_t aBlkPerFrame = (size_t)geo.n1Pad / TC_BLK, bBlkPerFrame = (size_t)geo.n2Pad / TC_BLK;
+    const size_t sBlkPerFrame = (size_t)geo.n1Pad / TC_SBLK, rBlkPerFrame = (size_t)geo.n2Pad / TC_RBLK;
     const unsigned char *EA = reinterpret_cast<const unsigned char *>(geo.EA);
     const unsigned char *EB = reinterpret_cast<const unsigned char *>(geo.EB);
+    const unsigned char *OA = reinterpret_cast<const unsigned char *>(geo.A);
     const unsigned char *OB = reinterpret_cast<const unsigned char *>(geo.B);
-    const uint32_t sEA = smem_u32(s.sEA), sEB = smem_u32(s.sEB), sItem = smem_u32(s.sItem), sExtra = smem_u32(s.extra);
-    const uint32_t full0 = smem_u32(s.full), empty0 = smem_u32(s.empty), afull0 = smem_u32(s.afull), aempty0 = smem_u32(s.aempty);
-    const uint32_t stageTx = geo.origInStage ? TC_STAGE_BYTES : TC_BLK_BYTES;
-    unsigned g = 0, kt = 0, slot = 0, sphase = 0;
+    const uint32_t sR = smem_u32(s.sR), sS = smem_u32(s.sS), sItem = smem_u32(s.sItem);
+    const uint32_t full0 = smem_u32(s.full), empty0 = smem_u32(s.empty), rfull0 = smem_u32(s.rfull), rempty0 = smem_u32(s.rempty);
+    unsigned kt = 0, slot = 0, sphase = 0;
     TC_FOR_ITEMS(w, geo) {
         TcItem it;
         if (!w.decode(geo, it) || w.exact) continue;
         const unsigned ab = kt & 1u;
-        bar_wait(aempty0 + ab * 8, ((kt >> 1) & 1u) ^ 1u);       // item kt - 2 has left this buffer
+        bar_wait(rempty0 + ab * 8, ((kt >> 1) & 1u) ^ 1u);       // item kt - 2 has left this buffer
         if (tc_elect_one()) {
-            bar_expect_tx(afull0 + ab * 8, TC_ATILE * 32 + (uint32_t)sizeof(TcFrame) + geo.itemOrigBytes);
-            tma_g2s(sEA + ab * (TC_ATILE * 32),
-                    EA + ((size_t)it.f * aBlkPerFrame + (size_t)it.ia * (TC_ATILE / TC_BLK)) * TC_BLK_BYTES,
-                    TC_ATILE * 32, afull0 + ab * 8);
-            tma_g2s(sItem + ab * (uint32_t)sizeof(TcFrame), geo.tf + it.f, (uint32_t)sizeof(TcFrame), afull0 + ab * 8);
-            if (geo.itemOrigBytes)
-                tma_g2s(sExtra + ab * geo.itemOrigBytes, OB + (size_t)it.f * bBlkPerFrame * TC_ORIG_BYTES,
-                        geo.itemOrigBytes, afull0 + ab * 8);
+            bar_expect_tx(rfull0 + ab * 8, TC_RBUF_BYTES + (uint32_t)sizeof(TcFrame));
+            const size_t rblk = (size_t)it.f * rBlkPerFrame + (size_t)it.c;
+            tma_g2s(sR + ab * TC_RBUF_BYTES, EB + rblk * TC_REMB_BYTES, TC_REMB_BYTES, rfull0 + ab * 8);
+            tma_g2s(sR + ab * TC_RBUF_BYTES + TC_REMB_BYTES, OB + rblk * TC_RORIG_BYTES, TC_RORIG_BYTES, rfull0 + ab * 8);
+            tma_g2s(sItem + ab * (uint32_t)sizeof(TcFrame), geo.tf + it.f, (uint32_t)sizeof(TcFrame), rfull0 + ab * 8);
         }
         __syncwarp();
-        const unsigned char *src = EB + ((size_t)it.f * bBlkPerFrame + (size_t)it.jb0) * TC_BLK_BYTES;
-        const unsigned char *osrc = OB + ((size_t)it.f * bBlkPerFrame + (size_t)it.jb0) * TC_ORIG_BYTES;
-        for (int jb = it.jb0; jb < it.jb1; ++jb, ++g, src += TC_BLK_BYTES, osrc += TC_ORIG_BYTES) {
+        const unsigned char *src = EA + ((size_t)it.f * sBlkPerFrame + (size_t)it.sb0) * TC_SEMB_BYTES;
+        const unsigned char *osrc = OA + ((size_t)it.f * sBlkPerFrame + (size_t)it.sb0) * TC_SORIG_BYTES;
+        for (int sb = it.sb0; sb < it.sb1; sb += TC_SPS, src += TC_SPS * TC_SEMB_BYTES, osrc += TC_SPS * TC_SORIG_BYTES) {
+            const unsigned cnt = (unsigned)min(TC_SPS, it.sb1 - sb);      // consecutive blocks are contiguous in memory
             bar_wait(empty0 + slot * 8, sphase ^ 1u);
             if (tc_elect_one()) {
-                s.info[slot] = ab | (jb == it.jb0 ? TC_INFO_FIRST : 0u) | (jb + 1 == it.jb1 ? TC_INFO_LAST : 0u);
-                bar_expect_tx(full0 + slot * 8, stageTx);
-                tma_g2s(sEB + slot * TC_STAGE_BYTES, src, TC_BLK_BYTES, full0 + slot * 8);
+                s.info[slot] = ab | (sb == it.sb0 ? TC_INFO_FIRST : 0u) | (sb + TC_SPS >= it.sb1 ? TC_INFO_LAST : 0u) |
+                               (cnt << TC_INFO_CNT_SHIFT);
+                bar_expect_tx(full0 + slot * 8, cnt * (geo.origInStage ? TC_SEMB_BYTES + TC_SORIG_BYTES : TC_SEMB_BYTES));
+                tma_g2s(sS + slot * TC_STAGE_BYTES, src, cnt * TC_SEMB_BYTES, full0 + slot * 8);
                 if (geo.origInStage)
-                    tma_g2s(sEB + slot * TC_STAGE_BYTES + TC_BLK_BYTES, osrc, TC_ORIG_BYTES, full0 + slot * 8);
+                    tma_g2s(sS + slot * TC_STAGE_BYTES + TC_SPS * TC_SEMB_BYTES, osrc, cnt * TC_SORIG_BYTES, full0 + slot * 8);
             }
             __syncwarp();
             if (++slot == TC_STAGES) { slot = 0; sphase ^= 1u; }
@@ -476,40 +483,39 @@ __device__ __forceinline__ void tc_producer(const TcGeom &geo, const TcSmem &s)
     __syncwarp();
 }
 
-// MMA warp h (h = 0, 1): owns TMEM half h.  The whole warp runs the loop (warp-uniform values stay in
-// uniform registers), one elected lane issues.  Per stage: 4 MMAs (A blocks) of the stage's B atoms
-// [64 h, 64 h + 64) into TMEM columns [256 h + 64 t, +64).  Two issuing warps because the serial
-// instruction stream of ONE warp per stage (waits, descriptor set-up, 8 MMAs, commits) was the
-// critical path of the whole CTA.
-__device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem, int h, const long long *trace)
+// MMA warp: the whole warp runs the loop (warp-uniform values stay in uniform registers), one elected
+// lane issues.  Per streamed block ONE MMA: D[128 streamed x 256 resident] into TMEM buffer g & 1.
+__device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem, const long long *trace)
 {
-    const uint32_t aBase = smem_u32(s.sEA), bBase = smem_u32(s.sEB) + (uint32_t)h * 1024u;
-    const uint32_t full0 = smem_u32(s.full), empty0 = smem_u32(s.empty), afull0 = smem_u32(s.afull), aempty0 = smem_u32(s.aempty);
-    const uint32_t tfull = smem_u32(&s.tfull[h]), tempty = smem_u32(&s.tempty[h]);
-    const uint32_t d0 = tmem + (uint32_t)(h * 256);
-    unsigned kt = 0, slot = 0, sphase = 0;
-    for (unsigned g = 0;; ++g) {
+    const uint32_t rBase = smem_u32(s.sR), sBase = smem_u32(s.sS);
+    const uint32_t full0 = smem_u32(s.full), empty0 = smem_u32(s.empty), rfull0 = smem_u32(s.rfull), rempty0 = smem_u32(s.rempty);
+    const uint32_t tfull0 = smem_u32(s.tfull), tempty0 = smem_u32(s.tempty);
+    unsigned kt = 0, slot = 0, sphase = 0, g = 0;
+    for (;;) {
         bar_wait(full0 + slot * 8, sphase);
         const unsigned info = s.info[slot];
         if (info & TC_INFO_STOP) break;
-        const unsigned ab = info & TC_INFO_AB;
-        if (info & TC_INFO_FIRST) bar_wait(afull0 + ab * 8, (kt >> 1) & 1u);
-        const uint64_t da0 = tc_smem_desc(aBase + ab * (TC_ATILE * 32));
-        const uint64_t db = tc_smem_desc(bBase + slot * TC_STAGE_BYTES);
-        bar_wait(tempty, (g & 1u) ^ 1u);                         // epilogue has read the previous block's half
-        tc_fence_after();
-        tc_stamp(trace, g, 2 * h);
-        if (tc_elect_one()) {
-            #pragma unroll
-            for (int t = 0; t < 4; ++t)                          // descriptor address field is in 16-byte units
-                tc_mma(d0 + (uint32_t)(t * 64), da0 + (uint64_t)(t * (TC_BLK_BYTES >> 4)), db);
-            tc_commit(tfull);
-            tc_commit(empty0 + slot * 8);
-            if (info & TC_INFO_LAST) tc_commit(aempty0 + ab * 8);
+        const unsigned ab = info & TC_INFO_AB, cnt = info >> TC_INFO_CNT_SHIFT;
+        if (info & TC_INFO_FIRST) bar_wait(rfull0 + ab * 8, (kt >> 1) & 1u);
+        const uint64_t db = tc_smem_desc(rBase + ab * TC_RBUF_BYTES, TC_RBLK * 16);
+        for (unsigned u = 0; u < cnt; ++u, ++g) {
+            const unsigned h = g & 1u;
+            const uint64_t da = tc_smem_desc(sBase + slot * TC_STAGE_BYTES + u * TC_SEMB_BYTES, TC_SBLK * 16);
+            bar_wait(tempty0 + h * 8, ((g >> 1) & 1u) ^ 1u);     // epilogue has read this buffer's previous step
+            tc_fence_after();
+            tc_stamp(trace, g, 0);
+            if (tc_elect_one()) {
+                tc_mma(tmem + h * 256u, da, db);
+                tc_commit(tfull0 + h * 8);
+                if (u + 1 == cnt) {
+                    tc_commit(empty0 + slot * 8);
+                    if (info & TC_INFO_LAST) tc_commit(rempty0 + ab * 8);
+                }
+            }
+            __syncwarp();
+            tc_stamp(trace, g, 1);
         }
         if (info & TC_INFO_LAST) ++kt;
-        __syncwarp();
-        tc_stamp(trace, g, 2 * h + 1);
         if (++slot == TC_STAGES) { slot = 0; sphase ^= 1u; }
     }
 }
@@ -541,38 +547,36 @@ __device__ __forceinline__ void tc_mask64(const uint32_t (&r)[32], const uint32_
     }
 }
 
-// per-warp constants of the epilogue loop
+// per-warp constants of the epilogue loop: warp w owns TMEM lanes 32 (w % 4) .. (streamed atoms
+// 32 q .. of every block) and columns 64 (w / 4) .. (resident atoms 64 cq .. of the chunk)
 struct TcEpi {
-    uint32_t tfull[2], tempty[2], tm[2];     // barrier addresses and TMEM addresses of the two halves
-    uint32_t empty0, afull0, aempty0;
-    int q, t, lane, rowWarp;
+    uint32_t tfull0, tempty0, tm0;           // barrier addresses and TMEM address of buffer 0
+    uint32_t empty0, rfull0, rempty0;
+    int q, cq, lane;
     __device__ __forceinline__ void init(const TcSmem &s, uint32_t tmem)
     {
         const int warp = threadIdx.x >> 5;
         lane = threadIdx.x & 31;
-        q = warp & 3; t = warp >> 2;
-        rowWarp = t * TC_BLK + q * 32;
-        #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            tfull[h] = smem_u32(&s.tfull[h]);
-            tempty[h] = smem_u32(&s.tempty[h]);
-            tm[h] = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + t * 64);
-        }
-        empty0 = smem_u32(s.empty); afull0 = smem_u32(s.afull); aempty0 = smem_u32(s.aempty);
+        q = warp & 3; cq = warp >> 2;
+        tfull0 = smem_u32(s.tfull);
+        tempty0 = smem_u32(s.tempty);
+        tm0 = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64);
+        empty0 = smem_u32(s.empty); rfull0 = smem_u32(s.rfull); rempty0 = smem_u32(s.rempty);
     }
-    // one TMEM half: wait, load 64 accumulators, hand the half back to the MMA warp, reduce.
-    // cand = this lane's atom has at least one candidate among the 64 columns
-    __device__ __forceinline__ void load_half(int h, unsigned parity, uint32_t (&r)[32], uint32_t (&gb)[8], bool &cand,
-                                              const long long *trace = nullptr, unsigned g = 0) const
+    // step g: wait for TMEM buffer g & 1, load 64 accumulators, hand the buffer back to the MMA warp, reduce.
+    // cand = this lane's streamed atom has at least one candidate among the warp's 64 resident atoms
+    __device__ __forceinline__ void load_step(unsigned g, uint32_t (&r)[32], uint32_t (&gb)[8], bool &cand,
+                                              const long long *trace = nullptr) const
     {
-        bar_wait(tfull[h], parity);
+        const unsigned h = g & 1u;
+        bar_wait(tfull0 + h * 8, (g >> 1) & 1u);
         tc_fence_after();
-        if (trace && (t * 4 + q == 0 || t * 4 + q == 15)) tc_stamp(trace, g, (t * 4 + q == 0 ? 4 : 8) + 2 * h);
-        tc_ld64p(tm[h], r);
-        if (trace && (t * 4 + q == 0 || t * 4 + q == 15)) tc_stamp(trace, g, (t * 4 + q == 0 ? 4 : 8) + 2 * h + 1);
+        if (trace && (cq * 4 + q == 0 || cq * 4 + q == 15)) tc_stamp(trace, g, cq * 4 + q == 0 ? 4 : 8);
+        tc_ld64p(tm0 + h * 256u, r);
+        if (trace && (cq * 4 + q == 0 || cq * 4 + q == 15)) tc_stamp(trace, g, cq * 4 + q == 0 ? 5 : 9);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) bar_arrive(tempty[h]);                  // the next block's MMAs into this half may start
+        if (lane == 0) bar_arrive(tempty0 + h * 8);            // the MMA of step g + 2 may start
         #pragma unroll
         for (int b = 0; b < 8; ++b) gb[b] = r[4 * b] & r[4 * b + 1] & r[4 * b + 2] & r[4 * b + 3];
         const uint32_t top = (gb[0] & gb[1] & gb[2]) & (gb[3] & gb[4] & gb[5]) & (gb[6] & gb[7]);
@@ -580,37 +584,11 @@ struct TcEpi {
     }
 };
 
-// Candidates of one TMEM half -> the warp's ring.  Every lane pushes its own candidates (bit k of
-// (mlo, mhi) = column k of the half), one per round, together with the ORIGINAL coordinates of the B
-// atom taken from the stage (entry.w = b.w bits | owner lane << 24), so the strict re-evaluation is
-// independent of the stage and can be batched into full warps.  `drain(32)` is called whenever 32
-// entries are queued.
-template <class Drain>
-__device__ __forceinline__ void tc_push(unsigned mlo, unsigned mhi, const float4 *origHalf, float4 *myQ,
-                                        int &qhead, int &qcount, int lane, unsigned ltmask, Drain &&drain)
-{
-    for (;;) {
-        const bool has = (mlo | mhi) != 0u;
-        const unsigned bal = __ballot_sync(NDA_FULL_MASK, has);
-        if (!bal) break;
-        if (has) {
-            int k;
-            if (mlo) { k = __ffs(mlo) - 1; mlo &= mlo - 1; }
-            else     { k = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
-            float4 b = origHalf[k];
-            b.w = __int_as_float((__float_as_int(b.w) & 0xffffff) | (lane << 24));
-            myQ[(qhead + qcount + __popc(bal & ltmask)) % TC_QCAP] = b;
-        }
-        qcount += __popc(bal);
-        if (qcount >= 32) drain(32);
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // RDF on the tensor-core filter
 // ------------------------------------------------------------------------------------------
 struct RdfTcArgs {
-    TcGeom g;
+    TcGeom g;                   // A = sel1 (streamed), B = sel2 (resident; its w component = group id)
     unsigned long long *counts;
     int nBins, nGroups, histCopies;
     float dr;
@@ -633,12 +611,11 @@ rdf_tc_kernel(const RdfTcArgs p)
 
     if (warp == TC_TMA_WARP) {
         tc_producer(geo, s);
-    } else if (warp >= TC_MMA_WARP) {
-        tc_mma_warp(s, tmem, warp - TC_MMA_WARP, geo.trace);
+    } else if (warp == TC_MMA_WARP) {
+        tc_mma_warp(s, tmem, geo.trace);
     } else {
         TcEpi ep;
         ep.init(s, tmem);
-        const int rowWarp = ep.rowWarp, rowInTile = rowWarp + lane;
         unsigned *myHist = hist + (warp % p.histCopies) * H;
         float4 *myQ = s.sQ + warp * TC_QCAP;
         const unsigned ltmask = lanemask_lt();
@@ -655,22 +632,25 @@ rdf_tc_kernel(const RdfTcArgs p)
                 }
                 sinceFlush = 1;
             }
-            const float4 ao = geo.A[(size_t)it.f * geo.n1Pad + (size_t)it.ia * TC_ATILE + rowInTile];
-            s.sA[rowInTile] = ao;                              // read back by this warp only (drain)
-            __syncwarp();
-            const int rowGlobal = it.ia * TC_ATILE + rowInTile;
+            const int colBase = it.c * TC_RBLK + ep.cq * 64;   // this warp's first resident atom
 
             if (w.exact) {
-                // all-exact frame: the reference arithmetic on every pair
+                // all-exact frame: the reference arithmetic on every pair of this warp's sub-tile
                 const FrameParams fpar = geo.tf[it.f].fp;
+                const float4 *Aorig = geo.A + (size_t)it.f * geo.n1Pad;
                 const float4 *Borig = geo.B + (size_t)it.f * geo.n2Pad;
-                const int j0 = it.jb0 * TC_BLK, j1 = min(geo.n2, it.jb1 * TC_BLK);
-                for (int j = j0; j < j1; ++j) {
-                    const float4 b = __ldg(&Borig[j]);
-                    if (!geo.sameSel || (j > rowGlobal)) {
-                        const float r2 = strict_r2(ao.x, ao.y, ao.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
-                        const int idx = strict_bin(r2, p.dr, p.nBins);
-                        if (idx >= 0) atomicAdd(&myHist[(kGrouped ? __float_as_int(b.w) : 0) * p.nBins + idx], 1u);
+                for (int sb = it.sb0; sb < it.sb1; ++sb) {
+                    const int row = sb * TC_SBLK + ep.q * 32 + lane;
+                    const float4 a = __ldg(&Aorig[row]);
+                    for (int k = 0; k < 64; ++k) {
+                        const int col = colBase + k;
+                        if (col >= geo.n2) break;
+                        const float4 b = __ldg(&Borig[col]);
+                        if (!geo.sameSel || (row > col)) {
+                            const float r2 = strict_r2(a.x, a.y, a.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
+                            const int idx = strict_bin(r2, p.dr, p.nBins);
+                            if (idx >= 0) atomicAdd(&myHist[(kGrouped ? __float_as_int(b.w) : 0) * p.nBins + idx], 1u);
+                        }
                     }
                 }
                 __syncwarp();
@@ -678,21 +658,22 @@ rdf_tc_kernel(const RdfTcArgs p)
             }
 
             const unsigned ab = kt & 1u;
-            bar_wait(ep.afull0 + ab * 8, (kt >> 1) & 1u);      // frame parameters have landed next to the A tile
+            bar_wait(ep.rfull0 + ab * 8, (kt >> 1) & 1u);      // resident originals and frame parameters have landed
             const TcFrame *tfS = &s.sItem[ab];
+            const float4 *rOrig = reinterpret_cast<const float4 *>(s.sR + ab * TC_RBUF_BYTES + TC_REMB_BYTES) + ep.cq * 64;
             int qhead = 0, qcount = 0;
-            // strict re-evaluation of n queued candidates, one per lane
+            // strict re-evaluation of n queued candidates, one per lane: entry = streamed atom's original
+            // coordinates, w = column (0..63) of the resident atom in this warp's sub-chunk
             auto drain = [&](int n) {
                 __syncwarp();
                 if (lane < n) {
-                    const float4 b = myQ[(qhead + lane) % TC_QCAP];
-                    const int wb = __float_as_int(b.w);
-                    const float4 a = s.sA[rowWarp + ((wb >> 24) & 31)];
+                    const float4 a = myQ[(qhead + lane) % TC_QCAP];
+                    const float4 b = rOrig[__float_as_int(a.w)];
                     const FrameParams fpar = tfS->fp;
                     const float r2 = p.fastStrict ? strict_r2_fastpath(a.x, a.y, a.z, b.x, b.y, b.z, fpar)
                                                   : strict_r2(a.x, a.y, a.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
                     const int idx = strict_bin(r2, p.dr, p.nBins);
-                    if (idx >= 0) atomicAdd(&myHist[(kGrouped ? (wb & 0xffffff) : 0) * p.nBins + idx], 1u);
+                    if (idx >= 0) atomicAdd(&myHist[(kGrouped ? __float_as_int(b.w) : 0) * p.nBins + idx], 1u);
                     ++nCand;
                 }
                 qhead = (qhead + n) % TC_QCAP;
@@ -700,32 +681,46 @@ rdf_tc_kernel(const RdfTcArgs p)
                 __syncwarp();
             };
 
-            for (int jb = it.jb0; jb < it.jb1; ++jb, ++g) {
-                const float4 *orig = reinterpret_cast<const float4 *>(s.sEB + slot * TC_STAGE_BYTES + TC_BLK_BYTES);
-                #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t r[32], gb[8];
-                    bool cand;
-                    ep.load_half(h, g & 1u, r, gb, cand);
-                    if (__any_sync(NDA_FULL_MASK, cand)) {
-                        unsigned mlo, mhi;
-                        tc_mask64(r, gb, mlo, mhi);
-                        if (geo.sameSel) {                      // col > row only (getRadialNbrDensity.cpp:27)
-                            const int d = rowGlobal - (jb * TC_BLK + h * 64);     // columns k <= d are dropped
-                            const unsigned long long keep = d < 0 ? ~0ull : (d >= 63 ? 0ull : ~((2ull << d) - 1ull));
-                            mlo &= (unsigned)keep;
-                            mhi &= (unsigned)(keep >> 32);
+            for (int sb = it.sb0; sb < it.sb1; ++sb, ++g) {
+                const int u = (sb - it.sb0) % TC_SPS;              // block u of its stage
+                uint32_t r[32], gb[8];
+                bool cand;
+                ep.load_step(g, r, gb, cand, geo.trace);
+                if (__any_sync(NDA_FULL_MASK, cand)) {
+                    unsigned mlo, mhi;
+                    tc_mask64(r, gb, mlo, mhi);
+                    if (geo.sameSel) {                          // count a pair once: streamed index > resident index
+                        const int d = (sb * TC_SBLK + ep.q * 32 + lane) - colBase;      // keep columns k < d
+                        const unsigned long long keep = d <= 0 ? 0ull : (d >= 64 ? ~0ull : ((1ull << d) - 1ull));
+                        mlo &= (unsigned)keep;
+                        mhi &= (unsigned)(keep >> 32);
+                    }
+                    // every lane pushes its own candidates, one per round, with its atom's ORIGINAL coordinates
+                    float4 e = reinterpret_cast<const float4 *>(s.sS + slot * TC_STAGE_BYTES + TC_SPS * TC_SEMB_BYTES)[u * TC_SBLK + ep.q * 32 + lane];
+                    for (;;) {
+                        const bool has = (mlo | mhi) != 0u;
+                        const unsigned bal = __ballot_sync(NDA_FULL_MASK, has);
+                        if (!bal) break;
+                        if (has) {
+                            int k;
+                            if (mlo) { k = __ffs(mlo) - 1; mlo &= mlo - 1; }
+                            else     { k = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
+                            e.w = __int_as_float(k);
+                            myQ[(qhead + qcount + __popc(bal & ltmask)) % TC_QCAP] = e;
                         }
-                        tc_push(mlo, mhi, orig + h * 64, myQ, qhead, qcount, lane, ltmask, drain);
+                        qcount += __popc(bal);
+                        if (qcount >= 32) drain(32);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) bar_arrive(ep.empty0 + slot * 8);   // done with this stage's original coordinates
-                if (++slot == TC_STAGES) slot = 0;
+                if (u == TC_SPS - 1 || sb + 1 == it.sb1) {         // last block of its stage
+                    __syncwarp();
+                    if (lane == 0) bar_arrive(ep.empty0 + slot * 8);   // done with this stage's original coordinates
+                    if (++slot == TC_STAGES) slot = 0;
+                }
             }
             if (qcount > 0) drain(qcount);
             __syncwarp();
-            if (lane == 0) bar_arrive(ep.aempty0 + ab * 8);    // done with this item's frame parameters
+            if (lane == 0) bar_arrive(ep.rempty0 + ab * 8);    // done with this item's resident data
             ++kt;
         }
         #pragma unroll
@@ -744,8 +739,8 @@ rdf_tc_kernel(const RdfTcArgs p)
 // within on the tensor-core filter
 // ------------------------------------------------------------------------------------------
 struct WithinTcArgs {
-    TcGeom g;                   // A = outSel atoms, B = refSel atoms; nBChunks = 1, sameSel = 0
-    unsigned *bits;             // [nFc][wordsPerFrame]
+    TcGeom g;                   // A = outSel atoms (streamed), B = refSel atoms (resident); sameSel = 0
+    unsigned *bits;             // [nFc][wordsPerFrame], zeroed by the host: found atoms are OR-ed in
     int wordsPerFrame;
     float d2;
     int literal;
@@ -762,113 +757,107 @@ within_tc_kernel(const WithinTcArgs p)
 
     if (warp == TC_TMA_WARP) {
         tc_producer(geo, s);
-    } else if (warp >= TC_MMA_WARP) {
-        tc_mma_warp(s, tmem, warp - TC_MMA_WARP, geo.trace);
+    } else if (warp == TC_MMA_WARP) {
+        tc_mma_warp(s, tmem, geo.trace);
     } else {
         TcEpi ep;
         ep.init(s, tmem);
-        const int rowWarp = ep.rowWarp, rowInTile = rowWarp + lane;
-        // The main loop only RECORDS which (half, lane) saw a dot product above the threshold: one
-        // ballot per half, no data-dependent work, so the 16 warps that share a TMEM half stay in
-        // step.  The flagged halves are resolved at the end of the item (resolve()).
-        constexpr int kFlagCap = TC_QCAP * 2;                  // (half index, ballot) pairs in this warp's ring space
+        // The 32 streamed atoms of a warp and step are exactly one word of the result bitmask.  The main
+        // loop decides what it can from D alone -- no candidate: nothing; D above the SURE threshold:
+        // the atom is within, OR its bit in -- and only RECORDS the rest (step, lanes): no data-dependent
+        // work, so the 16 warps that share a TMEM buffer stay in step.  The recorded steps are resolved
+        // with the reference arithmetic at the end of the item (resolve()).
+        constexpr int kFlagCap = TC_QCAP * 2;                  // (step, ballot) pairs in this warp's ring space
         uint2 *flags = reinterpret_cast<uint2 *>(s.sQ + warp * TC_QCAP);
-        unsigned g = 0, kt = 0, nCand = 0, nSure = 0;
+        unsigned g = 0, kt = 0, nCand = 0;
 
         TC_FOR_ITEMS(w, geo) {
             TcItem it;
             if (!w.decode(geo, it)) continue;
-            const float4 *Bglob = geo.B + (size_t)it.f * geo.n2Pad;
-            const float4 *Aglob = geo.A + (size_t)it.f * geo.n1Pad + (size_t)it.ia * TC_ATILE;
-            unsigned foundMask = 0u;                           // warp-uniform: bit l = lane l's atom is within
+            const float4 *Aglob = geo.A + (size_t)it.f * geo.n1Pad;
+            unsigned *bitsF = p.bits + (size_t)it.f * p.wordsPerFrame;
+            const int colBase = it.c * TC_RBLK + ep.cq * 64;   // this warp's first resident (refSel) atom
 
             if (w.exact) {
                 const FrameParams fpar = geo.tf[it.f].fp;
-                const float4 ao = Aglob[rowInTile];
-                bool found = false;
-                for (int j = 0; j < geo.n2 && !__all_sync(NDA_FULL_MASK, found); ++j) {
-                    const float4 b = __ldg(&Bglob[j]);
-                    if (!found && strict_within(ao, b, fpar, p.d2, p.literal)) found = true;
-                }
-                foundMask = __ballot_sync(NDA_FULL_MASK, found);
-            } else {
-                const unsigned ab = kt & 1u;
-                bar_wait(ep.afull0 + ab * 8, (kt >> 1) & 1u);  // frame parameters (and originals) have landed
-                const TcFrame *tfS = &s.sItem[ab];
-                const __half sureH = __float2half_ru(tfS->sureDelta);
-                // the frame's original refSel coordinates: shared memory (came with the A tile) or L2
-                const float4 *Bsrc = geo.itemOrigBytes
-                    ? reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(s.extra) + ab * geo.itemOrigBytes)
-                    : Bglob;
-                int nf = 0;
-                // Flagged (half, lane): the 64 columns of the half are re-evaluated with the reference
-                // arithmetic, two per lane, for the flagged lane's atom; atoms already found are skipped,
-                // so the count of strict evaluations stays ~ one half per found atom.
-                auto resolve = [&]() {
-                    __syncwarp();
-                    const FrameParams fpar = tfS->fp;
-                    const float4 ao = Aglob[rowInTile];
-                    for (int i = 0; i < nf; ++i) {
-                        const uint2 fl = flags[i];
-                        unsigned owners = fl.y & ~foundMask;
-                        if (!owners) continue;
-                        const float4 b0 = Bsrc[fl.x * 64 + lane];
-                        const float4 b1 = Bsrc[fl.x * 64 + 32 + lane];
-                        while (owners) {
-                            const int o = __ffs(owners) - 1;
-                            owners &= owners - 1;
-                            float4 a;
-                            a.x = __shfl_sync(NDA_FULL_MASK, ao.x, o);
-                            a.y = __shfl_sync(NDA_FULL_MASK, ao.y, o);
-                            a.z = __shfl_sync(NDA_FULL_MASK, ao.z, o);
-                            a.w = 0.f;
-                            const bool hit = strict_within(a, b0, fpar, p.d2, p.literal) || strict_within(a, b1, fpar, p.d2, p.literal);
-                            if (__any_sync(NDA_FULL_MASK, hit)) foundMask |= 1u << o;
-                            nCand += 2;
-                        }
+                const float4 *Bglob = geo.B + (size_t)it.f * geo.n2Pad;
+                for (int sb = it.sb0; sb < it.sb1; ++sb) {
+                    const float4 a = __ldg(&Aglob[sb * TC_SBLK + ep.q * 32 + lane]);
+                    bool found = false;
+                    for (int k = 0; k < 64 && colBase + k < geo.n2; ++k) {
+                        const float4 b = __ldg(&Bglob[colBase + k]);
+                        if (!found && strict_within(a, b, fpar, p.d2, p.literal)) found = true;
                     }
-                    nf = 0;
-                    __syncwarp();
-                };
-                for (int jb = it.jb0; jb < it.jb1; ++jb, ++g) {
-                    #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t r[32], gb[8];
-                        bool cand;
-                        ep.load_half(h, g & 1u, r, gb, cand, geo.trace, g);
-                        unsigned bal = __ballot_sync(NDA_FULL_MASK, cand) & ~foundMask;
-                        if (bal) {
-                            // flagged half: is the largest D of a flagged lane above the SURE threshold?  Then the
-                            // atom is within, no strict re-evaluation (and it is switched off right away)
-                            __half2 m = __hmax2(*reinterpret_cast<const __half2 *>(&r[0]), *reinterpret_cast<const __half2 *>(&r[1]));
-                            #pragma unroll
-                            for (int i = 2; i < 32; ++i) m = __hmax2(m, *reinterpret_cast<const __half2 *>(&r[i]));
-                            const bool sure = __hge(__hmax(__low2half(m), __high2half(m)), sureH);
-                            const unsigned sb = __ballot_sync(NDA_FULL_MASK, sure) & bal;
-                            foundMask |= sb;
-                            nSure += __popc(sb);
-                            bal &= ~sb;
-                            if (bal) {
-                                if (lane == 0) flags[nf] = make_uint2((unsigned)(jb * 2 + h), bal);
-                                if (++nf == kFlagCap) resolve();
-                            }
-                        }
-                    }
+                    const unsigned fb = __ballot_sync(NDA_FULL_MASK, found);
+                    const int word = sb * (TC_SBLK / 32) + ep.q;
+                    if (fb && lane == 0 && word < p.wordsPerFrame) atomicOr(&bitsF[word], fb);
                 }
-                if (nf) resolve();
+                continue;
+            }
+
+            const unsigned ab = kt & 1u;
+            bar_wait(ep.rfull0 + ab * 8, (kt >> 1) & 1u);      // resident originals and frame parameters have landed
+            const TcFrame *tfS = &s.sItem[ab];
+            const __half sureH = __float2half_ru(tfS->sureDelta);
+            const float4 *rOrig = reinterpret_cast<const float4 *>(s.sR + ab * TC_RBUF_BYTES + TC_REMB_BYTES) + ep.cq * 64;
+            int nf = 0;
+            // recorded (step, lanes): the 64 resident atoms of this warp are re-evaluated with the reference
+            // arithmetic, two per lane, for every recorded streamed atom
+            auto resolve = [&]() {
                 __syncwarp();
-                if (lane == 0) bar_arrive(ep.aempty0 + ab * 8);   // done with this item's shared-memory data
-                ++kt;
+                const FrameParams fpar = tfS->fp;
+                const float4 b0 = rOrig[lane], b1 = rOrig[32 + lane];
+                for (int i = 0; i < nf; ++i) {
+                    const uint2 fl = flags[i];
+                    const int word = (int)fl.x * (TC_SBLK / 32) + ep.q;
+                    const float4 ao = __ldg(&Aglob[(int)fl.x * TC_SBLK + ep.q * 32 + lane]);
+                    unsigned owners = fl.y, hits = 0u;
+                    while (owners) {
+                        const int o = __ffs(owners) - 1;
+                        owners &= owners - 1;
+                        float4 a;
+                        a.x = __shfl_sync(NDA_FULL_MASK, ao.x, o);
+                        a.y = __shfl_sync(NDA_FULL_MASK, ao.y, o);
+                        a.z = __shfl_sync(NDA_FULL_MASK, ao.z, o);
+                        a.w = 0.f;
+                        const bool hit = strict_within(a, b0, fpar, p.d2, p.literal) || strict_within(a, b1, fpar, p.d2, p.literal);
+                        if (__any_sync(NDA_FULL_MASK, hit)) hits |= 1u << o;
+                        nCand += 2;
+                    }
+                    if (hits && lane == 0 && word < p.wordsPerFrame) atomicOr(&bitsF[word], hits);
+                }
+                nf = 0;
+                __syncwarp();
+            };
+            for (int sb = it.sb0; sb < it.sb1; ++sb, ++g) {
+                uint32_t r[32], gb[8];
+                bool cand;
+                ep.load_step(g, r, gb, cand, geo.trace);
+                unsigned bal = __ballot_sync(NDA_FULL_MASK, cand);
+                if (bal) {
+                    // is the largest D of a flagged lane above the SURE threshold?  Then the atom is within
+                    __half2 m = __hmax2(*reinterpret_cast<const __half2 *>(&r[0]), *reinterpret_cast<const __half2 *>(&r[1]));
+                    #pragma unroll
+                    for (int i = 2; i < 32; ++i) m = __hmax2(m, *reinterpret_cast<const __half2 *>(&r[i]));
+                    const bool sure = __hge(__hmax(__low2half(m), __high2half(m)), sureH);
+                    const unsigned sbal = __ballot_sync(NDA_FULL_MASK, sure) & bal;
+                    const int word = sb * (TC_SBLK / 32) + ep.q;
+                    if (sbal && lane == 0 && word < p.wordsPerFrame) atomicOr(&bitsF[word], sbal);
+                    bal &= ~sbal;
+                    if (bal) {
+                        if (lane == 0) flags[nf] = make_uint2((unsigned)sb, bal);
+                        if (++nf == kFlagCap) resolve();
+                    }
+                }
             }
-            if (lane == 0) {
-                const int word = (it.ia * TC_ATILE + rowWarp) >> 5;
-                if (word < p.wordsPerFrame) p.bits[(size_t)it.f * p.wordsPerFrame + word] = foundMask;
-            }
+            if (nf) resolve();
+            __syncwarp();
+            if (lane == 0) bar_arrive(ep.rempty0 + ab * 8);    // done with this item's resident data
+            ++kt;
         }
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nCand += __shfl_xor_sync(NDA_FULL_MASK, nCand, o);
         if (lane == 0 && nCand) atomicAdd(&geo.stats[0], (unsigned long long)nCand);
-        (void)nSure;
     }
     tc_teardown(tmem);
 }

@@ -10,12 +10,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
 {
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
 }
-__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, long long *out)
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, long long *out, int vary)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 16384);
-    uint32_t *tmemPtr = reinterpret_cast<uint32_t *>(smem + 16384 + 16);
-    for (int i = threadIdx.x; i < 4096; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 65536);
+    uint32_t *tmemPtr = reinterpret_cast<uint32_t *>(smem + 65536 + 16);
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x3c003c00u;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -31,10 +31,14 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, long lon
     const uint32_t tmem = *tmemPtr;
     if (threadIdx.x == 0) {
         const uint32_t idesc = (1u << 4) | (((uint32_t)N >> 3) << 17) | ((128u >> 4) << 24);
-        const uint64_t da = make_desc(smem_u32(smem)), db = make_desc(smem_u32(smem) + 4096);
+        uint64_t da = make_desc(smem_u32(smem)), db = make_desc(smem_u32(smem) + 4096);
         const long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
             const uint32_t d = tmem + (uint32_t)((i & 1) * 256);
+            if (vary) {
+                da = make_desc(smem_u32(smem) + (uint32_t)(i & 3) * 4096u);
+                db = make_desc(smem_u32(smem) + 16384u + (uint32_t)((i >> 2) % 6) * 6144u + (uint32_t)((i >> 1) & 1) * 1024u);
+            }
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                          "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                          :: "r"(d), "l"(da), "l"(db), "r"(idesc), "r"(0u) : "memory");
@@ -57,17 +61,18 @@ int main()
 {
     long long *d, h[2];
     cudaMalloc(&d, 16);
-    cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+    cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66048);
     const int Ns[5] = {32, 64, 128, 256, 16};
-    for (int grid : {1, 148})
-        for (int n = 0; n < 5; ++n)
-            for (int iters : {1, 64, 1024}) {
-                rate_kernel<<<grid, 128, 32768>>>(Ns[n], iters, d);
+    for (int vary : {0, 1})
+        for (int n = 0; n < 4; ++n)
+            for (int iters : {64, 1024}) {
+                const int grid = 148;
+                rate_kernel<<<grid, 128, 66048>>>(Ns[n], iters, d, vary);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
                 cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-                printf("grid %3d N %3d iters %4d: issue %7lld clk, issue+complete %7lld clk  (%.1f clk/MMA)\n",
-                       grid, Ns[n], iters, h[0], h[1], (double)h[1] / iters);
+                printf("vary %d N %3d iters %4d: issue %7lld clk, issue+complete %7lld clk  (%.1f clk/MMA)\n",
+                       vary, Ns[n], iters, h[0], h[1], (double)h[1] / iters);
             }
     return 0;
 }

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Pipeline timeline of the tensor-core within kernel (CTA 0): NDA_TC_TRACE=1 python tools/tc_trace.py
 
-Per B block g: when each MMA warp got its TMEM half back and had committed, when epilogue warps 0 and 15
-saw the half and had loaded it.  Prints intervals in clocks."""
+Per step g: when the MMA warp got its TMEM buffer back and had committed, when epilogue warps 0 and 15
+saw the buffer and had loaded it.  Prints intervals in clocks."""
 import ctypes, os, sys
 import numpy as np
 import torch
@@ -26,19 +26,19 @@ tr = np.zeros(256 * 12, dtype=np.int64)
 _capi.check(lib.nda_debug_tc_trace(tr.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))))
 tr = tr.reshape(256, 12)
 t0 = tr[tr > 0].min()
-names = ["m0.pass", "m0.done", "m1.pass", "m1.done", "e0.h0.see", "e0.h0.ld", "e0.h1.see", "e0.h1.ld",
-         "e15.h0.see", "e15.h0.ld", "e15.h1.see", "e15.h1.ld"]
-print("g  " + " ".join("%10s" % n for n in names))
-for g in range(40, 64):
-    print("%3d " % g + " ".join("%10d" % (v - t0) for v in tr[g]))
-d = np.diff(tr[20:200, 0])
-print("block period (m0.pass to m0.pass): mean %.0f  min %d  max %d" % (d.mean(), d.min(), d.max()))
-for a, b, lbl in [(0, 1, "MMA warp 0: pass tempty -> issued+committed"), (1, 4, "m0 committed -> e0 sees tfull[0]"),
-                  (4, 5, "e0: tfull[0] seen -> loaded"), (5, 6, "e0: h0 loaded -> sees tfull[1]"), (6, 7, "e0: tfull[1] seen -> loaded"),
-                  (8, 9, "e15: tfull[0] seen -> loaded"), (3, 6, "m1 committed -> e0 sees tfull[1]")]:
-    x = tr[20:200, b] - tr[20:200, a]
-    print("%-48s mean %6.0f  min %6d  max %6d" % (lbl, x.mean(), x.min(), x.max()))
-x = tr[21:200, 0] - tr[20:199, 5]
-print("%-48s mean %6.0f  min %6d  max %6d" % ("e0 loaded h0(g) -> m0 passes tempty for g+1", x.mean(), x.min(), x.max()))
-x = tr[21:200, 0] - tr[20:199, 9]
-print("%-48s mean %6.0f  min %6d  max %6d" % ("e15 loaded h0(g) -> m0 passes tempty for g+1", x.mean(), x.min(), x.max()))
+names = {0: "mma.pass", 1: "mma.done", 4: "e0.see", 5: "e0.ld", 8: "e15.see", 9: "e15.ld"}
+cols = sorted(names)
+print("g   " + " ".join("%10s" % names[k] for k in cols))
+for g in range(64, 96):
+    print("%3d " % g + " ".join("%10d" % (tr[g][k] - t0) for k in cols))
+d = np.diff(tr[20:250, 0])
+print("step period (mma.pass to mma.pass): mean %.0f  median %.0f  min %d  max %d" % (d.mean(), np.median(d), d.min(), d.max()))
+for a, b, lbl in [(0, 1, "MMA warp: buffer back -> issued + committed"), (1, 4, "committed -> e0 sees tfull"),
+                  (4, 5, "e0: tfull seen -> loaded"), (8, 9, "e15: tfull seen -> loaded")]:
+    x = tr[20:250, b] - tr[20:250, a]
+    print("%-48s mean %6.0f  median %6.0f  min %6d  max %6d" % (lbl, x.mean(), np.median(x), x.min(), x.max()))
+for k, lbl in [(5, "e0"), (9, "e15")]:
+    x = tr[22:250, 0] - tr[20:248, k]
+    print("%-48s mean %6.0f  median %6.0f  min %6d  max %6d" % (lbl + " loaded step g -> MMA warp gets buffer for g+2", x.mean(), np.median(x), x.min(), x.max()))
+x = tr[21:250, 4] - tr[20:249, 5]
+print("%-48s mean %6.0f  median %6.0f  min %6d  max %6d" % ("e0: loaded step g -> sees step g+1", x.mean(), np.median(x), x.min(), x.max()))
