@@ -482,7 +482,10 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
         const float *hc = nullptr;
         int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
         if (rc0) return rc0;
-        if (tc_frames_eligible(hc, fb, fe, T0, 0.006)) {
+        const bool okTc = tc_frames_eligible(hc, fb, fe, T0, 0.006);
+        if (getenv("NDA_DEBUG")) fprintf(stderr, "[nda] rdf: tensor filter %s (T %.3f, frames %d..%d, cell0 %.2f %.2f %.2f)\n",
+                                         okTc ? "on" : "off", T0, fb, fe, hc[3 * (size_t)fb], hc[3 * (size_t)fb + 1], hc[3 * (size_t)fb + 2]);
+        if (okTc) {
             g_last_filter.store(100);
             return dev_rdf_tc(c, L, st, d_sel1, n1, d_sel2, n2, d_gid, nGroups, d_counts, nBins, d_cell, nF, fb, fe,
                               sameSel, dr, d_idx1, d_idx2, T0);
