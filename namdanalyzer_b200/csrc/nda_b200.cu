@@ -203,11 +203,11 @@ static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // ------------------------------------------------------------------------------------------
 static int launch_pack(Ctx &c, cudaStream_t st, const float *src, int nFtot, const int *gather, int n,
                        int nPad, int f0, int nFc, const int *gid, float4 *dst, unsigned *maxAbs,
-                       const float *cell, float4 *dstW, int pairLayout = 0)
+                       const float *cell, float4 *dstW, int pairLayout = 0, __half *embA = nullptr)
 {
     (void)c;
     dim3 grid(nPad / 32, (nFc + 31) / 32);
-    pack_kernel<<<grid, 256, 0, st>>>(src, nFtot, gather, n, nPad, f0, nFc, gid, dst, maxAbs, cell, dstW, pairLayout);
+    pack_kernel<<<grid, 256, 0, st>>>(src, nFtot, gather, n, nPad, f0, nFc, gid, dst, maxAbs, cell, dstW, pairLayout, embA);
     LAUNCHED();
     return NDA_OK;
 }
@@ -349,8 +349,9 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
     for (int f0 = fb; f0 < fe; f0 += pass) {
         const int nFc = std::min(pass, fe - f0);
         CK(cudaMemsetAsync(L.maxAbs.p, 0, (size_t)nFc * sizeof(unsigned), st));
+        // the A-role embedding needs no threshold: it is written by the pack kernel itself
         int rc = launch_pack(c, st, d_sel1, nF, d_idx1, n1, n1Pad, f0, nFc, sameSel ? d_gid : nullptr,
-                             L.packA.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, nullptr, 0);
+                             L.packA.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, nullptr, 0, L.embA.as<__half>());
         if (rc) return rc;
         if (!sameSel) {
             rc = launch_pack(c, st, d_sel2, nF, d_idx2, n2, n2Pad, f0, nFc, d_gid,
@@ -365,8 +366,6 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
         prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.maxAbs.as<unsigned>(), -1.0,
                                                           L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
-        rc = launch_embed(st, g.A, n1Pad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embA.as<__half>(), 1);
-        if (rc) return rc;
         rc = launch_embed(st, g.B, n2Pad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embB.as<__half>(), 0);
         if (rc) return rc;
         g.EA = L.embA.as<__half>(); g.EB = L.embB.as<__half>();
@@ -432,7 +431,7 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
         a.bits = d_bits + (size_t)(f0 - fb) * words;
         CK(cudaMemsetAsync(a.bits, 0, (size_t)nFc * words * sizeof(unsigned), st));   // found atoms are OR-ed in
         int rc = launch_pack(c, st, d_all, nF, d_outSel, outSize, nAPad, f0, nFc, nullptr,
-                             L.packA.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, nullptr, 0);
+                             L.packA.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, nullptr, 0, L.embA.as<__half>());
         if (rc) return rc;
         rc = launch_pack(c, st, d_all, nF, d_refSel, refSize, nBPad, f0, nFc, nullptr,
                          L.packB.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, nullptr, 0);
@@ -448,8 +447,6 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
         prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.maxAbs.as<unsigned>(), sureD2,
                                                           L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
-        rc = launch_embed(st, g.A, nAPad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embA.as<__half>(), 1);
-        if (rc) return rc;
         rc = launch_embed(st, g.B, nBPad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embB.as<__half>(), 0);
         if (rc) return rc;
         g.EA = L.embA.as<__half>(); g.EB = L.embB.as<__half>();

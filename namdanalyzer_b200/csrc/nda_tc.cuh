@@ -19,7 +19,7 @@
 // reference.  The per-pair cost drops from ~9 issue slots (fold2 filter) to ~0.4.
 //
 // Precision of the filter (all slack goes into the threshold, see prep_tc_kernel): phi is computed
-// in float64 and stored as fp16; K = 16 holds [hi(6) 1 1 | lo(6) 0 0] for the A role and
+// with a float64 range reduction (embed_axis) and stored as fp16; K = 16 holds [hi(6) 1 1 | lo(6) 0 0] for the A role and
 // [hi(6) -t_hi -t_lo | hi(6) 0 0] for the B role, so A's rounding is compensated and only B's 2^-11
 // relative rounding remains: |dot_computed - dot_exact| <= E = P (2^-11 * 1.01 + 2^-18).
 //
@@ -41,7 +41,6 @@
 //                    (its 64 resident atoms): one tcgen05.ld (.pack::16b) per step, the buffer is released
 //                    right after the load so the next MMA overlaps the reduction.
 #pragma once
-#include <cuda_fp16.h>
 #include "nda_kernels.cuh"
 
 constexpr int TC_EPI_WARPS = 16;
@@ -170,17 +169,12 @@ embed_kernel(const float4 *__restrict__ packed, int nPad, int nFc, const float *
         if (finite) {
             #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const double c = fabs((double)cf[k]);
-                if (c > 0.0 && c < 1.0e30) {
-                    const double rho = c * 0.15915494309189535;      // c / (2 pi)
-                    double s, co;
-                    sincospi(2.0 * ((double)x[k] / c), &s, &co);
-                    const double pc = rho * co, ps = rho * s;
-                    hi[2 * k] = __float2half_rn((float)pc);
-                    hi[2 * k + 1] = __float2half_rn((float)ps);
-                    lo[2 * k] = __float2half_rn((float)(pc - (double)__half2float(hi[2 * k])));
-                    lo[2 * k + 1] = __float2half_rn((float)(ps - (double)__half2float(hi[2 * k + 1])));
-                }
+                float pc, ps;
+                embed_axis(x[k], cf[k], pc, ps);                    // nda_kernels.cuh
+                hi[2 * k] = __float2half_rn(pc);
+                hi[2 * k + 1] = __float2half_rn(ps);
+                lo[2 * k] = __float2half_rn(pc - __half2float(hi[2 * k]));
+                lo[2 * k + 1] = __float2half_rn(ps - __half2float(hi[2 * k + 1]));
             }
         }
         __align__(16) __half c1[8];
