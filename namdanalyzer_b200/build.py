@@ -29,7 +29,8 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = ["-DNDA_TC_TRACE_BUILD"] if os.environ.get("NDA_TC_TRACE_BUILD") == "1" else []   # tools/tc_trace.py
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", OUT] + [os.path.join(SRC_DIR, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return OUT

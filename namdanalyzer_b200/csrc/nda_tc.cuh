@@ -290,10 +290,16 @@ struct TcGeom {
 
 // clock64 stamp k of step g (CTA 0, first 256 steps): 0/1 MMA warp got its TMEM buffer back / committed,
 // 4/5 epilogue warp 0 saw the buffer / had loaded it, 8/9 epilogue warp 15
+// Compiled in only with -DNDA_TC_TRACE_BUILD (NDA_TC_TRACE_BUILD=1 python -m namdanalyzer_b200.build --force):
+// even predicated off, the stamps cost issue slots in the epilogue loop.
 __device__ __forceinline__ void tc_stamp(const long long *tracePtr, unsigned g, int k)
 {
+#ifdef NDA_TC_TRACE_BUILD
     if (tracePtr && blockIdx.x == 0 && g < 256u && (threadIdx.x & 31) == 0)
         const_cast<long long *>(tracePtr)[g * 12 + k] = clock64();
+#else
+    (void)tracePtr; (void)g; (void)k;
+#endif
 }
 
 struct TcItem { int f, c, sb0, sb1; };
@@ -565,9 +571,15 @@ struct TcEpi {
         const unsigned h = g & 1u;
         bar_wait(tfull0 + h * 8, (g >> 1) & 1u);
         tc_fence_after();
+#ifdef NDA_TC_TRACE_BUILD
         if (trace && (cq * 4 + q == 0 || cq * 4 + q == 15)) tc_stamp(trace, g, cq * 4 + q == 0 ? 4 : 8);
+#endif
         tc_ld64p(tm0 + h * 256u, r);
+#ifdef NDA_TC_TRACE_BUILD
         if (trace && (cq * 4 + q == 0 || cq * 4 + q == 15)) tc_stamp(trace, g, cq * 4 + q == 0 ? 5 : 9);
+#else
+        (void)trace;
+#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(tempty0 + h * 8);            // the MMA of step g + 2 may start

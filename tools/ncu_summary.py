@@ -31,6 +31,10 @@ METRICS = [
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
     ("smsp__cycles_active.avg", "SMSP active cycles"),
+    ("sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active %"),
+    ("sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "tcgen05 issue pipe %"),
+    ("sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active", "TMA issue pipe %"),
+    ("lts__t_bytes.sum", "L2 bytes"),
 ]
 
 

@@ -1,5 +1,9 @@
 #!/usr/bin/env python
-"""Pipeline timeline of the tensor-core within kernel (CTA 0): NDA_TC_TRACE=1 python tools/tc_trace.py
+"""Pipeline timeline of the tensor-core within kernel (CTA 0).  Needs a trace build of the library:
+
+    NDA_TC_TRACE_BUILD=1 python -m namdanalyzer_b200.build --force && python tools/tc_trace.py
+    python -m namdanalyzer_b200.build --force        # back to the production build
+
 
 Per step g: when the MMA warp got its TMEM buffer back and had committed, when epilogue warps 0 and 15
 saw the buffer and had loaded it.  Prints intervals in clocks."""
