@@ -211,3 +211,40 @@ def test_device_api_tensor_path_frame_ranges_add_up():
     bits = whole.cpu().numpy().view(np.uint32)
     got = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(24, -1)[:, : os_.numel()]
     assert np.array_equal(got.T.astype(np.int32), want[c["outSel"]])
+
+
+def test_mixed_exact_and_tensor_frames_in_one_call(force_tc):
+    """a runaway coordinate (> 2^20 cells from the origin) sends ITS frame to the all-exact path inside the
+    tensor-core kernels, the other frames keep the filter: TMA / MMA warps skip those items, the epilogue
+    warps evaluate them strictly, and the barrier protocol must stay consistent"""
+    rng = np.random.default_rng(4242)
+    nF = 7
+    cell = np.tile(np.array([[60.0, 62.0, 58.0]], np.float32), (nF, 1))
+    xyz = rng.uniform(0, 60, (1900, nF, 3)).astype(np.float32)
+    xyz[5, 2, 0] = 3.0e8                                                # frame 2: ref atom far away
+    xyz[1500, 5, 1] = -7.0e8                                            # frame 5: out atom far away
+    r = np.arange(0, 700, dtype=np.int32)
+    o = np.arange(700, 1900, dtype=np.int32)
+    assert np.array_equal(within_mask(xyz, r, o, cell, 3.5), port.within(xyz, r, o, cell, 3.5))
+    assert force_tc.nda_last_filter() == TC
+    a, b = np.ascontiguousarray(xyz[:700]), np.ascontiguousarray(xyz[700:])
+    assert np.array_equal(rdf_counts(a, b, cell, 0, 60, 0.1), port.rdf_counts(a, b, cell, 0, 60, 0.1).astype(np.int64))
+    assert np.array_equal(rdf_counts(b, b, cell, 1, 60, 0.1), port.rdf_counts(b, b, cell, 1, 60, 0.1).astype(np.int64))
+    assert force_tc.nda_last_filter() == TC
+
+
+def test_many_small_items_and_single_frame(force_tc):
+    """more work items than CTAs with one or two steps each, and a one-frame call: item boundaries, the
+    STOP stage and odd step counts per stage"""
+    rng = np.random.default_rng(99)
+    for nF, n1, n2 in ((1, 130, 3000), (40, 129, 700), (3, 385, 257)):
+        cell = np.full((nF, 3), 55.0, np.float32)
+        a = rng.uniform(0, 55, (n1, nF, 3)).astype(np.float32)
+        b = rng.uniform(0, 55, (n2, nF, 3)).astype(np.float32)
+        assert np.array_equal(rdf_counts(a, b, cell, 0, 50, 0.1), port.rdf_counts(a, b, cell, 0, 50, 0.1).astype(np.int64))
+        assert force_tc.nda_last_filter() == TC
+        allA = np.concatenate([a, b])
+        r = np.arange(n1, n1 + n2, dtype=np.int32)
+        o = np.arange(0, n1, dtype=np.int32)
+        assert np.array_equal(within_mask(allA, r, o, cell, 2.5), port.within(allA, r, o, cell, 2.5))
+        assert force_tc.nda_last_filter() == TC
