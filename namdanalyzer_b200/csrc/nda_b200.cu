@@ -698,9 +698,8 @@ static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all,
         }
     }
     if (d_out) {
-        if ((fe - fb + 255) / 256 > 65535) return fail(NDA_ERR_ARG, "frame range too large for the mask expansion");
-        dim3 grid(outSize, (fe - fb + 255) / 256);
-        expand_mask_kernel<<<grid, 256, 0, st>>>(d_bits, words, d_outSel, outSize, nF, fb, fe - fb, d_out);
+        dim3 grid((fe - fb + 127) / 128, std::min(words, 65535));
+        expand_mask_kernel<<<grid, 128, 0, st>>>(d_bits, words, d_outSel, outSize, nF, fb, fe - fb, d_out);
         LAUNCHED();
     }
     return NDA_OK;

@@ -170,7 +170,8 @@ embed_kernel(const float4 *__restrict__ packed, int nPad, int nFc, const float *
             #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 float pc, ps;
-                embed_axis(x[k], cf[k], pc, ps);                    // nda_kernels.cuh
+                const double ca = fabs((double)cf[k]);
+                embed_axis(x[k], cf[k], ca > 0.0 ? 1.0 / ca : 0.0, pc, ps);     // nda_kernels.cuh
                 hi[2 * k] = __float2half_rn(pc);
                 hi[2 * k + 1] = __float2half_rn(ps);
                 lo[2 * k] = __float2half_rn(pc - __half2float(hi[2 * k]));
