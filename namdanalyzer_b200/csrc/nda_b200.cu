@@ -815,7 +815,9 @@ struct Uploader {
         size_t bytesPerFrame = 0;
         for (auto &a : arr) { a.pinned = host_ptr_is_pinned(a.host); bytesPerFrame += (size_t)a.nRows * 12; }
         if (bytesPerFrame == 0) bytesPerFrame = 12;
-        nChunks = (int)std::min<size_t>((size_t)maxChunks, std::max<size_t>(1, bytesPerFrame * nFc / ((size_t)12 << 20)));
+        // ~20 MB per chunk: with the tensor-core kernels a chunk's compute is a fraction of its copy, and
+        // every chunk costs ~30 us of copy set-up (measured: 110 MB in 5-6 chunks 2.6 ms, in 16 chunks 3.0 ms)
+        nChunks = (int)std::min<size_t>((size_t)maxChunks, std::max<size_t>(1, bytesPerFrame * nFc / ((size_t)20 << 20)));
         if (envOverride) if (const char *e = getenv(envOverride)) { int v = atoi(e); if (v >= 1) nChunks = v; }
         nChunks = std::max(1, std::min(nChunks, nFc));
         chunk = (nFc + nChunks - 1) / nChunks;
@@ -871,7 +873,9 @@ struct Uploader {
         CK(cudaStreamWaitEvent(c.copyStream, c.evDone[b], 0));             // device buffer b is free again
         // strided 2-D DMA from pinned memory runs at about half the link rate on one copy engine,
         // so the rows of every run are split over two copy streams (NDA_COPY_STREAMS=1 disables)
-        static const bool twoStreams = !(getenv("NDA_COPY_STREAMS") && atoi(getenv("NDA_COPY_STREAMS")) == 1);
+        // (rows of >= 2 KB reach the link rate on one engine; NDA_COPY_STREAMS=1|2 overrides)
+        static const int csEnv = getenv("NDA_COPY_STREAMS") ? atoi(getenv("NDA_COPY_STREAMS")) : 0;
+        const bool twoStreams = csEnv == 2 || (csEnv != 1 && w < 2048);
         bool usedSecond = false;
         for (size_t i = 0; i < arr.size(); ++i) {
             UploadArray &a = arr[i];
@@ -1274,7 +1278,7 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
     // ---- frame chunks: copy of chunk k+1 overlaps pack + kernel of chunk k (two raw buffers)
     Uploader up(*c, nF, fb, fe);
     up.add(allAtoms, nRows, runs);
-    rc = up.begin(8, "NDA_WITHIN_CHUNKS");
+    rc = up.begin(6, "NDA_WITHIN_CHUNKS");
     if (rc) return rc;
     const int chunk = up.chunk, nChunks = up.nChunks;
 
