@@ -58,7 +58,7 @@ int  nda_set_within_pure_predicate(int on);
  * of the call is not eligible (cut-off too close to the cell size, no unit cell, dense ranges) */
 int  nda_last_filter(void);
 /* debugging aid: with NDA_TC_TRACE=1 the last tensor-core within call recorded clock64 stamps of
- * CTA 0's pipeline (256 blocks x 12 stamps, see csrc/nda_tc.cuh: tc_stamp); copies them out */
+ * CTA 0's pipeline (256 steps x 32 stamps, see csrc/nda_tc.cuh: tc_stamp); copies them out */
 int  nda_debug_tc_trace(long long *out);
 
 /* ---- drop-in host entry points (reference signatures) --------------------------- */

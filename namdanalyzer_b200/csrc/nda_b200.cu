@@ -413,8 +413,8 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
     g.trace = nullptr;
     if (const char *e = getenv("NDA_TC_TRACE")) {              // debugging aid: clock64 trace of CTA 0 (tools/tc_trace.py)
         if (atoi(e) == 1) {
-            CK(c.sum.reserve(256 * 12 * 8));
-            CK(cudaMemsetAsync(c.sum.p, 0, 256 * 12 * 8, st));
+            CK(c.sum.reserve(256 * 32 * 8));
+            CK(cudaMemsetAsync(c.sum.p, 0, 256 * 32 * 8, st));
             g.trace = c.sum.as<long long>();
         }
     }
@@ -974,15 +974,15 @@ int nda_set_device(int device)
 int nda_get_device(void) { return g_dev; }
 int nda_last_filter(void) { return g_last_filter.load(); }
 
-// debugging aid (NDA_TC_TRACE=1): copies the clock64 trace of the last within call, 256 x 12 values
+// debugging aid (NDA_TC_TRACE=1): copies the clock64 trace of the last within call, 256 x 32 values
 int nda_debug_tc_trace(long long *out)
 {
     Ctx *c;
     int rc = ctx_get(&c);
     if (rc) return rc;
-    if (!c->sum.p || c->sum.cap < 256 * 12 * 8) return fail(NDA_ERR_ARG, "no trace recorded");
+    if (!c->sum.p || c->sum.cap < 256 * 32 * 8) return fail(NDA_ERR_ARG, "no trace recorded");
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(out, c->sum.p, 256 * 12 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, c->sum.p, 256 * 32 * 8, cudaMemcpyDeviceToHost));
     return NDA_OK;
 }
 uint64_t nda_launch_count(void) { return g_launches.load(); }

@@ -289,15 +289,15 @@ struct TcGeom {
     long long *trace;               // optional clock64 trace of CTA 0 (tools/tc_trace.py); nullptr in production
 };
 
-// clock64 stamp k of step g (CTA 0, first 256 steps): 0/1 MMA warp got its TMEM buffer back / committed,
-// 4/5 epilogue warp 0 saw the buffer / had loaded it, 8/9 epilogue warp 15
+// clock64 stamp k of step g (CTA 0, first 256 steps; 32 slots per step): 0/1 MMA warp got its TMEM buffer
+// back / committed, 4/5 epilogue warp 0 saw the buffer / had loaded it, 8/9 epilogue warp 15, 16 + w: warp w loaded
 // Compiled in only with -DNDA_TC_TRACE_BUILD (NDA_TC_TRACE_BUILD=1 python -m namdanalyzer_b200.build --force):
 // even predicated off, the stamps cost issue slots in the epilogue loop.
 __device__ __forceinline__ void tc_stamp(const long long *tracePtr, unsigned g, int k)
 {
 #ifdef NDA_TC_TRACE_BUILD
     if (tracePtr && blockIdx.x == 0 && g < 256u && (threadIdx.x & 31) == 0)
-        const_cast<long long *>(tracePtr)[g * 12 + k] = clock64();
+        const_cast<long long *>(tracePtr)[g * 32 + k] = clock64();
 #else
     (void)tracePtr; (void)g; (void)k;
 #endif
@@ -578,6 +578,7 @@ struct TcEpi {
         tc_ld64p(tm0 + h * 256u, r);
 #ifdef NDA_TC_TRACE_BUILD
         if (trace && (cq * 4 + q == 0 || cq * 4 + q == 15)) tc_stamp(trace, g, cq * 4 + q == 0 ? 5 : 9);
+        tc_stamp(trace, g, 16 + cq * 4 + q);                   // every epilogue warp: buffer loaded
 #else
         (void)trace;
 #endif

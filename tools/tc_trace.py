@@ -26,9 +26,9 @@ for _ in range(2):
     _capi.check(lib.nda_dev_within(xyz.data_ptr(), xyz.shape[0], nF, rs.data_ptr(), rs.numel(), os_.data_ptr(),
                                    os_.numel(), bits.data_ptr(), None, cell.data_ptr(), 3.0, 0, nF, st))
 torch.cuda.synchronize()
-tr = np.zeros(256 * 12, dtype=np.int64)
+tr = np.zeros(256 * 32, dtype=np.int64)
 _capi.check(lib.nda_debug_tc_trace(tr.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))))
-tr = tr.reshape(256, 12)
+tr = tr.reshape(256, 32)
 t0 = tr[tr > 0].min()
 names = {0: "mma.pass", 1: "mma.done", 4: "e0.see", 5: "e0.ld", 8: "e15.see", 9: "e15.ld"}
 cols = sorted(names)
@@ -46,3 +46,18 @@ for k, lbl in [(5, "e0"), (9, "e15")]:
     print("%-48s mean %6.0f  median %6.0f  min %6d  max %6d" % (lbl + " loaded step g -> MMA warp gets buffer for g+2", x.mean(), np.median(x), x.min(), x.max()))
 x = tr[21:250, 4] - tr[20:249, 5]
 print("%-48s mean %6.0f  median %6.0f  min %6d  max %6d" % ("e0: loaded step g -> sees step g+1", x.mean(), np.median(x), x.min(), x.max()))
+
+d = np.diff(tr[8:250, 0])
+print("histogram of step periods (clocks):", np.histogram(d, bins=[0, 300, 400, 500, 600, 800, 1000, 1500, 2500, 10000])[0].tolist(),
+      "edges 0,300,400,500,600,800,1000,1500,2500,10000")
+big = np.flatnonzero(d > 1200) + 8
+print("steps followed by a gap > 1200 clocks:", big.tolist())
+
+ld = tr[30:250, 16:32]                                      # every epilogue warp: when it had loaded step g
+first, last = ld.min(1), ld.max(1)
+print("spread of the 16 warps' loads per step: mean %.0f  median %.0f  max %d" % ((last - first).mean(), np.median(last - first), (last - first).max()))
+print("slowest warp per step (histogram over warps 0..15):", np.bincount(ld.argmax(1), minlength=16).tolist())
+x = tr[32:250, 0] - last[:218]
+print("last warp loaded step g -> MMA warp gets the buffer for g+2: mean %.0f  median %.0f  min %d" % (x.mean(), np.median(x), x.min()))
+x = first - tr[30:250, 1]
+print("MMA committed -> first warp has loaded: mean %.0f  median %.0f" % (x.mean(), np.median(x)))
