@@ -30,6 +30,8 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     extra = ["-DNDA_TC_TRACE_BUILD"] if os.environ.get("NDA_TC_TRACE_BUILD") == "1" else []   # tools/tc_trace.py
+    if os.environ.get("NDA_TC_EXPERIMENT"):       # pipeline-floor experiments (1: no reduction, 2: no TMEM load); WRONG results
+        extra.append("-DNDA_TC_EXPERIMENT=" + os.environ["NDA_TC_EXPERIMENT"])
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", OUT] + [os.path.join(SRC_DIR, s) for s in SOURCES]
     subprocess.check_call(cmd)

@@ -575,7 +575,12 @@ struct TcEpi {
 #ifdef NDA_TC_TRACE_BUILD
         if (trace && (cq * 4 + q == 0 || cq * 4 + q == 15)) tc_stamp(trace, g, cq * 4 + q == 0 ? 4 : 8);
 #endif
+#if defined(NDA_TC_EXPERIMENT) && NDA_TC_EXPERIMENT == 2
+        #pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0xffffffffu;       // floor experiment: no TMEM load at all
+#else
         tc_ld64p(tm0 + h * 256u, r);
+#endif
 #ifdef NDA_TC_TRACE_BUILD
         if (trace && (cq * 4 + q == 0 || cq * 4 + q == 15)) tc_stamp(trace, g, cq * 4 + q == 0 ? 5 : 9);
         tc_stamp(trace, g, 16 + cq * 4 + q);                   // every epilogue warp: buffer loaded
@@ -585,10 +590,16 @@ struct TcEpi {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(tempty0 + h * 8);            // the MMA of step g + 2 may start
+#if defined(NDA_TC_EXPERIMENT) && NDA_TC_EXPERIMENT >= 1
+        #pragma unroll
+        for (int b = 0; b < 8; ++b) gb[b] = r[4 * b];          // floor experiment: no reduction, never a candidate
+        cand = (r[0] == 0x12345678u) && (r[31] == 0x9abcdef0u);
+#else
         #pragma unroll
         for (int b = 0; b < 8; ++b) gb[b] = r[4 * b] & r[4 * b + 1] & r[4 * b + 2] & r[4 * b + 3];
         const uint32_t top = (gb[0] & gb[1] & gb[2]) & (gb[3] & gb[4] & gb[5]) & (gb[6] & gb[7]);
         cand = (top & TC_SIGNS) != TC_SIGNS;
+#endif
     }
 };
 
