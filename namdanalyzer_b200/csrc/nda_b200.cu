@@ -228,9 +228,16 @@ static bool filter_tc_requested()
 // 0.6 % of the pairs are in range (config 3, 2.3 %: fold2 0.96e12 vs tensor 0.42e12 pairs/s;
 // config 5, 0.14 %: fold2 2.7e12 vs tensor 6.0e12), estimated here from the cut-off sphere volume
 // over the cell volume.
-static bool tc_frames_eligible(const float *cell, int fb, int fe, double T, double maxFraction)
+// nStream / nResident: the tensor kernels pad the streamed selection to 128 and the resident one to 256
+// atoms; with more than ~4x padding the packed-FP32 kernel (5.4x slower per pair) wins.
+static bool tc_frames_eligible(const float *cell, int fb, int fe, double T, double maxFraction,
+                               int nStream, int nResident)
 {
     const double k = 0.15915494309189535;
+    {
+        const double padded = (double)round_up(nStream, 128) * (double)round_up(nResident, 256);
+        if (padded > 4.0 * (double)nStream * (double)nResident && !getenv("NDA_TC_ALLOW_PADDING")) return false;
+    }
     if (const char *e = getenv("NDA_TC_MAX_FRACTION")) { const double v = atof(e); if (v > 0.0) maxFraction = v; }
     for (int f = fb; f < fe; ++f) {
         const double cx = fabs((double)cell[3 * (size_t)f]), cy = fabs((double)cell[3 * (size_t)f + 1]), cz = fabs((double)cell[3 * (size_t)f + 2]);
@@ -479,7 +486,7 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
         const float *hc = nullptr;
         int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
         if (rc0) return rc0;
-        const bool okTc = tc_frames_eligible(hc, fb, fe, T0, 0.006);
+        const bool okTc = tc_frames_eligible(hc, fb, fe, T0, 0.006, n1, n2);
         if (getenv("NDA_DEBUG")) fprintf(stderr, "[nda] rdf: tensor filter %s (T %.3f, frames %d..%d, cell0 %.2f %.2f %.2f)\n",
                                          okTc ? "on" : "off", T0, fb, fe, hc[3 * (size_t)fb], hc[3 * (size_t)fb + 1], hc[3 * (size_t)fb + 2]);
         if (okTc) {
@@ -605,7 +612,7 @@ static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all,
         const float *hc = nullptr;
         int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
         if (rc0) return rc0;
-        if (tc_frames_eligible(hc, fb, fe, Tt, 0.02)) {
+        if (tc_frames_eligible(hc, fb, fe, Tt, 0.02, outSize, refSize)) {
             rc0 = dev_within_tc(c, L, st, d_all, nF, d_refSel, refSize, d_outSel, outSize, d_bits, d_cell, d2t, Tt, fb, fe);
             if (rc0) return rc0;
             doneTc = true;

@@ -21,9 +21,10 @@ TC = 100
 
 @pytest.fixture()
 def force_tc():
-    old = {k: os.environ.get(k) for k in ("NDA_FILTER", "NDA_TC_MAX_FRACTION")}
+    old = {k: os.environ.get(k) for k in ("NDA_FILTER", "NDA_TC_MAX_FRACTION", "NDA_TC_ALLOW_PADDING")}
     os.environ["NDA_FILTER"] = "tc"
     os.environ["NDA_TC_MAX_FRACTION"] = "1.0"
+    os.environ["NDA_TC_ALLOW_PADDING"] = "1"
     yield _capi.load()
     for k, v in old.items():
         if v is None:
@@ -119,16 +120,20 @@ def test_within_pairs_on_both_sides_of_the_cutoff(dist):
     r = np.arange(0, n_ref, dtype=np.int32)
     o = np.arange(n_ref, xyz.shape[0], dtype=np.int32)
     want = port.within(xyz, r, o, cell, dist)
-    got = within_mask(xyz, r, o, cell, dist)
-    assert lib.nda_last_filter() == TC
-    assert np.array_equal(got, want)
-    frac = want[n_ref:].mean()
-    assert 0.2 < frac < 0.8                                             # both sides of the cut-off are populated
-    os.environ["NDA_TC_NO_SURE"] = "1"                                  # same masks without the shortcut
+    os.environ["NDA_TC_ALLOW_PADDING"] = "1"                            # few ref atoms: keep the tensor path anyway
     try:
-        assert np.array_equal(within_mask(xyz, r, o, cell, dist), want)
+        got = within_mask(xyz, r, o, cell, dist)
+        assert lib.nda_last_filter() == TC
+        assert np.array_equal(got, want)
+        frac = want[n_ref:].mean()
+        assert 0.2 < frac < 0.8                                         # both sides of the cut-off are populated
+        os.environ["NDA_TC_NO_SURE"] = "1"                              # same masks without the shortcut
+        try:
+            assert np.array_equal(within_mask(xyz, r, o, cell, dist), want)
+        finally:
+            del os.environ["NDA_TC_NO_SURE"]
     finally:
-        del os.environ["NDA_TC_NO_SURE"]
+        del os.environ["NDA_TC_ALLOW_PADDING"]
 
 
 def test_within_literal_early_out_below_one_angstrom_on_tensor_path():
@@ -180,6 +185,9 @@ def test_filter_routing():
     assert lib.nda_last_filter() != TC                                  # 6.5 % of the pairs in range: dense
     assert np.array_equal(rdf_counts(a, a, cell, 1, 30, 0.1), port.rdf_counts(a, a, cell, 1, 30, 0.1).astype(np.int64))
     assert lib.nda_last_filter() == TC                                  # 0.05 %: sparse
+    tiny = np.arange(0, 9, dtype=np.int32)                              # 9 ref atoms would be padded to 256 columns
+    assert np.array_equal(within_mask(xyz, tiny, o, cell, 3.0), port.within(xyz, tiny, o, cell, 3.0))
+    assert lib.nda_last_filter() != TC
     mixed = cell.copy()
     mixed[1] = 100000.0                                                 # one frame without a cell: whole call falls back
     assert np.array_equal(within_mask(xyz, r, o, mixed, 3.0), port.within(xyz, r, o, mixed, 3.0))
