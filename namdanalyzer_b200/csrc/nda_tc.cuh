@@ -714,21 +714,51 @@ rdf_tc_kernel(const RdfTcArgs p)
                         mlo &= (unsigned)keep;
                         mhi &= (unsigned)(keep >> 32);
                     }
-                    // every lane pushes its own candidates, one per round, with its atom's ORIGINAL coordinates
+                    // candidates -> ring, with the streamed atom's ORIGINAL coordinates (taken from the stage)
                     float4 e = reinterpret_cast<const float4 *>(s.sS + slot * TC_STAGE_BYTES + TC_SPS * TC_SEMB_BYTES)[u * TC_SBLK + ep.q * 32 + lane];
-                    for (;;) {
-                        const bool has = (mlo | mhi) != 0u;
-                        const unsigned bal = __ballot_sync(NDA_FULL_MASK, has);
-                        if (!bal) break;
-                        if (has) {
-                            int k;
-                            if (mlo) { k = __ffs(mlo) - 1; mlo &= mlo - 1; }
-                            else     { k = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
-                            e.w = __int_as_float(k);
-                            myQ[(qhead + qcount + __popc(bal & ltmask)) % TC_QCAP] = e;
+                    unsigned owners = __ballot_sync(NDA_FULL_MASK, (mlo | mhi) != 0u);
+                    const int maxPerLane = __reduce_max_sync(NDA_FULL_MASK, __popc(mlo) + __popc(mhi));
+                    // rounds of the lane-parallel push = most candidates on one lane (~30 instructions each);
+                    // the owner-by-owner push costs ~22 instructions per lane that has any
+                    if (4 * __popc(owners) >= 5 * maxPerLane) {
+                        // every lane pushes its own candidates, one per round
+                        for (;;) {
+                            const bool has = (mlo | mhi) != 0u;
+                            const unsigned bal = __ballot_sync(NDA_FULL_MASK, has);
+                            if (!bal) break;
+                            if (has) {
+                                int k;
+                                if (mlo) { k = __ffs(mlo) - 1; mlo &= mlo - 1; }
+                                else     { k = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
+                                e.w = __int_as_float(k);
+                                myQ[(qhead + qcount + __popc(bal & ltmask)) % TC_QCAP] = e;
+                            }
+                            qcount += __popc(bal);
+                            if (qcount >= 32) drain(32);
                         }
-                        qcount += __popc(bal);
-                        if (qcount >= 32) drain(32);
+                    } else {
+                        // few lanes with many candidates each (a water next to the protein sees half of a resident
+                        // chunk, its neighbours none): go owner by owner; the owner's mask IS the ballot, lane l
+                        // takes columns l and 32 + l
+                        while (owners) {
+                            const int o = __ffs(owners) - 1;
+                            owners &= owners - 1;
+                            const unsigned om[2] = {__shfl_sync(NDA_FULL_MASK, mlo, o), __shfl_sync(NDA_FULL_MASK, mhi, o)};
+                            float4 eo;
+                            eo.x = __shfl_sync(NDA_FULL_MASK, e.x, o);
+                            eo.y = __shfl_sync(NDA_FULL_MASK, e.y, o);
+                            eo.z = __shfl_sync(NDA_FULL_MASK, e.z, o);
+                            #pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                const unsigned m = om[half];
+                                if ((m >> lane) & 1u) {
+                                    eo.w = __int_as_float(32 * half + lane);
+                                    myQ[(qhead + qcount + __popc(m & ltmask)) % TC_QCAP] = eo;
+                                }
+                                qcount += __popc(m);
+                                if (qcount >= 32) drain(32);
+                            }
+                        }
                     }
                 }
                 if (u == TC_SPS - 1 || sb + 1 == it.sb1) {         // last block of its stage
