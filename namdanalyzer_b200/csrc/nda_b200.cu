@@ -223,11 +223,10 @@ static bool filter_tc_requested()
 
 // Host-side mirror of prep_tc_kernel with a 10 % margin: true when no frame of [fb, fe) would be
 // sent to the all-exact path by the tensor-core filter.  T = in-range limit on r2.
-// maxFraction: the tensor-core filter pays per CANDIDATE (mask + queue + strict re-evaluation on 16
-// warps per SM), the packed-FP32 filter per PAIR; measured on a B200 the cross-over is where about
-// 0.6 % of the pairs are in range (config 3, 2.3 %: fold2 0.96e12 vs tensor 0.42e12 pairs/s;
-// config 5, 0.14 %: fold2 2.7e12 vs tensor 6.0e12), estimated here from the cut-off sphere volume
-// over the cell volume.
+// maxFraction: optional cap on the expected in-range fraction (cut-off sphere over cell volume).  Measured on
+// a B200 (tools/density_sweep.py, config-3 geometry) the tensor filter is ahead at every density it is
+// eligible for -- 3.6x at 0.02 % of the pairs in range, 2.1x at 2.2 %, 2.0x at 5.4 % -- so the default is no
+// cap; NDA_TC_MAX_FRACTION=<f> sets one.
 // nStream / nResident: the tensor kernels pad the streamed selection to 128 and the resident one to 256
 // atoms; with more than ~4x padding the packed-FP32 kernel (5.4x slower per pair) wins.
 static bool tc_frames_eligible(const float *cell, int fb, int fe, double T, double maxFraction,
@@ -486,7 +485,7 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
         const float *hc = nullptr;
         int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
         if (rc0) return rc0;
-        const bool okTc = tc_frames_eligible(hc, fb, fe, T0, 0.006, n1, n2);
+        const bool okTc = tc_frames_eligible(hc, fb, fe, T0, 1.0, n1, n2);
         if (getenv("NDA_DEBUG")) fprintf(stderr, "[nda] rdf: tensor filter %s (T %.3f, frames %d..%d, cell0 %.2f %.2f %.2f)\n",
                                          okTc ? "on" : "off", T0, fb, fe, hc[3 * (size_t)fb], hc[3 * (size_t)fb + 1], hc[3 * (size_t)fb + 2]);
         if (okTc) {
@@ -612,7 +611,7 @@ static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all,
         const float *hc = nullptr;
         int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
         if (rc0) return rc0;
-        if (tc_frames_eligible(hc, fb, fe, Tt, 0.02, outSize, refSize)) {
+        if (tc_frames_eligible(hc, fb, fe, Tt, 1.0, outSize, refSize)) {
             rc0 = dev_within_tc(c, L, st, d_all, nF, d_refSel, refSize, d_outSel, outSize, d_bits, d_cell, d2t, Tt, fb, fe);
             if (rc0) return rc0;
             doneTc = true;

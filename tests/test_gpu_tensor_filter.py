@@ -1,9 +1,8 @@
 """GPU (B200): the tensor-core filter (csrc/nda_tc.cuh) against the oracle.
 
 The filter only PRE-SELECTS pairs (periodic embedding -> tcgen05.mma -> sign test); every count and mask
-bit must still be the reference's, bit for bit.  These tests force the tensor-core path onto geometries
-the production heuristic would hand to the packed-FP32 filter (NDA_TC_MAX_FRACTION=1: dense ranges are a
-performance question, not a correctness one), attack the two thresholds of the within kernel with pairs
+bit must still be the reference's, bit for bit.  These tests keep the tensor-core path on tiny selections
+the production heuristic would hand to the packed-FP32 filter (NDA_TC_ALLOW_PADDING=1), attack the two thresholds of the within kernel with pairs
 placed a few ulps on either side of the cut-off, and check the routing itself.
 """
 import os
@@ -181,8 +180,16 @@ def test_filter_routing():
     assert np.array_equal(within_mask(xyz, r, o, nocell, 3.0), port.within(xyz, r, o, nocell, 3.0))
     assert lib.nda_last_filter() != TC
     a = np.ascontiguousarray(xyz[:1500])
+    assert np.array_equal(rdf_counts(a, a, cell, 1, 200, 0.1), port.rdf_counts(a, a, cell, 1, 200, 0.1).astype(np.int64))
+    assert lib.nda_last_filter() != TC                                  # 20 A in a 60 A cell: beyond ~0.28 c
     assert np.array_equal(rdf_counts(a, a, cell, 1, 149, 0.1), port.rdf_counts(a, a, cell, 1, 149, 0.1).astype(np.int64))
-    assert lib.nda_last_filter() != TC                                  # 6.5 % of the pairs in range: dense
+    assert lib.nda_last_filter() == TC                                  # 6.5 % of the pairs in range: still tensor
+    os.environ["NDA_TC_MAX_FRACTION"] = "0.01"                          # ... unless a density cap is asked for
+    try:
+        assert np.array_equal(rdf_counts(a, a, cell, 1, 149, 0.1), port.rdf_counts(a, a, cell, 1, 149, 0.1).astype(np.int64))
+        assert lib.nda_last_filter() != TC
+    finally:
+        del os.environ["NDA_TC_MAX_FRACTION"]
     assert np.array_equal(rdf_counts(a, a, cell, 1, 30, 0.1), port.rdf_counts(a, a, cell, 1, 30, 0.1).astype(np.int64))
     assert lib.nda_last_filter() == TC                                  # 0.05 %: sparse
     tiny = np.arange(0, 9, dtype=np.int32)                              # 9 ref atoms would be padded to 256 columns
