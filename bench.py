@@ -210,7 +210,7 @@ def workload_config(args, sample=None):
     c = {"workload": "BASELINE configs[1]: 'name OH2 and within 3 of protein', 25000 atoms "
                      "(1231 ref x 7923 out), %d frames per GPU per step, synthetic seed 1002" % args.frames,
          "pairs_per_step_per_gpu": 1231.0 * 7923.0 * args.frames,
-         "l2_policy": "inputs (300 MB raw + 164 MB packed per step) exceed the 126 MB L2; no explicit flush",
+         "l2_policy": "inputs (300 MB raw coordinates + ~450 MB packed coordinates and fp16 embeddings per step) exceed the 126 MB L2; no explicit flush",
          "frame_sharding": "each rank owns its own frame batch; no data-path collective"}
     if sample:
         c["sample"] = sample
