@@ -227,6 +227,18 @@ static bool filter_tc_requested()
 // a B200 (tools/density_sweep.py, config-3 geometry) the tensor filter is ahead at every density it is
 // eligible for -- 3.6x at 0.02 % of the pairs in range, 2.1x at 2.2 %, 2.0x at 5.4 % -- so the default is no
 // cap; NDA_TC_MAX_FRACTION=<f> sets one.
+// Longest range the tensor filter takes, as thr <= factor * P (P = sum (c_k / 2 pi)^2; for a cubic cell
+// factor 1 is a range of 0.28 c, 1.5 is 0.34 c, 2 is 0.39 c, 3 is 0.48 c).  The chord bound weakens with
+// the range (S saturates at 4 P) and the candidate path takes over: measured on small water boxes
+// (tools/range_sweep.py, 14.9 A) the tensor filter is 1.44x / 1.2x / 1.24x ahead of the FP32 filter at
+// range / c = 0.22 / 0.28 / 0.34 and behind (0.75x, 0.84x) at 0.40 and 0.48.  Results are identical at
+// every range; NDA_TC_RANGE_FACTOR overrides.
+static double tc_range_factor()
+{
+    if (const char *e = getenv("NDA_TC_RANGE_FACTOR")) { const double v = atof(e); if (v > 0.0) return v; }
+    return 1.5;
+}
+
 // nStream / nResident: the tensor kernels pad the streamed selection to 128 and the resident one to 256
 // atoms; with more than ~4x padding the packed-FP32 kernel (5.4x slower per pair) wins.
 static bool tc_frames_eligible(const float *cell, int fb, int fe, double T, double maxFraction,
@@ -244,7 +256,7 @@ static bool tc_frames_eligible(const float *cell, int fb, int fe, double T, doub
         const double P = (cx * cx + cy * cy + cz * cz) * k * k;
         const double Eb = P * (4.8828125e-04 * 1.01 + 3.814697265625e-06) + 1.0e-6;
         const double thr = T * 1.001 + 1.0e-6;
-        if (!(2.5 * Eb * 1.1 <= thr && thr * 1.1 <= P && P < 5.0e4)) return false;
+        if (!(2.5 * Eb * 1.1 <= thr && thr * 1.1 <= tc_range_factor() * P * 1.2 && P < 2.5e4)) return false;
         const double sphere = 4.1887902047863905 * T * sqrt(T);
         if (sphere > maxFraction * cx * cy * cz) return false;
     }
@@ -370,7 +382,7 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
                                                              L.fp.as<FrameParams>(), stats);
         LAUNCHED();
         prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.maxAbs.as<unsigned>(), -1.0,
-                                                          L.thrDot.as<TcFrame>(), stats);
+                                                          tc_range_factor() * 1.2, L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
         rc = launch_embed(st, g.B, n2Pad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embB.as<__half>(), 0);
         if (rc) return rc;
@@ -451,7 +463,7 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
         // per-axis early-outs (getWithin.cpp:64-71) that holds for distance >= 1 (SURVEY B-2)
         const double sureD2 = (!a.literal || d2 >= 1.0f) && !getenv("NDA_TC_NO_SURE") ? (double)d2 : -1.0;
         prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.maxAbs.as<unsigned>(), sureD2,
-                                                          L.thrDot.as<TcFrame>(), stats);
+                                                          tc_range_factor() * 1.2, L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
         rc = launch_embed(st, g.B, nBPad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embB.as<__half>(), 0);
         if (rc) return rc;

@@ -96,7 +96,7 @@ struct __align__(16) TcFrame {
 };
 
 __global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, const unsigned *__restrict__ maxAbs,
-                               double sureD2, TcFrame *__restrict__ tf, unsigned long long *__restrict__ stats)
+                               double sureD2, double rangeFactor, TcFrame *__restrict__ tf, unsigned long long *__restrict__ stats)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nFc) return;
@@ -112,7 +112,7 @@ __global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, cons
         const double Eb = P * (4.8828125e-04 * 1.01 + 3.814697265625e-06) + 1.0e-6;
         const double thr = (double)o.fp.thr;
         const double t = P - 0.5 * thr - 1.25 * Eb;
-        if (2.5 * Eb <= thr && thr <= P && t > 0.0 && P < 6.0e4) {      // P < 6e4: thrDot and every D fit fp16
+        if (2.5 * Eb <= thr && thr <= rangeFactor * P && P < 3.0e4) {   // P < 3e4: thrDot and every D fit fp16
             o.thrDot = __double2float_rd(t);
             if (sureD2 > 0.0) {
                 const double cmax = fmax(fabs((double)o.fp.cx), fmax(fabs((double)o.fp.cy), fabs((double)o.fp.cz)));
@@ -143,10 +143,10 @@ __global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, cons
 
 // ------------------------------------------------------------------------------------------
 // embedding: packed float4 [nFc][nPad] -> fp16 blocks [nFc][nPad/rows][2][rows][8]
-//   A role (rows = 128): [hi(6), 1, 1 | lo(6), 0, 0]      B role (rows = 256): [hi(6), -t_hi, -t_lo | hi(6), 0, 0]
+//   A role (rows = 128): [hi(6), 1, 1 | lo(6), isPad, -6e4]   B role (rows = 256): [hi(6), -t_hi, -t_lo | hi(6), -6e4, isPad]
 // with t_hi + t_lo <= thrDot of the frame, so that the MMA delivers D = dot - thrDot and the SIGN of
-// D is the filter decision.  Padding and non-finite atoms get a zero embedding but keep slots 6/7:
-// their D is -thrDot < 0, never a candidate.
+// D is the filter decision.  Padding and non-finite atoms get a zero embedding and isPad = 1: every pair
+// they take part in has D <= -6e4, never a candidate (thrDot itself may be negative for long ranges).
 // grid (nPad/128, min(nFc, 65535)), block 128
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -184,7 +184,11 @@ embed_kernel(const float4 *__restrict__ packed, int nPad, int nFc, const float *
         if (roleA) {
             hi[6] = __float2half_rn(1.f);
             hi[7] = hi[6];
+            c1[6] = __float2half_rn(finite ? 0.f : 1.f);        // (isPadA, -6e4) x (-6e4, isPadB): see embed_row_a
+            c1[7] = __float2half_rn(-60000.f);
         } else {
+            c1[6] = __float2half_rn(-60000.f);
+            c1[7] = __float2half_rn(finite ? 0.f : 1.f);
             const float t = tf[f].thrDot;                       // 3e38 (-> inf) on all-exact frames: unused there
             const __half th = __float2half_rd(t);
             const __half tl = __float2half_rd(t - __half2float(th));

@@ -180,8 +180,8 @@ def test_filter_routing():
     assert np.array_equal(within_mask(xyz, r, o, nocell, 3.0), port.within(xyz, r, o, nocell, 3.0))
     assert lib.nda_last_filter() != TC
     a = np.ascontiguousarray(xyz[:1500])
-    assert np.array_equal(rdf_counts(a, a, cell, 1, 200, 0.1), port.rdf_counts(a, a, cell, 1, 200, 0.1).astype(np.int64))
-    assert lib.nda_last_filter() != TC                                  # 20 A in a 60 A cell: beyond ~0.28 c
+    assert np.array_equal(rdf_counts(a, a, cell, 1, 250, 0.1), port.rdf_counts(a, a, cell, 1, 250, 0.1).astype(np.int64))
+    assert lib.nda_last_filter() != TC                                  # 25 A in a 60 A cell: beyond ~0.34 c
     assert np.array_equal(rdf_counts(a, a, cell, 1, 149, 0.1), port.rdf_counts(a, a, cell, 1, 149, 0.1).astype(np.int64))
     assert lib.nda_last_filter() == TC                                  # 6.5 % of the pairs in range: still tensor
     os.environ["NDA_TC_MAX_FRACTION"] = "0.01"                          # ... unless a density cap is asked for
@@ -263,3 +263,26 @@ def test_many_small_items_and_single_frame(force_tc):
         o = np.arange(0, n1, dtype=np.int32)
         assert np.array_equal(within_mask(allA, r, o, cell, 2.5), port.within(allA, r, o, cell, 2.5))
         assert force_tc.nda_last_filter() == TC
+
+
+def test_long_ranges_up_to_half_the_cell(force_tc):
+    """NDA_TC_RANGE_FACTOR lifts the range limit: the dot-product threshold turns negative, padding atoms
+    are kept out by their own K slots, and the counts must still be the oracle's up to ~0.48 c"""
+    rng = np.random.default_rng(31)
+    cell = np.array([[31.0, 33.0, 30.5], [32.0, 31.5, 31.0]], np.float32)
+    a = rng.uniform(-40, 70, (700, 2, 3)).astype(np.float32)
+    b = rng.uniform(-40, 70, (300, 2, 3)).astype(np.float32)
+    os.environ["NDA_TC_RANGE_FACTOR"] = "3.9"
+    try:
+        for nb in (100, 149):                                           # 10 A and 14.9 A in a ~31 A cell
+            assert np.array_equal(rdf_counts(a, a, cell, 1, nb, 0.1), port.rdf_counts(a, a, cell, 1, nb, 0.1).astype(np.int64))
+            assert force_tc.nda_last_filter() == TC
+            assert np.array_equal(rdf_counts(a, b, cell, 0, nb, 0.1), port.rdf_counts(a, b, cell, 0, nb, 0.1).astype(np.int64))
+        allA = np.concatenate([a, b])
+        r = np.arange(700, 1000, dtype=np.int32)
+        o = np.arange(0, 700, dtype=np.int32)
+        for dist in (9.0, 14.0):
+            assert np.array_equal(within_mask(allA, r, o, cell, dist), port.within(allA, r, o, cell, dist))
+            assert force_tc.nda_last_filter() == TC
+    finally:
+        del os.environ["NDA_TC_RANGE_FACTOR"]
