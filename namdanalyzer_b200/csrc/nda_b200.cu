@@ -104,6 +104,8 @@ struct Ctx {
     DevBuf raw[2][2];                             // [array][double buffer] raw coordinate chunks
     DevBuf cell, idx1, idx2, gid, counts, bits, sum;
     std::vector<float> hostCell;                  // cell edges read back for the filter choice (device API)
+    const float *hostCellPtr = nullptr;           // ... of this device array, frames [hostCellFb, hostCellFe)
+    int hostCellFb = 0, hostCellFe = 0, hostCellUses = 0;
     void *stage[2] = {nullptr, nullptr};          // pinned staging for pageable inputs
     size_t stageCap[2] = {0, 0};
     cudaError_t stage_reserve(int b, size_t bytes)
@@ -264,13 +266,22 @@ static bool tc_frames_eligible(const float *cell, int fb, int fe, double T, doub
 }
 
 // cell edges of frames [fb, fe) on the host: the caller's host array when there is one, else a
-// read-back of the device array (device API; 12 bytes per frame)
+// read-back of the device array (device API; 12 bytes per frame).  The read-back needs a stream
+// synchronisation, so it is cached per (device pointer, frame range) and refreshed every 64th call:
+// the host copy only decides WHICH filter runs -- prep_frames / prep_tc_kernel re-check every frame on
+// the device and send a frame that does not qualify to the all-exact path -- so a stale copy can cost
+// time, never correctness.
 static int host_cell_view(Ctx &c, cudaStream_t st, const float *h_cell, const float *d_cell, int fb, int fe, const float **out)
 {
     if (h_cell) { *out = h_cell; return NDA_OK; }
-    c.hostCell.resize((size_t)3 * fe);
-    CK(cudaMemcpyAsync(c.hostCell.data() + 3 * (size_t)fb, d_cell + 3 * (size_t)fb, (size_t)(fe - fb) * 12, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    const bool hit = c.hostCellPtr == d_cell && fb >= c.hostCellFb && fe <= c.hostCellFe && ++c.hostCellUses < 64 &&
+                     !getenv("NDA_NO_CELL_CACHE");
+    if (!hit) {
+        c.hostCell.resize((size_t)3 * fe);
+        CK(cudaMemcpyAsync(c.hostCell.data() + 3 * (size_t)fb, d_cell + 3 * (size_t)fb, (size_t)(fe - fb) * 12, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        c.hostCellPtr = d_cell; c.hostCellFb = fb; c.hostCellFe = fe; c.hostCellUses = 0;
+    }
     *out = c.hostCell.data();
     return NDA_OK;
 }
