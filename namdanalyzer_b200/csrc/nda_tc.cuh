@@ -899,6 +899,8 @@ within_tc_kernel(const WithinTcArgs p)
                     bal &= ~sbal;
                     if (bal) {
                         if (lane == 0) flags[nf] = make_uint2((unsigned)sb, bal);
+                        // resolve() will need these 32 atoms' original coordinates: start pulling them in now
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(&Aglob[sb * TC_SBLK + ep.q * 32 + lane]));
                         if (++nf == kFlagCap) resolve();
                     }
                 }
