@@ -10,6 +10,7 @@
 #include <string.h>
 #include <math.h>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -76,6 +77,9 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// rows [srcRow, srcRow + count*stride) of a host array land at uploaded rows [dstRow, dstRow + count)
+struct RowRun { int dstRow, srcRow, stride, count; };
+
 struct Ctx {
     int dev = -1;
     bool ready = false;
@@ -117,6 +121,14 @@ struct Ctx {
         return e;
     }
     double stats[4] = {0, 0, 0, 0};
+    // row plan of the last within call, reused while the caller passes the same selections again
+    // (frame-by-frame and chunk-by-chunk callers do: selection/selParser.py:117-126)
+    struct WithinPlan {
+        std::vector<int> refSel, outSel, remap, ref2, out2;
+        std::vector<RowRun> runs;
+        int nAtoms = -1, nRows = 0;
+    } plan;
+    bool statsPending = false;                    // counters of the last call still sit in lane[].ctl (read on demand)
     // CUDA-event brackets around the pair kernel of every pass of the last entry-point call
     std::vector<cudaEvent_t> kev;
     int kevUsed = 0;
@@ -762,8 +774,6 @@ static int dev_distances(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, c
 //    DMA'd as one contiguous block; the driver's own pageable path moves narrow rows one by one.
 //  * Two device buffers per array alternate between the copy stream and the compute stream:
 //    the upload of chunk k+1 overlaps pack + kernel of chunk k.
-struct RowRun { int dstRow, srcRow, stride, count; };
-
 static void runs_from_rows(const std::vector<int> &rows, std::vector<RowRun> &runs)
 {
     runs.clear();
@@ -819,8 +829,10 @@ struct UploadArray {
 
 struct Uploader {
     Ctx &c;
-    int nF, fb, fe, chunk = 0, nChunks = 0;
+    int nF, fb, fe, chunk = 0, nChunks = 0;     // chunk = the largest chunk (what the buffers are sized for)
+    std::vector<int> bnd;                        // chunk k covers frames [bnd[k], bnd[k+1])
     std::vector<UploadArray> arr;
+    bool taperTail = true;
     Uploader(Ctx &ctx, int nF_, int fb_, int fe_) : c(ctx), nF(nF_), fb(fb_), fe(fe_) {}
 
     void add(const float *host, int nRows)                              // all rows 0..nRows-1
@@ -853,6 +865,26 @@ struct Uploader {
         const int maxChunk = (int)std::max<size_t>(1, ((size_t)3 << 30) / bytesPerFrame);   // <= 3 GB per buffer
         chunk = std::max(1, std::min(chunk, maxChunk));
         nChunks = (nFc + chunk - 1) / chunk;
+        bnd.assign((size_t)nChunks + 1, fe);
+        for (int k = 0; k < nChunks; ++k) bnd[k] = fb + k * chunk;
+        // The copies are the bottleneck, so what the caller waits for after the last byte has arrived is the
+        // compute (and the host post-processing) of the LAST chunk: taper the tail -- one more chunk, the last
+        // two of 1/2 and 1/4 of the regular size (NDA_NO_TAPER=1 keeps them uniform).
+        static const bool noTaper = getenv("NDA_NO_TAPER") != nullptr;
+        if (taperTail && !noTaper && nChunks >= 3 && nChunks < maxChunks + 1 && chunk * 4 <= maxChunk * 3 && nFc >= 16 * nChunks) {
+            const int n = nChunks + 1;
+            const double unit = (double)nFc / ((double)(n - 2) + 0.75);
+            bnd.assign((size_t)n + 1, fe);
+            bnd[0] = fb;
+            int big = 0;
+            for (int k = 1; k < n; ++k) {
+                const double upTo = k <= n - 2 ? unit * k : unit * (n - 2) + unit * 0.5;
+                bnd[k] = std::min(fe - 1, std::max(bnd[k - 1] + 1, fb + (int)(upTo + 0.5)));
+            }
+            for (int k = 0; k < n; ++k) big = std::max(big, bnd[k + 1] - bnd[k]);
+            nChunks = n;
+            chunk = big;
+        }
         size_t stageBytes = 0;
         for (size_t i = 0; i < arr.size(); ++i) {
             if (arr.size() > 2) return fail(NDA_ERR_ARG, "internal: at most two arrays per upload");
@@ -871,8 +903,8 @@ struct Uploader {
         return NDA_OK;
     }
 
-    int f0(int k) const { return fb + k * chunk; }
-    int f1(int k) const { return std::min(fe, f0(k) + chunk); }
+    int f0(int k) const { return bnd[k]; }
+    int f1(int k) const { return bnd[k + 1]; }
     float *dev(int i, int k) const { return c.raw[i][k & 1].as<float>(); }
 
     // enqueue the upload of chunk k on the copy stream (gathering on the host first if pageable)
@@ -959,6 +991,7 @@ struct Uploader {
 
 static cudaError_t reset_stats(Ctx &c, cudaStream_t st)
 {
+    c.statsPending = false;
     cudaError_t e = cudaMemsetAsync(c.lane[0].ctl.as<unsigned char>() + 16, 0, 16, st);
     if (e != cudaSuccess) return e;
     return cudaMemsetAsync(c.lane[1].ctl.as<unsigned char>() + 16, 0, 16, st);
@@ -966,15 +999,53 @@ static cudaError_t reset_stats(Ctx &c, cudaStream_t st)
 
 static int read_stats(Ctx &c, double pairs, float ms)
 {
+    c.stats[0] = pairs;
+    c.stats[3] = (double)ms;
+    c.statsPending = true;               // two blocking 16-byte reads (~35 us): only when somebody asks
+    return NDA_OK;
+}
+
+static int fetch_stats(Ctx &c)
+{
+    if (!c.statsPending) return NDA_OK;
+    CK(cudaDeviceSynchronize());         // a device-pointer call may still be running on the caller's stream
     unsigned long long h[2][2] = {{0, 0}, {0, 0}};
     CK(cudaMemcpy(h[0], c.lane[0].ctl.as<unsigned char>() + 16, 16, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(h[1], c.lane[1].ctl.as<unsigned char>() + 16, 16, cudaMemcpyDeviceToHost));
-    c.stats[0] = pairs;
     c.stats[1] = (double)(h[0][0] + h[1][0]);
     c.stats[2] = (double)(h[0][1] + h[1][1]);
-    c.stats[3] = (double)ms;
+    c.statsPending = false;
     return NDA_OK;
 }
+
+// host-side phase clock of one entry-point call (NDA_DEBUG=2 prints it)
+struct HostTrace {
+    bool on;
+    const char *what;
+    std::chrono::steady_clock::time_point t0, last;
+    std::string line;
+    explicit HostTrace(const char *w) : what(w)
+    {
+        static const bool e = getenv("NDA_DEBUG") && atoi(getenv("NDA_DEBUG")) >= 2;
+        on = e;
+        if (on) t0 = last = std::chrono::steady_clock::now();
+    }
+    void mark(const char *name)
+    {
+        if (!on) return;
+        auto t = std::chrono::steady_clock::now();
+        char b[96];
+        snprintf(b, sizeof b, " %s %.0f", name, std::chrono::duration<double, std::micro>(t - last).count());
+        line += b;
+        last = t;
+    }
+    ~HostTrace()
+    {
+        if (!on) return;
+        fprintf(stderr, "[nda] %s host us:%s | total %.0f\n", what, line.c_str(),
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 // ------------------------------------------------------------------------------------------
 // C ABI
@@ -1023,6 +1094,8 @@ int nda_last_stats(double stats[4])
     Ctx *c;
     int rc = ctx_get(&c);
     if (rc) return rc;
+    rc = fetch_stats(*c);
+    if (rc) return rc;
     memcpy(stats, c->stats, sizeof c->stats);
     return NDA_OK;
 }
@@ -1063,7 +1136,9 @@ int nda_dev_radial_nbr_counts(const float *d_sel1, int n1, const float *d_sel2, 
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     begin_call(*c);
     CK(reset_stats(*c, st));
-    return dev_rdf(*c, c->lane[0], st, d_sel1, n1, d_sel2, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr);
+    rc = dev_rdf(*c, c->lane[0], st, d_sel1, n1, d_sel2, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr);
+    if (rc) return rc;
+    return read_stats(*c, (sameSel ? 0.5 * (double)n1 * ((double)n1 - 1.0) : (double)n1 * (double)n2) * (fe - fb), 0.f);
 }
 
 int nda_dev_within(const float *d_allAtoms, int nAtoms, int nF, const int *d_refSel, int refSize,
@@ -1080,8 +1155,10 @@ int nda_dev_within(const float *d_allAtoms, int nAtoms, int nF, const int *d_ref
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     begin_call(*c);
     CK(reset_stats(*c, st));
-    return dev_within(*c, c->lane[0], st, d_allAtoms, nAtoms, nF, d_refSel, refSize, d_outSel, outSelSize, d_bits, d_out,
-                      d_cellDims, distance, fb, fe);
+    rc = dev_within(*c, c->lane[0], st, d_allAtoms, nAtoms, nF, d_refSel, refSize, d_outSel, outSelSize, d_bits, d_out,
+                    d_cellDims, distance, fb, fe);
+    if (rc) return rc;
+    return read_stats(*c, (double)refSize * outSelSize * (fe - fb), 0.f);
 }
 
 int nda_dev_distances_sum(const float *d_sel1, int n1, const float *d_sel2, int n2, double *d_sum,
@@ -1115,8 +1192,10 @@ int nda_dev_radial_nbr_counts_sel(const float *d_all, int nAtoms, const int *d_i
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     begin_call(*c);
     CK(reset_stats(*c, st));
-    return dev_rdf(*c, c->lane[0], st, d_all, n1, d_all, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr,
-                   d_idx1, d_idx2);
+    rc = dev_rdf(*c, c->lane[0], st, d_all, n1, d_all, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr,
+                 d_idx1, d_idx2);
+    if (rc) return rc;
+    return read_stats(*c, (sameSel ? 0.5 * (double)n1 * ((double)n1 - 1.0) : (double)n1 * (double)n2) * (fe - fb), 0.f);
 }
 
 int nda_dev_distances_sum_sel(const float *d_all, int nAtoms, const int *d_idx1, int n1, const int *d_idx2, int n2,
@@ -1281,35 +1360,56 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
         return fail(NDA_ERR_ARG, "null pointer argument");
     if (nAtoms < 0 || nF <= 0 || refSize < 0 || outSelSize < 0 || fb < 0 || fe > nF || fb > fe)
         return fail(NDA_ERR_ARG, "bad size / frame range");
-    for (int i = 0; i < refSize; ++i)
-        if (refSel[i] < 0 || refSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "refSel[%d] = %d outside [0, %d)", i, refSel[i], nAtoms);
-    for (int i = 0; i < outSelSize; ++i)
-        if (outSel[i] < 0 || outSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "outSel[%d] = %d outside [0, %d)", i, outSel[i], nAtoms);
-    if (outSelSize == 0 || fe == fb) return NDA_OK;
+    if (outSelSize == 0 || fe == fb) {
+        for (int i = 0; i < refSize; ++i)
+            if (refSel[i] < 0 || refSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "refSel[%d] = %d outside [0, %d)", i, refSel[i], nAtoms);
+        for (int i = 0; i < outSelSize; ++i)
+            if (outSel[i] < 0 || outSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "outSel[%d] = %d outside [0, %d)", i, outSel[i], nAtoms);
+        return NDA_OK;
+    }
     std::lock_guard<std::mutex> lk(g_mutex);
     Ctx *c;
     int rc = ctx_get(&c);
     if (rc) return rc;
     cudaStream_t st = c->stream;
     begin_call(*c);
+    HostTrace ht("within");
     const int nFc = fe - fb;
     const int words = (outSelSize + 31) / 32;
 
     // ---- which rows travel, and the selections re-expressed in uploaded-row numbers
-    std::vector<int> remap;
-    std::vector<RowRun> runs;
-    int nRows = 0;
-    plan_rows(refSel, refSize, outSel, outSelSize, nAtoms, remap, runs, nRows);
-    std::vector<int> ref2((size_t)std::max(refSize, 1)), out2((size_t)outSelSize);
-    for (int i = 0; i < refSize; ++i) ref2[i] = remap[refSel[i]];
-    for (int i = 0; i < outSelSize; ++i) out2[i] = remap[outSel[i]];
+    Ctx::WithinPlan &pl = c->plan;
+    const bool samePlan = pl.nAtoms == nAtoms && (int)pl.refSel.size() == refSize && (int)pl.outSel.size() == outSelSize &&
+                          (refSize == 0 || memcmp(pl.refSel.data(), refSel, (size_t)refSize * 4) == 0) &&
+                          memcmp(pl.outSel.data(), outSel, (size_t)outSelSize * 4) == 0;
+    if (!samePlan) {
+        pl.nAtoms = -1;
+        for (int i = 0; i < refSize; ++i)
+            if (refSel[i] < 0 || refSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "refSel[%d] = %d outside [0, %d)", i, refSel[i], nAtoms);
+        for (int i = 0; i < outSelSize; ++i)
+            if (outSel[i] < 0 || outSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "outSel[%d] = %d outside [0, %d)", i, outSel[i], nAtoms);
+        plan_rows(refSel, refSize, outSel, outSelSize, nAtoms, pl.remap, pl.runs, pl.nRows);
+        pl.ref2.resize((size_t)std::max(refSize, 1));
+        pl.out2.resize((size_t)outSelSize);
+        for (int i = 0; i < refSize; ++i) pl.ref2[i] = pl.remap[refSel[i]];
+        for (int i = 0; i < outSelSize; ++i) pl.out2[i] = pl.remap[outSel[i]];
+        pl.refSel.assign(refSel, refSel + refSize);
+        pl.outSel.assign(outSel, outSel + outSelSize);
+        pl.nAtoms = nAtoms;
+    }
+    const std::vector<int> &ref2 = pl.ref2, &out2 = pl.out2;
+    const int nRows = pl.nRows;
 
     // ---- frame chunks: copy of chunk k+1 overlaps pack + kernel of chunk k (two raw buffers)
     Uploader up(*c, nF, fb, fe);
-    up.add(allAtoms, nRows, runs);
+    up.add(allAtoms, nRows, pl.runs);
     rc = up.begin(6, "NDA_WITHIN_CHUNKS");
     if (rc) return rc;
-    const int chunk = up.chunk, nChunks = up.nChunks;
+    const int nChunks = up.nChunks;
+    ht.mark("plan");
+    rc = up.issue(0);                                       // the link is the bottleneck: start it first
+    if (rc) return rc;
+    ht.mark("issue0");
 
     CK(c->cell.reserve((size_t)nF * 12));
     CK(c->idx1.reserve((size_t)std::max(refSize, 1) * 4));
@@ -1326,7 +1426,7 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
 
     auto scatter = [&](int k) {                             // host: set the 1s of chunk k
         if (!out) return;
-        const int f0 = k * chunk, f1 = std::min(nFc, f0 + chunk);
+        const int f0 = up.f0(k) - fb, f1 = up.f1(k) - fb;
         // ~6e5 cache-missing stores for config 2: spread the frames over the host threads
         #pragma omp parallel for schedule(static) num_threads(g_host_threads) if (f1 - f0 >= 16)
         for (int f = f0; f < f1; ++f) {
@@ -1344,8 +1444,7 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
 
     CK(cudaEventRecord(c->evSetup, st));                    // lane 1 must see cell / selections uploaded
     CK(cudaStreamWaitEvent(c->lane[1].stream, c->evSetup, 0));
-    rc = up.issue(0);
-    if (rc) return rc;
+    ht.mark("setup");
     for (int k = 0; k < nChunks; ++k) {
         const int f0 = up.f0(k), wc = up.f1(k) - f0, buf = k & 1;
         Ctx::Lane &L = c->lane[buf];                        // alternate lanes: kernel k+1 fills the tail of kernel k
@@ -1370,8 +1469,11 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
     CK(cudaEventRecord(c->evLaneJoin, c->lane[1].stream));
     CK(cudaStreamWaitEvent(st, c->evLaneJoin, 0));
     CK(cudaEventRecord(c->ev1, st));
+    ht.mark("loop");
     CK(cudaStreamSynchronize(st));
+    ht.mark("sync");
     scatter(nChunks - 1);
+    ht.mark("scatter");
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     rc = read_stats(*c, (double)refSize * outSelSize * nFc, ms);
@@ -1542,6 +1644,7 @@ int nda_get_hb_counts(const float *acceptors, int nA, int nF, const float *donor
     }
     CK(cudaMemcpyAsync(counts, c->counts.p, (size_t)nF * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    c->statsPending = false;
     c->stats[0] = 0.5 * (double)nA * (double)nD;
     c->stats[1] = (double)nPairs;
     return NDA_OK;
