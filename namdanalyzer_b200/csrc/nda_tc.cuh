@@ -46,6 +46,7 @@
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_MMA_WARP  = TC_EPI_WARPS;                     // warp 16 issues the MMAs
 constexpr int TC_TMA_WARP  = TC_EPI_WARPS + 1;                 // warp 17 issues the TMA copies
+constexpr int TC_STAGE_FREE_WARP = 2;      // within kernel: the epilogue warp that releases a stage once its MMAs are done
 constexpr int TC_THREADS   = (TC_EPI_WARPS + 2) * 32;          // 576
 constexpr int TC_SBLK      = 128;                              // streamed atoms per step (MMA M)
 constexpr int TC_RBLK      = 256;                              // resident atoms per work item (MMA N)
@@ -405,16 +406,19 @@ __device__ __forceinline__ uint32_t tc_setup(const TcSmem &s, int origInStage)
 {
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        // a stage is free again when its MMA has completed (tcgen05.commit) and, if it carries
-        // original coordinates, when the 16 epilogue warps are done with them
-        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], origInStage ? 1 + TC_EPI_WARPS : 1); }
+        // A stage is free again when its MMAs have completed.  The epilogue says so, not a second
+        // tcgen05.commit of the MMA warp (back-to-back commits stall that warp for ~350 clocks, measured):
+        // a warp that has seen tfull of a stage's last block knows that block's MMA -- and, in issue order,
+        // every earlier one -- is done.  With original coordinates in the stage all 16 warps arrive when they
+        // are done with them; otherwise one designated warp arrives right after its tfull wait.
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], origInStage ? TC_EPI_WARPS : 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.tfull[i], 1);
             mbar_init(&s.tempty[i], TC_EPI_WARPS);
             mbar_init(&s.rfull[i], 1);
-            // a resident buffer (embedding, originals, frame parameters) is free when the item's MMAs
-            // have completed and the 16 epilogue warps have left the item
-            mbar_init(&s.rempty[i], 1 + TC_EPI_WARPS);
+            // a resident buffer (embedding, originals, frame parameters) is free when the 16 epilogue
+            // warps have left the item (each has then seen tfull of the item's last MMA)
+            mbar_init(&s.rempty[i], TC_EPI_WARPS);
         }
         mbar_fence_init();
     }
@@ -497,7 +501,9 @@ __device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem, cons
     const uint32_t tfull0 = smem_u32(s.tfull), tempty0 = smem_u32(s.tempty);
     unsigned kt = 0, slot = 0, sphase = 0, g = 0;
     for (;;) {
+        tc_stamp(trace, g, 2);                                   // trace: about to wait for the stage
         bar_wait(full0 + slot * 8, sphase);
+        tc_stamp(trace, g, 3);                                   // trace: stage has landed
         const unsigned info = s.info[slot];
         if (info & TC_INFO_STOP) break;
         const unsigned ab = info & TC_INFO_AB, cnt = info >> TC_INFO_CNT_SHIFT;
@@ -506,16 +512,13 @@ __device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem, cons
         for (unsigned u = 0; u < cnt; ++u, ++g) {
             const unsigned h = g & 1u;
             const uint64_t da = tc_smem_desc(sBase + slot * TC_STAGE_BYTES + u * TC_SEMB_BYTES, TC_SBLK * 16);
+            tc_stamp(trace, g, 6);                               // trace: about to wait for the TMEM buffer
             bar_wait(tempty0 + h * 8, ((g >> 1) & 1u) ^ 1u);     // epilogue has read this buffer's previous step
             tc_fence_after();
             tc_stamp(trace, g, 0);
             if (tc_elect_one()) {
                 tc_mma(tmem + h * 256u, da, db);
                 tc_commit(tfull0 + h * 8);
-                if (u + 1 == cnt) {
-                    tc_commit(empty0 + slot * 8);
-                    if (info & TC_INFO_LAST) tc_commit(rempty0 + ab * 8);
-                }
             }
             __syncwarp();
             tc_stamp(trace, g, 1);
@@ -822,7 +825,8 @@ within_tc_kernel(const WithinTcArgs p)
         // with the reference arithmetic at the end of the item (resolve()).
         constexpr int kFlagCap = TC_QCAP * 2;                  // (step, ballot) pairs in this warp's ring space
         uint2 *flags = reinterpret_cast<uint2 *>(s.sQ + warp * TC_QCAP);
-        unsigned g = 0, kt = 0, nCand = 0;
+        unsigned g = 0, kt = 0, nCand = 0, slot = 0;
+        const bool freesStages = warp == TC_STAGE_FREE_WARP;   // this warp hands finished stages back to the TMA warp
 
         TC_FOR_ITEMS(w, geo) {
             TcItem it;
@@ -886,6 +890,10 @@ within_tc_kernel(const WithinTcArgs p)
                 uint32_t r[32], gb[8];
                 bool cand;
                 ep.load_step(g, r, gb, cand, geo.trace);
+                if (freesStages && ((sb - it.sb0) % TC_SPS == TC_SPS - 1 || sb + 1 == it.sb1)) {
+                    if (lane == 0) bar_arrive(ep.empty0 + slot * 8);   // tfull seen: the stage's MMAs are done
+                    if (++slot == TC_STAGES) slot = 0;
+                }
                 unsigned bal = __ballot_sync(NDA_FULL_MASK, cand);
                 if (bal) {
                     // is the largest D of a flagged lane above the SURE threshold?  Then the atom is within

@@ -29,6 +29,8 @@ torch.cuda.synchronize()
 tr = np.zeros(256 * 32, dtype=np.int64)
 _capi.check(lib.nda_debug_tc_trace(tr.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong))))
 tr = tr.reshape(256, 32)
+if os.path.isdir("gpurun_out"):
+    np.save("gpurun_out/trace_raw_%s.npy" % os.environ.get("TRACE_TAG", "x"), tr)
 t0 = tr[tr > 0].min()
 names = {0: "mma.pass", 1: "mma.done", 4: "e0.see", 5: "e0.ld", 8: "e15.see", 9: "e15.ld"}
 cols = sorted(names)
@@ -61,3 +63,13 @@ x = tr[32:250, 0] - last[:218]
 print("last warp loaded step g -> MMA warp gets the buffer for g+2: mean %.0f  median %.0f  min %d" % (x.mean(), np.median(x), x.min()))
 x = first - tr[30:250, 1]
 print("MMA committed -> first warp has loaded: mean %.0f  median %.0f" % (x.mean(), np.median(x)))
+
+# where the MMA warp spends its step: stage wait (first block of a stage only), TMEM-buffer wait, issue
+sw = tr[20:250, 3] - tr[20:250, 2]
+has = tr[20:250, 2] > 0
+print("MMA warp, steps that open a stage (%d of %d): wait for the stage  mean %.0f  median %.0f  max %d" %
+      (has.sum(), has.size, sw[has].mean(), np.median(sw[has]), sw[has].max()))
+bw = tr[20:250, 0] - tr[20:250, 6]
+print("MMA warp: wait for the TMEM buffer (incl. fence)                 mean %.0f  median %.0f  min %d  max %d" % (bw.mean(), np.median(bw), bw.min(), bw.max()))
+ov = tr[21:250, 6] - tr[20:249, 1]
+print("MMA warp: committed step g -> at the buffer wait of step g+1     mean %.0f  median %.0f  min %d  max %d" % (ov.mean(), np.median(ov), ov.min(), ov.max()))
