@@ -104,7 +104,9 @@ struct Ctx {
     // the tail of chunk k's.  ctl: [0..1] work counter (u32 x2), stats u64 x2 at +16.
     struct Lane { DevBuf packA, packB, packAw, packBw, fp, maxAbs, ctl, embA, embB, thrDot; cudaStream_t stream = nullptr; };
     Lane lane[2];
-    cudaEvent_t evSetup = nullptr, evLaneJoin = nullptr;
+    cudaEvent_t evSetup = nullptr, evLaneJoin = nullptr, evSetupCopy = nullptr;
+    void *setupStage = nullptr;                   // pinned staging for the small per-call arrays (cell, selections)
+    size_t setupCap = 0;
     DevBuf raw[2][2];                             // [array][double buffer] raw coordinate chunks
     DevBuf cell, idx1, idx2, gid, counts, bits, sum;
     std::vector<float> hostCell;                  // cell edges read back for the filter choice (device API)
@@ -173,6 +175,7 @@ static int ctx_get(Ctx **out)
         CK(cudaStreamCreateWithFlags(&c.lane[1].stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c.evSetup, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c.evLaneJoin, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.evSetupCopy, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c.copyStream2, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming));
@@ -819,6 +822,34 @@ static bool host_ptr_is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
+// The small per-call arrays (cell edges, selections, group ids) go host -> device on the COPY stream,
+// ahead of the first bulk chunk, from our own pinned staging.  On the compute stream they would sit in
+// another channel of the same copy engine: when the caller's array is pinned (a true async DMA) the
+// engine keeps serving the copy stream's channel while it has ready work, and the 12 KB of cell edges
+// waited for TWO bulk chunks (~0.9 ms) -- with it the first chunk's kernels (seen in bench.py).
+struct SetupItem { void *dst; const void *src; size_t bytes; };
+
+static int upload_setup(Ctx &c, const SetupItem *items, int n)
+{
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += (items[i].bytes + 255) & ~(size_t)255;
+    if (total > c.setupCap) {
+        if (c.setupStage) { cudaFreeHost(c.setupStage); c.setupStage = nullptr; c.setupCap = 0; }
+        CK(cudaMallocHost(&c.setupStage, total + total / 2 + 4096));
+        c.setupCap = total + total / 2 + 4096;
+    }
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!items[i].bytes) continue;
+        char *h = static_cast<char *>(c.setupStage) + off;
+        memcpy(h, items[i].src, items[i].bytes);
+        CK(cudaMemcpyAsync(items[i].dst, h, items[i].bytes, cudaMemcpyHostToDevice, c.copyStream));
+        off += (items[i].bytes + 255) & ~(size_t)255;
+    }
+    CK(cudaEventRecord(c.evSetupCopy, c.copyStream));
+    return NDA_OK;
+}
+
 struct UploadArray {
     const float *host = nullptr;
     int nRows = 0;                       // rows uploaded (after the row plan)
@@ -1238,12 +1269,17 @@ int nda_get_radial_nbr_counts(const float *sel1, int n1, const float *sel2, int 
         CK(c->cell.reserve((size_t)nF * 12));
         CK(cudaMemsetAsync(c->counts.p, 0, H * 8, st));
         CK(reset_stats(*c, st));
-        CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
         if (groupId) {
             for (int i = 0; i < n2; ++i)
                 if (groupId[i] < 0 || groupId[i] >= nGroups) return fail(NDA_ERR_ARG, "groupId[%d] = %d outside [0, %d)", i, groupId[i], nGroups);
             CK(c->gid.reserve((size_t)n2 * 4));
-            CK(cudaMemcpyAsync(c->gid.p, groupId, (size_t)n2 * 4, cudaMemcpyHostToDevice, st));
+        }
+        {
+            const SetupItem items[2] = {{c->cell.p, cellDims, (size_t)nF * 12},
+                                        {groupId ? c->gid.p : nullptr, groupId, groupId ? (size_t)n2 * 4 : 0}};
+            rc = upload_setup(*c, items, 2);
+            if (rc) return rc;
+            CK(cudaStreamWaitEvent(st, c->evSetupCopy, 0));
         }
         // frame chunks: the upload of chunk k+1 overlaps pack + kernel of chunk k
         Uploader up(*c, nF, fb, fe);
@@ -1311,7 +1347,12 @@ int nda_get_distances_sum(const float *sel1, int n1, const float *sel2, int n2, 
     CK(c->sum.reserve(M * 8));
     CK(c->cell.reserve((size_t)nF * 12));
     CK(cudaMemsetAsync(c->sum.p, 0, M * 8, st));
-    CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
+    {
+        const SetupItem items[1] = {{c->cell.p, cellDims, (size_t)nF * 12}};
+        rc = upload_setup(*c, items, 1);
+        if (rc) return rc;
+        CK(cudaStreamWaitEvent(st, c->evSetupCopy, 0));
+    }
     Uploader up(*c, nF, fb, fe);
     up.add(sel1, n1);
     if (!sameSel) up.add(sel2, n2);
@@ -1407,21 +1448,26 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
     if (rc) return rc;
     const int nChunks = up.nChunks;
     ht.mark("plan");
+    CK(c->cell.reserve((size_t)nF * 12));
+    CK(c->idx1.reserve((size_t)std::max(refSize, 1) * 4));
+    CK(c->idx2.reserve((size_t)outSelSize * 4));
+    {                                                       // ~60 KB on the copy stream, then the first chunk
+        const SetupItem items[3] = {{c->cell.p, cellDims, (size_t)nF * 12},
+                                    {c->idx1.p, ref2.data(), (size_t)refSize * 4},
+                                    {c->idx2.p, out2.data(), (size_t)outSelSize * 4}};
+        rc = upload_setup(*c, items, 3);
+        if (rc) return rc;
+    }
     rc = up.issue(0);                                       // the link is the bottleneck: start it first
     if (rc) return rc;
     ht.mark("issue0");
 
-    CK(c->cell.reserve((size_t)nF * 12));
-    CK(c->idx1.reserve((size_t)std::max(refSize, 1) * 4));
-    CK(c->idx2.reserve((size_t)outSelSize * 4));
     CK(c->bits.reserve((size_t)nFc * words * 4));
     CK(c->pinned_reserve((size_t)nFc * words * 4));
     uint32_t *hbits = reinterpret_cast<uint32_t *>(c->pinned);
 
     CK(reset_stats(*c, st));
-    CK(cudaMemcpyAsync(c->cell.p, cellDims, (size_t)nF * 12, cudaMemcpyHostToDevice, st));
-    if (refSize) CK(cudaMemcpyAsync(c->idx1.p, ref2.data(), (size_t)refSize * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->idx2.p, out2.data(), (size_t)outSelSize * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamWaitEvent(st, c->evSetupCopy, 0));
     CK(cudaEventRecord(c->ev0, st));
 
     auto scatter = [&](int k) {                             // host: set the 1s of chunk k
@@ -1457,13 +1503,24 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
         if (rc) return rc;
         rc = up.release(k, ls);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(hbits + (size_t)(f0 - fb) * words, c->bits.as<unsigned>() + (size_t)(f0 - fb) * words,
-                           (size_t)wc * words * 4, cudaMemcpyDeviceToHost, ls));
+        static const bool d2hEngine = getenv("NDA_D2H_COPY_ENGINE") != nullptr;   // A/B switch: the old way
+        if (d2hEngine) {
+            CK(cudaMemcpyAsync(hbits + (size_t)(f0 - fb) * words, c->bits.as<unsigned>() + (size_t)(f0 - fb) * words,
+                               (size_t)wc * words * 4, cudaMemcpyDeviceToHost, ls));
+        } else {                                             // SMs write the pinned buffer: no copy-engine queueing
+            const size_t nW = (size_t)wc * words;
+            copy_words_kernel<<<(unsigned)std::min<size_t>((nW + 255) / 256, 296), 256, 0, ls>>>(
+                c->bits.as<unsigned>() + (size_t)(f0 - fb) * words, hbits + (size_t)(f0 - fb) * words, nW);
+            LAUNCHED();
+        }
         CK(cudaEventRecord(c->evBits[buf], ls));
         if (k + 1 < nChunks) { rc = up.issue(k + 1); if (rc) return rc; }   // host gathers k+1 while the GPU works on k
+        ht.mark("enq");
         if (k > 0) {                                         // ... and scatters chunk k-1
             CK(cudaEventSynchronize(c->evBits[buf ^ 1]));
+            ht.mark("wait");
             scatter(k - 1);
+            ht.mark("scat");
         }
     }
     CK(cudaEventRecord(c->evLaneJoin, c->lane[1].stream));
