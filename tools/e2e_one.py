@@ -9,7 +9,8 @@ from namdanalyzer_b200.lib import pylibFuncs as plf
 nF = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 c = synth.config2(n_frames=nF)
-xyz = torch.from_numpy(c["allAtoms"]).pin_memory().numpy()
+flags0 = sys.argv[3] if len(sys.argv) > 3 else ""
+xyz = c["allAtoms"] if "u" in flags0 else torch.from_numpy(c["allAtoms"]).pin_memory().numpy()   # u: pageable input
 out = np.zeros(xyz.shape[:2], np.int32)
 flags = sys.argv[3] if len(sys.argv) > 3 else ""     # emulate bench.py conditions: p d s r c
 if "p" in flags:
