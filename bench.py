@@ -362,8 +362,15 @@ def run_ours(args, rank, world, local_rank):
         t_ach = pairs_step * 32.0 / (k_ms * 1e-3) / 1e12
         roofline = dict(common, bound="tensor", achieved=t_ach, peak=tpeak, unit="TFLOP/s", frac=t_ach / tpeak,
                         flop_per_pair=32.0, peak_source=tsrc,
-                        note="tcgen05.mma M=128 N=64 K=16 (6 of 16 K slots carry the embedding, 2 the threshold): the MMAs are "
-                             "operand-fetch bound and the kernel is bound by the TMEM hand-over and the epilogue, see DESIGN.md 5.7",
+                        note="one tcgen05.mma M=128 N=256 K=16 per 32768 pairs (12 of the 16 K slots carry the embedding, 2 the "
+                             "threshold); every accumulator is read back exactly once, so the kernel is bound by the TMEM "
+                             "hand-over (2 buffers of 256 columns) and the epilogue's ALU work, not by MMA rate: see DESIGN.md 5.7",
+                        tmem_cells_per_clk_per_sm={
+                            "achieved": pairs_step / (k_ms * 1e-3) / (torch.cuda.get_device_properties(dev).multi_processor_count
+                                                                      * clocks["sm_mhz"] * 1e6)
+                            if (clocks and clocks.get("sm_mhz")) else None,
+                            "mma_write_peak": 256.0, "tmem_read_peak_measured": 230.0,
+                            "how": "tools/tmem_ld_rate.cu (16 warps, tcgen05.ld 32x32b.x32.pack::16b) on B200"},
                         fp32_equivalent=fp32_view)
     else:
         roofline = dict(common, bound="fp32", **{k: fp32_view[k] for k in ("achieved", "peak", "unit", "frac", "frac_of_nominal",
