@@ -573,6 +573,20 @@ struct TcEpi {
     }
     // step g: wait for TMEM buffer g & 1, load 64 accumulators, hand the buffer back to the MMA warp, reduce.
     // cand = this lane's streamed atom has at least one candidate among the warp's 64 resident atoms
+    // within: the same hand-over, reduced with MAX instead of AND -- one chain gives both answers the loop
+    // needs: max D >= 0 (a candidate among the 64) and max D >= sureDelta (certainly within).  A NaN
+    // accumulator (NaN coordinates) is ignored by the maximum, as it must be: such a pair is never within.
+    __device__ __forceinline__ void load_step_max(unsigned g, __half &mx, const long long *trace = nullptr) const
+    {
+        uint32_t r[32], gb[8];
+        bool cand;
+        load_step<false>(g, r, gb, cand, trace);
+        __half2 m = __hmax2(*reinterpret_cast<const __half2 *>(&r[0]), *reinterpret_cast<const __half2 *>(&r[1]));
+        #pragma unroll
+        for (int i = 2; i < 32; ++i) m = __hmax2(m, *reinterpret_cast<const __half2 *>(&r[i]));
+        mx = __hmax(__low2half(m), __high2half(m));
+    }
+    template <bool kReduce = true>
     __device__ __forceinline__ void load_step(unsigned g, uint32_t (&r)[32], uint32_t (&gb)[8], bool &cand,
                                               const long long *trace = nullptr) const
     {
@@ -602,10 +616,14 @@ struct TcEpi {
         for (int b = 0; b < 8; ++b) gb[b] = r[4 * b];          // floor experiment: no reduction, never a candidate
         cand = (r[0] == 0x12345678u) && (r[31] == 0x9abcdef0u);
 #else
-        #pragma unroll
-        for (int b = 0; b < 8; ++b) gb[b] = r[4 * b] & r[4 * b + 1] & r[4 * b + 2] & r[4 * b + 3];
-        const uint32_t top = (gb[0] & gb[1] & gb[2]) & (gb[3] & gb[4] & gb[5]) & (gb[6] & gb[7]);
-        cand = (top & TC_SIGNS) != TC_SIGNS;
+        if (kReduce) {
+            #pragma unroll
+            for (int b = 0; b < 8; ++b) gb[b] = r[4 * b] & r[4 * b + 1] & r[4 * b + 2] & r[4 * b + 3];
+            const uint32_t top = (gb[0] & gb[1] & gb[2]) & (gb[3] & gb[4] & gb[5]) & (gb[6] & gb[7]);
+            cand = (top & TC_SIGNS) != TC_SIGNS;
+        } else {
+            cand = false;
+        }
 #endif
     }
 };
@@ -887,9 +905,15 @@ within_tc_kernel(const WithinTcArgs p)
                 __syncwarp();
             };
             for (int sb = it.sb0; sb < it.sb1; ++sb, ++g) {
+#if defined(NDA_TC_EXPERIMENT) || defined(NDA_TC_WITHIN_AND)
                 uint32_t r[32], gb[8];
                 bool cand;
                 ep.load_step(g, r, gb, cand, geo.trace);
+#else
+                __half mx;
+                ep.load_step_max(g, mx, geo.trace);
+                const bool cand = __hge(mx, __ushort_as_half((unsigned short)0));
+#endif
                 if (freesStages && ((sb - it.sb0) % TC_SPS == TC_SPS - 1 || sb + 1 == it.sb1)) {
                     if (lane == 0) bar_arrive(ep.empty0 + slot * 8);   // tfull seen: the stage's MMAs are done
                     if (++slot == TC_STAGES) slot = 0;
@@ -897,10 +921,13 @@ within_tc_kernel(const WithinTcArgs p)
                 unsigned bal = __ballot_sync(NDA_FULL_MASK, cand);
                 if (bal) {
                     // is the largest D of a flagged lane above the SURE threshold?  Then the atom is within
+#if defined(NDA_TC_EXPERIMENT) || defined(NDA_TC_WITHIN_AND)
                     __half2 m = __hmax2(*reinterpret_cast<const __half2 *>(&r[0]), *reinterpret_cast<const __half2 *>(&r[1]));
                     #pragma unroll
                     for (int i = 2; i < 32; ++i) m = __hmax2(m, *reinterpret_cast<const __half2 *>(&r[i]));
-                    const bool sure = __hge(__hmax(__low2half(m), __high2half(m)), sureH);
+                    const __half mx = __hmax(__low2half(m), __high2half(m));
+#endif
+                    const bool sure = __hge(mx, sureH);
                     const unsigned sbal = __ballot_sync(NDA_FULL_MASK, sure) & bal;
                     const int word = sb * (TC_SBLK / 32) + ep.q;
                     if (sbal && lane == 0 && word < p.wordsPerFrame) atomicOr(&bitsF[word], sbal);
