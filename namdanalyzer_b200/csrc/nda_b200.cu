@@ -337,13 +337,13 @@ static int launch_embed(cudaStream_t st, const float4 *packed, int nPad, int nFc
 
 // streamed blocks per work item: >= 16 items per CTA for the static round-robin to balance (the sameSel
 // workload is triangular), but an item stays >= minBlocks steps so that the resident chunk is amortised
-static void tc_chunking(TcGeom &g, int numSMs, long long framesInPass, int minBlocks)
+static void tc_chunking(TcGeom &g, int numSMs, long long framesInPass, int minBlocks, int maxBlocks = 1024)
 {
     const long long target = 16LL * numSMs;
     const long long rows = std::max<long long>(1, framesInPass * g.nRChunks);
     const long long chunksWanted = std::max<long long>(1, (target + rows - 1) / rows);
     long long cs = (g.nSBlocks + chunksWanted - 1) / chunksWanted;
-    cs = std::max<long long>(minBlocks, std::min<long long>(1024, cs));
+    cs = std::min<long long>(maxBlocks, std::max<long long>(minBlocks, std::min<long long>(1024, cs)));
     g.chunkS = (int)std::min<long long>(cs, std::max(1, g.nSBlocks));
     g.nSChunks = (g.nSBlocks + g.chunkS - 1) / g.chunkS;
 }
@@ -464,7 +464,7 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
             g.trace = c.sum.as<long long>();
         }
     }
-    tc_chunking(g, c.numSMs, pass, 16);
+    tc_chunking(g, c.numSMs, pass, 16, TC_WITHIN_MAX_STEPS);   // a warp records at most one (step, lanes) entry per step
     a.wordsPerFrame = words;
     a.d2 = d2;
     a.literal = g_within_pure.load() ? 0 : 1;

@@ -46,6 +46,7 @@
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_MMA_WARP  = TC_EPI_WARPS;                     // warp 16 issues the MMAs
 constexpr int TC_TMA_WARP  = TC_EPI_WARPS + 1;                 // warp 17 issues the TMA copies
+constexpr int TC_WITHIN_MAX_STEPS = 128;   // within: streamed blocks per work item <= (step, lanes) records a warp can hold (TC_QCAP * 2)
 constexpr int TC_STAGE_FREE_WARP = 2;      // within kernel: the epilogue warp that releases a stage once its MMAs are done
 constexpr int TC_THREADS   = (TC_EPI_WARPS + 2) * 32;          // 576
 constexpr int TC_SBLK      = 128;                              // streamed atoms per step (MMA M)
@@ -60,6 +61,7 @@ constexpr int TC_RORIG_BYTES = TC_RBLK * 16;                   // 4 KB
 constexpr int TC_RBUF_BYTES = TC_REMB_BYTES + TC_RORIG_BYTES;  // resident chunk buffer (12 KB)
 constexpr int TC_STAGES    = 4;                                // stages in flight (8 streamed blocks)
 constexpr int TC_QCAP      = 64;                               // per-warp candidate ring, 16-byte entries
+static_assert(TC_WITHIN_MAX_STEPS * 8 <= TC_QCAP * 16, "within flag list must fit in the warp's ring space");
 // instruction descriptor: D = F16 (bits 4-5 = 0), A = B = F16, both K-major, N = 256 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
 constexpr uint32_t TC_IDESC = (0u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -576,22 +578,29 @@ struct TcEpi {
     // within: the same hand-over, reduced with MAX instead of AND -- one chain gives both answers the loop
     // needs: max D >= 0 (a candidate among the 64) and max D >= sureDelta (certainly within).  A NaN
     // accumulator (NaN coordinates) is ignored by the maximum, as it must be: such a pair is never within.
-    __device__ __forceinline__ void load_step_max(unsigned g, __half &mx, const long long *trace = nullptr) const
+    // (h, parity) = (g & 1, (g >> 1) & 1) are passed separately so that an unrolled caller can make the
+    // buffer index a compile-time constant and carry the parity in a register
+    __device__ __forceinline__ void load_step_max(unsigned h, unsigned parity, unsigned g, __half &mx,
+                                                  const long long *trace = nullptr) const
     {
         uint32_t r[32], gb[8];
         bool cand;
-        load_step<false>(g, r, gb, cand, trace);
+        load_step_hp<false>(h, parity, g, r, gb, cand, trace);
         __half2 m = __hmax2(*reinterpret_cast<const __half2 *>(&r[0]), *reinterpret_cast<const __half2 *>(&r[1]));
         #pragma unroll
         for (int i = 2; i < 32; ++i) m = __hmax2(m, *reinterpret_cast<const __half2 *>(&r[i]));
         mx = __hmax(__low2half(m), __high2half(m));
     }
-    template <bool kReduce = true>
     __device__ __forceinline__ void load_step(unsigned g, uint32_t (&r)[32], uint32_t (&gb)[8], bool &cand,
                                               const long long *trace = nullptr) const
     {
-        const unsigned h = g & 1u;
-        bar_wait(tfull0 + h * 8, (g >> 1) & 1u);
+        load_step_hp<true>(g & 1u, (g >> 1) & 1u, g, r, gb, cand, trace);
+    }
+    template <bool kReduce>
+    __device__ __forceinline__ void load_step_hp(unsigned h, unsigned parity, unsigned g, uint32_t (&r)[32], uint32_t (&gb)[8],
+                                                 bool &cand, const long long *trace = nullptr) const
+    {
+        bar_wait(tfull0 + h * 8, parity);
         tc_fence_after();
 #ifdef NDA_TC_TRACE_BUILD
         if (trace && (cq * 4 + q == 0 || cq * 4 + q == 15)) tc_stamp(trace, g, cq * 4 + q == 0 ? 4 : 8);
@@ -841,7 +850,7 @@ within_tc_kernel(const WithinTcArgs p)
         // the atom is within, OR its bit in -- and only RECORDS the rest (step, lanes): no data-dependent
         // work, so the 16 warps that share a TMEM buffer stay in step.  The recorded steps are resolved
         // with the reference arithmetic at the end of the item (resolve()).
-        constexpr int kFlagCap = TC_QCAP * 2;                  // (step, ballot) pairs in this warp's ring space
+        constexpr int kFlagCap = TC_WITHIN_MAX_STEPS;          // (step, ballot) pairs in this warp's ring space
         uint2 *flags = reinterpret_cast<uint2 *>(s.sQ + warp * TC_QCAP);
         unsigned g = 0, kt = 0, nCand = 0, slot = 0;
         const bool freesStages = warp == TC_STAGE_FREE_WARP;   // this warp hands finished stages back to the TMA warp
@@ -904,14 +913,17 @@ within_tc_kernel(const WithinTcArgs p)
                 nf = 0;
                 __syncwarp();
             };
-            for (int sb = it.sb0; sb < it.sb1; ++sb, ++g) {
+            // One step of the main loop.  Every call site passes a literal h (= g & 1, the TMEM buffer), so
+            // barrier and TMEM addresses are immediates; the barrier parity (g >> 1) & 1 is carried in `par`.
+            unsigned par = (g >> 1) & 1u;
+            auto step = [&](const unsigned h, const int sb, const unsigned gg) {
 #if defined(NDA_TC_EXPERIMENT) || defined(NDA_TC_WITHIN_AND)
                 uint32_t r[32], gb[8];
                 bool cand;
-                ep.load_step(g, r, gb, cand, geo.trace);
+                ep.load_step_hp<true>(h, par, gg, r, gb, cand, geo.trace);
 #else
                 __half mx;
-                ep.load_step_max(g, mx, geo.trace);
+                ep.load_step_max(h, par, gg, mx, geo.trace);
                 const bool cand = __hge(mx, __ushort_as_half((unsigned short)0));
 #endif
                 if (freesStages && ((sb - it.sb0) % TC_SPS == TC_SPS - 1 || sb + 1 == it.sb1)) {
@@ -933,13 +945,23 @@ within_tc_kernel(const WithinTcArgs p)
                     if (sbal && lane == 0 && word < p.wordsPerFrame) atomicOr(&bitsF[word], sbal);
                     bal &= ~sbal;
                     if (bal) {
+                        // an item has at most kFlagCap steps (the host caps chunkS), so the list cannot overflow
+                        if (nf == kFlagCap) __trap();
                         if (lane == 0) flags[nf] = make_uint2((unsigned)sb, bal);
+                        ++nf;
                         // resolve() will need these 32 atoms' original coordinates: start pulling them in now
                         asm volatile("prefetch.global.L2 [%0];" :: "l"(&Aglob[sb * TC_SBLK + ep.q * 32 + lane]));
-                        if (++nf == kFlagCap) resolve();
                     }
                 }
+            };
+            int sb = it.sb0;
+            if ((g & 1u) && sb < it.sb1) { step(1u, sb, g); ++sb; ++g; par ^= 1u; }
+            for (; sb + 1 < it.sb1; sb += 2, g += 2) {
+                step(0u, sb, g);
+                step(1u, sb + 1, g + 1);
+                par ^= 1u;
             }
+            if (sb < it.sb1) { step(0u, sb, g); ++g; }
             if (nf) resolve();
             __syncwarp();
             if (lane == 0) bar_arrive(ep.rempty0 + ab * 8);    // done with this item's resident data
