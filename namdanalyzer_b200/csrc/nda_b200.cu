@@ -265,7 +265,7 @@ static bool tc_frames_eligible(const float *cell, int fb, int fe, double T, doub
 {
     const double k = 0.15915494309189535;
     {
-        const double padded = (double)round_up(nStream, 128) * (double)round_up(nResident, 256);
+        const double padded = (double)round_up(nStream, 256) * (double)round_up(nResident, 256);
         if (padded > 4.0 * (double)nStream * (double)nResident && !getenv("NDA_TC_ALLOW_PADDING")) return false;
     }
     if (const char *e = getenv("NDA_TC_MAX_FRACTION")) { const double v = atof(e); if (v > 0.0) maxFraction = v; }
@@ -344,8 +344,11 @@ static void tc_chunking(TcGeom &g, int numSMs, long long framesInPass, int minBl
     const long long chunksWanted = std::max<long long>(1, (target + rows - 1) / rows);
     long long cs = (g.nSBlocks + chunksWanted - 1) / chunksWanted;
     cs = std::min<long long>(maxBlocks, std::max<long long>(minBlocks, std::min<long long>(1024, cs)));
-    g.chunkS = (int)std::min<long long>(cs, std::max(1, g.nSBlocks));
+    cs = (cs + 1) & ~1LL;                                   // even, like nSBlocks: every work item is a whole number of
+                                                            // two-block stages, so the step parity is 0 at every item start
+    g.chunkS = (int)std::min<long long>(cs, std::max(2, g.nSBlocks));
     g.nSChunks = (g.nSBlocks + g.chunkS - 1) / g.chunkS;
+    if ((g.nSBlocks | g.chunkS) & 1) { g.chunkS = 0; g.nSChunks = 0; }   // cannot happen; launches nothing rather than mis-stepping
 }
 
 static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, int n1, const float *d_sel2, int n2,
@@ -362,7 +365,7 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
         return fail(NDA_ERR_ARG, "nGroups*outSize = %zu histogram cells do not fit in shared memory (max %zu)", H, budget / 4);
     const size_t smem = base + (size_t)copies * H * 4;
     // sel1 is streamed in 128-atom blocks (TMEM lanes), sel2 is resident in 256-atom chunks (columns)
-    const int n1Pad = round_up(n1, sameSel ? TC_RBLK : TC_SBLK);
+    const int n1Pad = round_up(n1, TC_SPS * TC_SBLK);          // whole two-block stages (= TC_RBLK)
     const int n2Pad = sameSel ? n1Pad : round_up(n2, TC_RBLK);
     const size_t bytesPerFrame = (size_t)n1Pad * (16 + 32) + (sameSel ? (size_t)n1Pad * 32 : (size_t)n2Pad * (16 + 32));
     const int pass = frames_per_pass(bytesPerFrame, fe - fb);
@@ -380,7 +383,7 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
     TcGeom &g = a.g;
     g.n1 = n1; g.n1Pad = n1Pad; g.n2 = n2; g.n2Pad = n2Pad;
     g.nRChunks = (n2 + TC_RBLK - 1) / TC_RBLK;
-    g.nSBlocks = (n1 + TC_SBLK - 1) / TC_SBLK;
+    g.nSBlocks = n1Pad / TC_SBLK;                              // even; a trailing all-padding block has no candidates
     g.sameSel = sameSel ? 1 : 0;
     g.stats = stats;
     g.origInStage = 1;
@@ -435,7 +438,7 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
 {
     const int words = (outSize + 31) / 32;
     // outSel is streamed in 128-atom blocks (TMEM lanes), refSel is resident in 256-atom chunks (columns)
-    const int nAPad = round_up(outSize, TC_SBLK);
+    const int nAPad = round_up(outSize, TC_SPS * TC_SBLK);     // whole two-block stages
     const int nBPad = round_up(refSize, TC_RBLK);
     const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * (16 + 32);
     const int pass = frames_per_pass(bytesPerFrame, fe - fb);
@@ -452,7 +455,7 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
     TcGeom &g = a.g;
     g.n1 = outSize; g.n1Pad = nAPad; g.n2 = refSize; g.n2Pad = nBPad;
     g.nRChunks = (refSize + TC_RBLK - 1) / TC_RBLK;
-    g.nSBlocks = (outSize + TC_SBLK - 1) / TC_SBLK;
+    g.nSBlocks = nAPad / TC_SBLK;                              // even; a trailing all-padding block has no candidates
     g.sameSel = 0;
     g.stats = stats;
     g.origInStage = 0;

@@ -46,6 +46,12 @@
 constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_MMA_WARP  = TC_EPI_WARPS;                     // warp 16 issues the MMAs
 constexpr int TC_TMA_WARP  = TC_EPI_WARPS + 1;                 // warp 17 issues the TMA copies
+// the grouped RDF (residue-wise water density) is dominated by its push / drain code next to the protein:
+// two inlined copies of it measured 0.8 % slower than one, so only the ungrouped kernel is unrolled
+#ifndef NDA_TC_RDF_UNROLL_GROUPED
+#define NDA_TC_RDF_UNROLL_GROUPED 0
+#endif
+constexpr bool TC_RDF_UNROLL_GROUPED = NDA_TC_RDF_UNROLL_GROUPED != 0;
 constexpr int TC_WITHIN_MAX_STEPS = 128;   // within: streamed blocks per work item <= (step, lanes) records a warp can hold (TC_QCAP * 2)
 constexpr int TC_STAGE_FREE_WARP = 2;      // within kernel: the epilogue warp that releases a stage once its MMAs are done
 constexpr int TC_THREADS   = (TC_EPI_WARPS + 2) * 32;          // 576
@@ -737,8 +743,10 @@ rdf_tc_kernel(const RdfTcArgs p)
             // One step.  The unrolled loop below passes a literal h (= g & 1, the TMEM buffer) so that barrier and
             // TMEM addresses are immediates; the barrier parity (g >> 1) & 1 is carried in `par` (as in the within kernel).
             unsigned par = (g >> 1) & 1u;
+            // Items are whole two-block stages (the host makes nSBlocks and chunkS even), so g is even at every
+            // item start and block u of a stage is always TMEM buffer u: h below is both.
             auto step = [&](const unsigned h, const int sb, const unsigned gg) {
-                const int u = (sb - it.sb0) % TC_SPS;              // block u of its stage
+                const int u = (int)h;                              // block u of its stage
                 uint32_t r[32], gb[8];
                 bool cand;
                 ep.load_step_hp<true>(h, par, gg, r, gb, cand, geo.trace);
@@ -798,27 +806,20 @@ rdf_tc_kernel(const RdfTcArgs p)
                         }
                     }
                 }
-                if (u == TC_SPS - 1 || sb + 1 == it.sb1) {         // last block of its stage
+                if (u == TC_SPS - 1) {                             // last block of its stage
                     __syncwarp();
                     if (lane == 0) bar_arrive(ep.empty0 + slot * 8);   // done with this stage's original coordinates
                     if (++slot == TC_STAGES) slot = 0;
                 }
             };
-            int sb = it.sb0;
-            if constexpr (!kGrouped) {
-                // sparse candidates (0.4 % of the pairs in range for a bulk-water RDF): the loop is dominated by
-                // the no-candidate path, unrolling by two saves its address arithmetic (+3.4 %)
-                if ((g & 1u) && sb < it.sb1) { step(1u, sb, g); ++sb; ++g; par ^= 1u; }
-                for (; sb + 1 < it.sb1; sb += 2, g += 2) {
+            if constexpr (TC_RDF_UNROLL_GROUPED || !kGrouped) {
+                for (int sb = it.sb0; sb < it.sb1; sb += 2, g += 2) {      // one stage per iteration
                     step(0u, sb, g);
                     step(1u, sb + 1, g + 1);
                     par ^= 1u;
                 }
-                if (sb < it.sb1) { step(0u, sb, g); ++g; }
             } else {
-                // residue-wise water density: steps next to the protein carry dozens of candidates, the push /
-                // drain code dominates and four inlined copies of it cost more than they save (-3.5 %)
-                for (; sb < it.sb1; ++sb, ++g) {
+                for (int sb = it.sb0; sb < it.sb1; ++sb, ++g) {
                     step(g & 1u, sb, g);
                     par ^= g & 1u;
                 }
@@ -948,7 +949,7 @@ within_tc_kernel(const WithinTcArgs p)
                 ep.load_step_max(h, par, gg, mx, geo.trace);
                 const bool cand = __hge(mx, __ushort_as_half((unsigned short)0));
 #endif
-                if (freesStages && ((sb - it.sb0) % TC_SPS == TC_SPS - 1 || sb + 1 == it.sb1)) {
+                if (h == 1u && freesStages) {                          // block 1 of a stage is always TMEM buffer 1 (see the RDF kernel)
                     if (lane == 0) bar_arrive(ep.empty0 + slot * 8);   // tfull seen: the stage's MMAs are done
                     if (++slot == TC_STAGES) slot = 0;
                 }
@@ -976,14 +977,11 @@ within_tc_kernel(const WithinTcArgs p)
                     }
                 }
             };
-            int sb = it.sb0;
-            if ((g & 1u) && sb < it.sb1) { step(1u, sb, g); ++sb; ++g; par ^= 1u; }
-            for (; sb + 1 < it.sb1; sb += 2, g += 2) {
+            for (int sb = it.sb0; sb < it.sb1; sb += 2, g += 2) {          // one stage per iteration
                 step(0u, sb, g);
                 step(1u, sb + 1, g + 1);
                 par ^= 1u;
             }
-            if (sb < it.sb1) { step(0u, sb, g); ++g; }
             if (nf) resolve();
             __syncwarp();
             if (lane == 0) bar_arrive(ep.rempty0 + ab * 8);    // done with this item's resident data
