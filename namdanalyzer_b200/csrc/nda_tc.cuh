@@ -545,12 +545,16 @@ constexpr unsigned TC_SIGNS = 0x80008000u;
 
 // bit k of (lo, hi) = column k is a candidate, evaluated only inside the 8-column groups (4 registers)
 // whose AND shows a clear sign bit
+template <bool kHaveGb>
 __device__ __forceinline__ void tc_mask64(const uint32_t (&r)[32], const uint32_t (&gb)[8], unsigned &lo, unsigned &hi)
 {
     lo = 0u; hi = 0u;
     #pragma unroll
     for (int b = 0; b < 8; ++b) {
-        if (__any_sync(NDA_FULL_MASK, (gb[b] & TC_SIGNS) != TC_SIGNS)) {
+        // kHaveGb = false: the main loop reduced with a flat AND of all 32 registers (16 LOP3 instead of 20)
+        // and the per-group AND is computed here, on the candidate path only
+        const uint32_t gbb = kHaveGb ? gb[b] : (r[4 * b] & r[4 * b + 1] & r[4 * b + 2] & r[4 * b + 3]);
+        if (__any_sync(NDA_FULL_MASK, (gbb & TC_SIGNS) != TC_SIGNS)) {
             unsigned m = 0u;
             #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -591,7 +595,7 @@ struct TcEpi {
     {
         uint32_t r[32], gb[8];
         bool cand;
-        load_step_hp<false>(h, parity, g, r, gb, cand, trace);
+        load_step_hp<0>(h, parity, g, r, gb, cand, trace);
         __half2 m = __hmax2(*reinterpret_cast<const __half2 *>(&r[0]), *reinterpret_cast<const __half2 *>(&r[1]));
         #pragma unroll
         for (int i = 2; i < 32; ++i) m = __hmax2(m, *reinterpret_cast<const __half2 *>(&r[i]));
@@ -600,9 +604,10 @@ struct TcEpi {
     __device__ __forceinline__ void load_step(unsigned g, uint32_t (&r)[32], uint32_t (&gb)[8], bool &cand,
                                               const long long *trace = nullptr) const
     {
-        load_step_hp<true>(g & 1u, (g >> 1) & 1u, g, r, gb, cand, trace);
+        load_step_hp<1>(g & 1u, (g >> 1) & 1u, g, r, gb, cand, trace);
     }
-    template <bool kReduce>
+    // kReduce: 0 none (the caller reduces), 1 per-8-column partial ANDs in gb + their AND, 2 flat AND (gb unused)
+    template <int kReduce>
     __device__ __forceinline__ void load_step_hp(unsigned h, unsigned parity, unsigned g, uint32_t (&r)[32], uint32_t (&gb)[8],
                                                  bool &cand, const long long *trace = nullptr) const
     {
@@ -631,10 +636,16 @@ struct TcEpi {
         for (int b = 0; b < 8; ++b) gb[b] = r[4 * b];          // floor experiment: no reduction, never a candidate
         cand = (r[0] == 0x12345678u) && (r[31] == 0x9abcdef0u);
 #else
-        if (kReduce) {
+        if (kReduce == 1) {
             #pragma unroll
             for (int b = 0; b < 8; ++b) gb[b] = r[4 * b] & r[4 * b + 1] & r[4 * b + 2] & r[4 * b + 3];
             const uint32_t top = (gb[0] & gb[1] & gb[2]) & (gb[3] & gb[4] & gb[5]) & (gb[6] & gb[7]);
+            cand = (top & TC_SIGNS) != TC_SIGNS;
+        } else if (kReduce == 2) {
+            uint32_t top = r[0] & r[1] & r[2];
+            #pragma unroll
+            for (int i = 3; i < 31; i += 2) top &= r[i] & r[i + 1];
+            top &= r[31];
             cand = (top & TC_SIGNS) != TC_SIGNS;
         } else {
             cand = false;
@@ -749,10 +760,12 @@ rdf_tc_kernel(const RdfTcArgs p)
                 const int u = (int)h;                              // block u of its stage
                 uint32_t r[32], gb[8];
                 bool cand;
-                ep.load_step_hp<true>(h, par, gg, r, gb, cand, geo.trace);
+                // sparse candidates (ungrouped): flat AND, partial ANDs recomputed on the rare candidate path (-1.2 %);
+                // grouped (residue-wise water density): the candidate path is the common one, keep the partials (+1 %)
+                ep.load_step_hp<kGrouped ? 1 : 2>(h, par, gg, r, gb, cand, geo.trace);
                 if (__any_sync(NDA_FULL_MASK, cand)) {
                     unsigned mlo, mhi;
-                    tc_mask64(r, gb, mlo, mhi);
+                    tc_mask64<kGrouped>(r, gb, mlo, mhi);
                     if (geo.sameSel) {                          // count a pair once: streamed index > resident index
                         const int d = (sb * TC_SBLK + ep.q * 32 + lane) - colBase;      // keep columns k < d
                         const unsigned long long keep = d <= 0 ? 0ull : (d >= 64 ? ~0ull : ((1ull << d) - 1ull));
@@ -943,7 +956,7 @@ within_tc_kernel(const WithinTcArgs p)
 #if defined(NDA_TC_EXPERIMENT) || defined(NDA_TC_WITHIN_AND)
                 uint32_t r[32], gb[8];
                 bool cand;
-                ep.load_step_hp<true>(h, par, gg, r, gb, cand, geo.trace);
+                ep.load_step_hp<1>(h, par, gg, r, gb, cand, geo.trace);
 #else
                 __half mx;
                 ep.load_step_max(h, par, gg, mx, geo.trace);
