@@ -195,6 +195,13 @@ static int ctx_get(Ctx **out)
             // gathering pageable rows is memory-bound host work: 16 threads reach ~50 GB/s on the 16-core
             // GPU hosts measured (8: 33 GB/s, more threads than cores: slower)
             int t = (int)std::max(1u, std::min(16u, hw));
+            // one process per GPU: the ranks of a node share its cores, and OpenMP teams that outnumber the cores
+            // spin against each other (2 ranks x 16 threads on 16 cores: 10x slower end to end, measured)
+            for (const char *name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE"}) {
+                const char *e = getenv(name);
+                const int ranks = e ? atoi(e) : 0;
+                if (ranks > 1) { t = std::max(1, std::min(t, (int)hw / ranks)); break; }
+            }
             if (const char *e = getenv("NDA_HOST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) t = v; }
             g_host_threads = t;
         }
