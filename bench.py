@@ -217,8 +217,36 @@ def workload_config(args, sample=None):
     return c
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run (and so allocate pinned host buffers) on the CPU socket the GPU hangs off.
+    With 8 ranks pulling 8 x 47 GB/s out of host memory, buffers on the far socket cost the end-to-end
+    number more than anything on the GPU side.  Best effort: returns a description or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not out:
+            return None
+        dom, rest = out.split(":", 1)
+        bus = "%s:%s" % (dom[-4:], rest)                       # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu_bus": bus, "numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------- our arm
 def run_ours(args, rank, world, local_rank):
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None     # before any host buffer exists
     import torch
     import torch.distributed as dist
     from namdanalyzer_b200 import synth, _capi
@@ -412,6 +440,7 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": roofline,
         "check": {"hits_resident": hits_dev, "hits_e2e": hits_e2e},
+        "numa_binding": numa,
         "filter": "tensor-core (tcgen05) periodic-embedding filter + strict FP32 re-evaluation" if tensor_path
                   else "packed-FP32 filter %d + strict FP32 re-evaluation" % filt,
     }
