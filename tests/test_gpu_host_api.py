@@ -199,3 +199,39 @@ def test_dcd_file_to_resident_trajectory(tmp_path):
     T = DCDFile(p).resident()
     want = port.within(c["allAtoms"], c["refSel"], c["outSel"], c["cellDims"], 3.0)
     assert np.array_equal(T.within(c["refSel"], c["outSel"], 3.0), want)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_upload_pipeline_chunk_boundaries(monkeypatch, pinned):
+    """The host entry points cut the frames into chunks (tapered tail); force many
+    small chunks on a small system so that every boundary, both staging buffers, the pinned (strided
+    DMA) and the pageable (gathered) upload and the per-chunk mask scatter are exercised, and compare
+    every frame with the oracle.  The second call with the same selections reuses the cached row plan,
+    the third one must not."""
+    import torch
+    from namdanalyzer_b200.lib import pylibFuncs as plf
+    c = synth.config2(n_frames=150, n_water=700)
+    xyz, cell, r, o = c["allAtoms"], c["cellDims"], c["refSel"], c["outSel"]
+    if pinned:
+        xyz = torch.from_numpy(xyz).pin_memory().numpy()
+        cell = torch.from_numpy(cell).pin_memory().numpy()
+    want = port.within(c["allAtoms"], r, o, c["cellDims"], 3.0)
+    for chunks in ("7", "3", "1"):
+        monkeypatch.setenv("NDA_WITHIN_CHUNKS", chunks)
+        for rep in range(2):
+            out = np.zeros(xyz.shape[:2], np.int32)
+            plf.py_getWithin(xyz, r, o, out, cell, 3.0)
+            assert np.array_equal(out, want), (chunks, rep)
+    o2 = np.ascontiguousarray(o[::2])                          # another selection: the cached plan must go
+    out = np.zeros(xyz.shape[:2], np.int32)
+    plf.py_getWithin(xyz, r, o2, out, cell, 3.0)
+    assert np.array_equal(out, port.within(c["allAtoms"], r, o2, c["cellDims"], 3.0))
+    # RDF and distances share the uploader
+    monkeypatch.setenv("NDA_UPLOAD_CHUNKS", "5")
+    w = np.ascontiguousarray(xyz[o[:300]])
+    pr = np.ascontiguousarray(xyz[r[:200]])
+    got = plf.py_getRadialNbrCounts(w, pr, cell, 0, 40, 0.1)
+    assert np.array_equal(got, port.rdf_counts(w, pr, c["cellDims"], 0, 40, 0.1))
+    d = plf.py_getDistancesSum(w[:5], pr, cell, 0)
+    dw = port.distances_sum(w[:5], pr, c["cellDims"], 0)
+    assert np.max(np.abs(d - dw) / np.maximum(dw, 1e-30)) < 1e-12
