@@ -231,8 +231,9 @@ static int launch_pack(Ctx &c, cudaStream_t st, const float *src, int nFtot, con
                        int nPad, int f0, int nFc, const int *gid, float4 *dst, unsigned *maxAbs,
                        const float *cell, float4 *dstW, int pairLayout = 0, __half *embA = nullptr)
 {
-    (void)c;
-    dim3 grid(nPad / 32, (nFc + 31) / 32);
+    const long long tiles = (long long)(nPad / 32) * ((nFc + 31) / 32);
+    if (tiles > 0x7fffffffLL) return fail(NDA_ERR_ARG, "internal: pack tile count overflows");
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)c.numSMs * 8));
     pack_kernel<<<grid, 256, 0, st>>>(src, nFtot, gather, n, nPad, f0, nFc, gid, dst, maxAbs, cell, dstW, pairLayout, embA);
     LAUNCHED();
     return NDA_OK;
