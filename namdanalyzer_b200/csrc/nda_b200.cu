@@ -233,7 +233,7 @@ static int launch_pack(Ctx &c, cudaStream_t st, const float *src, int nFtot, con
 {
     const long long tiles = (long long)(nPad / 32) * ((nFc + 31) / 32);
     if (tiles > 0x7fffffffLL) return fail(NDA_ERR_ARG, "internal: pack tile count overflows");
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)c.numSMs * 8));
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)c.numSMs * 5));
     pack_kernel<<<grid, 256, 0, st>>>(src, nFtot, gather, n, nPad, f0, nFc, gid, dst, maxAbs, cell, dstW, pairLayout, embA);
     LAUNCHED();
     return NDA_OK;
