@@ -356,6 +356,11 @@ static void tc_chunking(TcGeom &g, int numSMs, long long framesInPass, int minBl
                                                             // two-block stages, so the step parity is 0 at every item start
     g.chunkS = (int)std::min<long long>(cs, std::max(2, g.nSBlocks));
     g.nSChunks = (g.nSBlocks + g.chunkS - 1) / g.chunkS;
+    // spread the stages over the ranges evenly: 79 stages in 7 ranges = 2 x 12 + 5 x 11, not 6 x 12 + 7
+    // (with static round-robin scheduling a short last range is pure imbalance)
+    const int stages = g.nSBlocks / 2, base = stages / g.nSChunks, rem = stages % g.nSChunks;
+    g.chunkS = 2 * (base + (rem ? 1 : 0));
+    g.nBigChunks = rem ? rem : g.nSChunks;
     if ((g.nSBlocks | g.chunkS) & 1) { g.chunkS = 0; g.nSChunks = 0; }   // cannot happen; launches nothing rather than mis-stepping
 }
 

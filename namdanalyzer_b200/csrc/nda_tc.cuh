@@ -294,7 +294,8 @@ struct TcGeom {
     int n1, n1Pad, n2, n2Pad;       // n1Pad % 128 == 0, n2Pad % 256 == 0
     int nRChunks;                   // ceil(n2 / 256): resident chunks that hold real atoms
     int nSBlocks;                   // ceil(n1 / 128): streamed blocks that hold real atoms
-    int chunkS, nSChunks;           // streamed blocks per work item
+    int chunkS, nSChunks;           // streamed blocks per work item (the largest ranges), ranges per (frame, chunk)
+    int nBigChunks;                 // ranges 0 .. nBigChunks-1 have chunkS blocks, the rest chunkS - 2
     int sameSel;
     unsigned nItems;                // nFc * nRChunks * nSChunks
     unsigned long long *stats;
@@ -354,8 +355,11 @@ struct TcWalk {
     __device__ __forceinline__ bool decode(const TcGeom &g, TcItem &it) const
     {
         it.f = f; it.c = c;
-        it.sb0 = ks * g.chunkS;
-        it.sb1 = min(g.nSBlocks, it.sb0 + g.chunkS);
+        // the first nBigChunks ranges have chunkS blocks, the others one stage (two blocks) fewer: the
+        // streamed blocks are spread over the ranges as evenly as whole stages allow
+        const int small = max(0, ks - g.nBigChunks);
+        it.sb0 = ks * g.chunkS - 2 * small;
+        it.sb1 = min(g.nSBlocks, it.sb0 + g.chunkS - (ks >= g.nBigChunks ? 2 : 0));
         if (g.sameSel) it.sb0 = max(it.sb0, 2 * c);            // streamed index > resident index only
         return it.sb0 < it.sb1;
     }
