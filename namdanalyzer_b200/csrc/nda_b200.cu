@@ -920,15 +920,23 @@ struct Uploader {
         // compute (and the host post-processing) of the LAST chunk: taper the tail -- one more chunk, the last
         // two of 1/2 and 1/4 of the regular size (NDA_NO_TAPER=1 keeps them uniform).
         static const bool noTaper = getenv("NDA_NO_TAPER") != nullptr;
+        static const int taperLevels = getenv("NDA_TAPER_LEVELS") ? std::max(1, std::min(4, atoi(getenv("NDA_TAPER_LEVELS")))) : 2;
         if (taperTail && !noTaper && nChunks >= 3 && nChunks < maxChunks + 1 && chunk * 4 <= maxChunk * 3 && nFc >= 16 * nChunks) {
-            const int n = nChunks + 1;
-            const double unit = (double)nFc / ((double)(n - 2) + 0.75);
+            // regular chunks of one unit, then `levels` chunks of 1/2, 1/4, ... of a unit (the last one takes what is left)
+            const int levels = std::min(taperLevels, nChunks - 1);
+            const int n = nChunks + levels - 1;                   // levels - 1 more chunks than the uniform split
+            const int nReg = n - levels;
+            double tailUnits = 0.0, w = 0.5;
+            for (int l = 0; l < levels; ++l, w *= 0.5) tailUnits += w;
+            const double unit = (double)nFc / ((double)nReg + tailUnits);
             bnd.assign((size_t)n + 1, fe);
             bnd[0] = fb;
             int big = 0;
+            double upTo = 0.0;
+            w = 0.5;
             for (int k = 1; k < n; ++k) {
-                const double upTo = k <= n - 2 ? unit * k : unit * (n - 2) + unit * 0.5;
-                bnd[k] = std::min(fe - 1, std::max(bnd[k - 1] + 1, fb + (int)(upTo + 0.5)));
+                if (k <= nReg) upTo += unit; else { upTo += unit * w; w *= 0.5; }
+                bnd[k] = std::min(fe - (n - k), std::max(bnd[k - 1] + 1, fb + (int)(upTo + 0.5)));
             }
             for (int k = 0; k < n; ++k) big = std::max(big, bnd[k + 1] - bnd[k]);
             nChunks = n;
