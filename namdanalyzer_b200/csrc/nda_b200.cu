@@ -422,11 +422,8 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
         }
         g.A = L.packA.as<float4>();
         g.B = sameSel ? g.A : L.packB.as<float4>();
-        prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
-                                                             L.fp.as<FrameParams>(), stats);
-        LAUNCHED();
-        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.maxAbs.as<unsigned>(), -1.0,
-                                                          tc_range_factor() * 1.2, L.thrDot.as<TcFrame>(), stats);
+        prep_frames_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T, L.fp.as<FrameParams>(),
+                                                                -1.0, tc_range_factor() * 1.2, L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
         rc = launch_embed(st, g.B, n2Pad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embB.as<__half>(), 0);
         if (rc) return rc;
@@ -500,14 +497,11 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
         if (rc) return rc;
         g.A = L.packA.as<float4>();
         g.B = L.packB.as<float4>();
-        prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
-                                                             L.fp.as<FrameParams>(), stats);
-        LAUNCHED();
         // the "sure" shortcut needs the pure predicate to be what the reference computes: with the literal
         // per-axis early-outs (getWithin.cpp:64-71) that holds for distance >= 1 (SURVEY B-2)
         const double sureD2 = (!a.literal || d2 >= 1.0f) && !getenv("NDA_TC_NO_SURE") ? (double)d2 : -1.0;
-        prep_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(L.fp.as<FrameParams>(), nFc, L.maxAbs.as<unsigned>(), sureD2,
-                                                          tc_range_factor() * 1.2, L.thrDot.as<TcFrame>(), stats);
+        prep_frames_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T, L.fp.as<FrameParams>(),
+                                                                sureD2, tc_range_factor() * 1.2, L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
         rc = launch_embed(st, g.B, nBPad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embB.as<__half>(), 0);
         if (rc) return rc;

@@ -104,11 +104,10 @@ struct __align__(16) TcFrame {
     float pad[2];
 };
 
-__global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, const unsigned *__restrict__ maxAbs,
-                               double sureD2, double rangeFactor, TcFrame *__restrict__ tf, unsigned long long *__restrict__ stats)
+__device__ __forceinline__ void prep_tc_body(const int f, const FrameParams *__restrict__ fp, const unsigned *__restrict__ maxAbs,
+                                             double sureD2, double rangeFactor, TcFrame *__restrict__ tf,
+                                             unsigned long long *__restrict__ stats)
 {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nFc) return;
     TcFrame o;
     o.fp = fp[f];
     o.thrDot = 3.0e38f;
@@ -148,6 +147,24 @@ __global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, cons
         }
     }
     tf[f] = o;
+}
+
+__global__ void prep_tc_kernel(const FrameParams *__restrict__ fp, int nFc, const unsigned *__restrict__ maxAbs,
+                               double sureD2, double rangeFactor, TcFrame *__restrict__ tf, unsigned long long *__restrict__ stats)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < nFc) prep_tc_body(f, fp, maxAbs, sureD2, rangeFactor, tf, stats);
+}
+
+// prep_frames + prep_tc in one launch: the thread that wrote fp[f] reads it back itself
+__global__ void prep_frames_tc_kernel(const float *__restrict__ cell, int f0, int nFc, const unsigned *__restrict__ maxAbs,
+                                      double T, FrameParams *__restrict__ fp, double sureD2, double rangeFactor,
+                                      TcFrame *__restrict__ tf, unsigned long long *__restrict__ stats)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nFc) return;
+    prep_frames_body(f, cell, f0, maxAbs, T, fp, stats);
+    prep_tc_body(f, fp, maxAbs, sureD2, rangeFactor, tf, stats);
 }
 
 // ------------------------------------------------------------------------------------------
