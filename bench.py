@@ -45,8 +45,8 @@ FP32_NOMINAL_TFLOPS = 2 * 128 * 148 * 1.965e9 / 1e12     # 74.5
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1000, help="frames per step (BASELINE: 1000)")
     ap.add_argument("--no-extras", action="store_true", help="skip the RDF extra and the CPU baseline")
