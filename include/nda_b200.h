@@ -23,11 +23,17 @@
  * "host" entry points take host pointers (pageable or pinned) and do the
  * host<->device copies themselves.  "dev" entry points take device pointers in
  * the same layouts, enqueue on the given CUDA stream (a cudaStream_t passed as
- * void*, NULL = the library's own stream) and do not synchronise.
+ * void*, NULL = the library's own stream) and do not synchronise, with one exception: the
+ * within / RDF calls read the cell edges of the frame range back (12 bytes per frame, one
+ * stream synchronisation) to choose the filter; the read-back is cached per (pointer, frame range)
+ * and refreshed every 64th call.  All nda_dev_* calls of a device share one set of scratch
+ * buffers: the library orders consecutive calls with an event, also across different caller streams.
+ * One call at a time per DEVICE (a per-device lock); calls on different devices run concurrently.
  */
 #ifndef NDA_B200_H
 #define NDA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -45,8 +51,34 @@ const char *nda_last_error(void);
  * branch and never the scipy kd-tree (dataParsers/dcdParser.py:181). */
 int  nda_get_parallel_backend(void);
 int  nda_device_count(void);
-int  nda_set_device(int device);          /* device used by the calling thread's context */
+/* Devices of the CALLING THREAD.  nda_set_device: one device (also the one the nda_dev_* entry points
+ * use).  nda_set_devices: the host entry points (nda_get_within*, nda_get_radial_nbr_*, nda_get_distances*)
+ * split their frame range [floor(g nF / G), floor((g + 1) nF / G)) over the G devices -- the frame is the
+ * outermost loop of every reference function (lib/openmp/src/getWithin.cpp:31, getDistances.cpp:26,
+ * getRadialNbrDensity.cpp:12) -- one host thread and one context per device, every device uploading
+ * only its own frame columns over its own link; histograms (u64) and distance sums (f64) are merged by
+ * ONE ncclAllReduce per call on the compute streams (communicators from ncclCommInitAll; NCCL is
+ * dlopen()ed), within needs no collective.  Default: NDA_DEVICES ("0,1,2" or "all") if set, else the
+ * current CUDA device.  nda_get_devices returns the count (and up to `capacity` ids). */
+int  nda_set_device(int device);
+int  nda_set_devices(const int *devices, int n);
+int  nda_get_devices(int *devices, int capacity);
 int  nda_get_device(void);
+/* how the last multi-device host call merged its partial results: 0 no merge (one device, or within),
+ * 1 ncclAllReduce, 2 summed on the host (NCCL not loadable, or NDA_COLLECTIVE=host) */
+int  nda_last_collective(void);
+/* Tuning / debugging switches.  The environment variables of the same names (NDA_FILTER,
+ * NDA_TC_RANGE_FACTOR, NDA_TC_MAX_FRACTION, NDA_TC_ALLOW_PADDING, NDA_NO_CELL_CACHE, NDA_STRICT_SLOW,
+ * NDA_TC_NO_SURE, NDA_CTAS_PER_SM, NDA_DEBUG, NDA_HOST_THREADS, NDA_UPLOAD_CHUNKS, NDA_WITHIN_CHUNKS,
+ * NDA_NO_TAPER, NDA_TAPER_LEVELS, NDA_COPY_STREAMS, NDA_D2H_COPY_ENGINE, NDA_COLLECTIVE=nccl|host,
+ * NDA_SUBPASS_FRAMES, NDA_COMPAT_CUDA, NDA_NVTX) are read ONCE, when the library is first used; afterwards
+ * only this call changes a value.  value NULL or "" restores the default.  No switch changes a result,
+ * except NDA_COMPAT_CUDA=1: nda_get_within then also marks every refSel atom in every frame, as the
+ * reference's legacy CUDA build does (lib/cuda/src/getWithin.cu:27-28). */
+int  nda_set_option(const char *name, const char *value);
+/* frees every device buffer, pinned staging area, stream, event and NCCL communicator the library
+ * holds (they are kept between calls otherwise); the next call builds them again */
+int  nda_shutdown(void);
 /* kernels launched by this library in this process since the last reset */
 uint64_t nda_launch_count(void);
 void     nda_launch_count_reset(void);
@@ -57,9 +89,16 @@ int  nda_set_within_pure_predicate(int on);
  * NDA_FILTER=tc|rint|fold|fold2|fold2a0..3 selects; tc (default) falls back to fold2 when a frame
  * of the call is not eligible (cut-off too close to the cell size, no unit cell, dense ranges) */
 int  nda_last_filter(void);
-/* debugging aid: with NDA_TC_TRACE=1 the last tensor-core within call recorded clock64 stamps of
- * CTA 0's pipeline (256 steps x 32 stamps, see csrc/nda_tc.cuh: tc_stamp); copies them out */
+/* debugging aid (trace builds of tools/build_variants.py only): with NDA_TC_TRACE=1 the last tensor-core
+ * within call recorded clock64 stamps of CTA 0's pipeline (256 steps x 32 stamps, csrc/nda_tc.cuh: tc_stamp) */
 int  nda_debug_tc_trace(long long *out);
+/* parity support: ONE production tcgen05.mma (M = 128, N = 256, K = 16, fp16 accumulators; the instruction
+ * descriptor, operand layout and tcgen05.ld.pack::16b read-back of the pair kernels) on caller-supplied
+ * operands.  A uint16 [128][16], B uint16 [256][16]: fp16 bit patterns, row-major (host pointers).
+ * out uint32 [128][128]: out[row][32 * cq + n] = register n of the epilogue warp that owns columns
+ * 64 cq .. 64 cq + 63 of that row.  tests/test_gpu_tensor_filter.py pins with it that an accumulator is the
+ * correctly rounded exact sum and that register n holds columns 2n (low half) and 2n + 1 (high half). */
+int  nda_debug_tc_probe(const uint16_t *A, const uint16_t *B, uint32_t *out);
 
 /* ---- drop-in host entry points (reference signatures) --------------------------- */
 
@@ -76,9 +115,10 @@ int nda_get_within(const float *allAtoms, int nbrAtoms, int nbrFrames,
 int nda_get_distances(const float *sel1, int sel1_size, const float *sel2, int sel2_size,
                       float *out, const float *cellDims, int nbrFrames, int sameSel);
 
-/* lib/openmp/src/getRadialNbrDensity.cpp:8-52.  out float32 [outSize] is OVERWRITTEN with
- * count[idx] / nbrFrames, idx = (int)(dist/dr); sameSel != 0 counts each unordered pair
- * once (col > row).  maxR is accepted and ignored, as in the reference. */
+/* lib/openmp/src/getRadialNbrDensity.cpp:8-52.  count[idx] / nbrFrames, idx = (int)(dist/dr), is
+ * ADDED to out float32 [outSize], as the reference accumulates (:40-41; every stock caller passes
+ * zeros); sameSel != 0 counts each unordered pair once (col > row).  maxR is accepted and ignored,
+ * as in the reference. */
 int nda_get_radial_nbr_density(const float *sel1, int sel1_size, const float *sel2, int sel2_size,
                                float *out, int outSize, const float *cellDims, int nbrFrames,
                                int sameSel, float maxR, float dr);
@@ -216,6 +256,11 @@ int nda_measure_fp32_peak(int variant, double *tflops);
  * [0] pairs evaluated by the fast filter, [1] candidates re-evaluated exactly,
  * [2] frames that ran in all-exact mode (cut-off >= half the box), [3] kernel ms. */
 int nda_last_stats(double stats[4]);
+
+/* Platform ceiling for the end-to-end numbers: `bytes` of contiguous pinned host memory copied to EVERY
+ * device of the calling thread at the same time (one plain cudaMemcpyAsync each, `reps` times, one host
+ * thread per device); *gbps = aggregate rate over the slowest device's time. */
+int nda_measure_h2d(size_t bytes, int reps, double *gbps);
 
 /* Device time (CUDA events on the launching stream) spent in the pair kernel(s) -- rdf_kernel,
  * within_kernel or distances_kernel, one launch per pass -- of the last entry-point call on this

@@ -12,7 +12,7 @@ There is no CPU fallback: without ``lib/libnda_b200.so`` or without a B200 every
 import sys
 import types
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 _PAIR_OPS = ("py_getWithin", "py_getDistances", "py_getRadialNbrDensity", "py_getParallelBackend",
              "py_setWaterDistPBC", "py_waterOrientAtSurface", "py_getHBCorr", "py_getDCDCoor", "py_getDCDCell")
@@ -24,8 +24,12 @@ def install():
     The reference imports its operators by name at module import time
     (NAMDAnalyzer/dataParsers/dcdParser.py:22-31, dataAnalysis/RadialDensity.py:21-25), so call this
     BEFORE importing NAMDAnalyzer.  If the reference's compiled ``pylibFuncs`` exists its other
-    entry points (DCD readers, scattering functions, ...) are kept; only the four pair operators
-    are replaced.  Returns the module object that was installed."""
+    entry points (scattering functions, ...) are kept; the operators in ``_PAIR_OPS`` are replaced: the
+    four pair operators, the three SURVEY section 8 f-3 / f-4 operators and the two DCD readers of row
+    f-2 (the reference's own reader does not compile outside MSVC).  When ``NAMDAnalyzer.selection.selParser``
+    is importable, ``SelParser.process`` is patched as well (``namdanalyzer_b200.selection``): the per-frame
+    Python loop behind ``selection('... within ... frame a:b')`` becomes one vectorised decode (row f-1).
+    Returns the module object that was installed."""
     from .lib import pylibFuncs as ours
     name = "NAMDAnalyzer.lib.pylibFuncs"
     try:
@@ -48,4 +52,10 @@ def install():
         sys.modules[name] = mod
     for op in _PAIR_OPS:
         setattr(mod, op, getattr(ours, op))
+    try:                                                    # row f-1 for the reference's own callers
+        import importlib
+        from .selection import patch_selparser
+        patch_selparser(importlib.import_module("NAMDAnalyzer.selection.selParser").SelParser)
+    except Exception:
+        pass                                                # reference not importable here: nothing to patch
     return mod

@@ -24,6 +24,13 @@ SIGNATURES = {
     "nda_device_count": (c_int, []),
     "nda_set_device": (c_int, [c_int]),
     "nda_get_device": (c_int, []),
+    "nda_set_devices": (c_int, [c_i32p, c_int]),
+    "nda_get_devices": (c_int, [c_i32p, c_int]),
+    "nda_last_collective": (c_int, []),
+    "nda_set_option": (c_int, [ctypes.c_char_p, ctypes.c_char_p]),
+    "nda_shutdown": (c_int, []),
+    "nda_debug_tc_probe": (c_int, [ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_uint16), c_u32p]),
+    "nda_measure_h2d": (c_int, [ctypes.c_size_t, c_int, c_f64p]),
     "nda_launch_count": (ctypes.c_uint64, []),
     "nda_launch_count_reset": (None, []),
     "nda_set_within_pure_predicate": (c_int, [c_int]),
@@ -84,6 +91,35 @@ def load():
             fn.argtypes = argtypes
         _lib = lib
     return _lib
+
+
+def set_option(name, value=None):
+    """nda_set_option: ``value`` None restores the default.  The library reads its NDA_* environment
+    variables once, at first use; this is the only way to change a switch afterwards."""
+    check(load().nda_set_option(name.encode(), None if value is None else str(value).encode()))
+
+
+class options:
+    """``with _capi.options(NDA_FILTER="fold2"): ...`` -- set switches for a block, restore the defaults after."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k in self.kw:
+            set_option(k, os.environ.get(k))      # back to what the process was started with
+        return False
+
+
+def set_devices(devices):
+    """Shard the host entry points' frames over these devices (one process, one host thread per device)."""
+    arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+    check(load().nda_set_devices(arr, len(devices)))
 
 
 def check(rc):

@@ -13,7 +13,7 @@ OUT = os.path.join(_HERE, "lib", "libnda_b200.so")
 SOURCES = ["nda_b200.cu"]
 DEPS = ["nda_b200.cu", "nda_kernels.cuh", "nda_device.cuh", "nda_surface.cuh", "nda_tc.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-fopenmp", "-lgomp"]
+              "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-Xcompiler", "-fopenmp", "-lgomp", "-ldl"]
 
 
 def _stale():
@@ -29,13 +29,23 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    extra = ["-DNDA_TC_TRACE_BUILD"] if os.environ.get("NDA_TC_TRACE_BUILD") == "1" else []   # tools/tc_trace.py
-    if os.environ.get("NDA_TC_EXPERIMENT"):       # pipeline-floor experiments (1: no reduction, 2: no TMEM load); WRONG results
-        extra.append("-DNDA_TC_EXPERIMENT=" + os.environ["NDA_TC_EXPERIMENT"])
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+    # Only ONE configuration is ever built here: no environment variable or flag can change what the product
+    # library computes.  Trace / pipeline-floor experiment builds live in tools/build_variants.py and are
+    # written to tools/variants/ under their own names.
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", OUT] + [os.path.join(SRC_DIR, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return OUT
+
+
+def build_variant(tag, defines, out_dir):
+    """tools/build_variants.py: the same sources with extra -D flags into ``out_dir/libnda_b200_<tag>.so``."""
+    nvcc = os.environ.get("NVCC", "nvcc")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "libnda_b200_%s.so" % tag)
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] +
+                          [os.path.join(SRC_DIR, s) for s in SOURCES])
+    return out
 
 
 if __name__ == "__main__":

@@ -17,20 +17,128 @@
 #include <vector>
 #include <algorithm>
 
+#include <nvtx3/nvToolsExt.h>
+#include <nccl.h>
+#include <type_traits>
+#include <dlfcn.h>
+#include <condition_variable>
+#include <map>
+
 #include "../../include/nda_b200.h"
 #include "nda_kernels.cuh"
 #include "nda_tc.cuh"
 #include "nda_surface.cuh"
 
 // ------------------------------------------------------------------------------------------
-// errors, launch accounting
+// errors, launch accounting, options
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_within_pure{0};
 static std::atomic<int> g_last_filter{-1};          // filter of the last pair-kernel launch: 0..5 FP32 filters, 100 tensor core
-static std::mutex g_mutex;
-static int g_host_threads = 4;          // host threads gathering pageable rows into pinned staging
+static std::atomic<int> g_last_collective{0};       // how the last multi-device call merged its partials: 0 none, 1 NCCL, 2 host sum
+
+// Every tuning / debugging switch of the library.  The environment is read ONCE, when the library is
+// first used; afterwards only nda_set_option() changes a value (tests and tools use it), so an entry
+// point never calls getenv().  Names are the environment variables' names.
+struct Config {
+    int    filterTc = 1;            // NDA_FILTER=tc (default) | rint | fold | fold2 | fold2a0..3
+    int    filterKind = kFilterFold2 + 1;
+    double tcRangeFactor = 1.5;     // NDA_TC_RANGE_FACTOR: longest range the tensor filter takes, thr <= factor * P
+    double tcMaxFraction = 0.0;     // NDA_TC_MAX_FRACTION: cap on the expected in-range fraction (0 = none)
+    int    tcAllowPadding = 0;      // NDA_TC_ALLOW_PADDING: tensor filter even for mostly-padding selections
+    int    noCellCache = 0;         // NDA_NO_CELL_CACHE
+    int    strictSlow = 0;          // NDA_STRICT_SLOW: IEEE divisions in every strict re-evaluation
+    int    tcNoSure = 0;            // NDA_TC_NO_SURE: within without the SURE shortcut
+    int    tcTrace = 0;             // NDA_TC_TRACE: clock64 trace buffer (trace builds only, tools/)
+    int    ctasPerSM = 0;           // NDA_CTAS_PER_SM: cap on the persistent FP32 kernels' CTAs per SM
+    int    debug = 0;               // NDA_DEBUG: 1 filter choice, 2 + host phase clock
+    int    hostThreads = 0;         // NDA_HOST_THREADS: host threads gathering pageable rows (0 = automatic)
+    int    uploadChunks = 0;        // NDA_UPLOAD_CHUNKS / NDA_WITHIN_CHUNKS: frame chunks per host call (0 = automatic)
+    int    withinChunks = 0;
+    int    noTaper = 0;             // NDA_NO_TAPER, NDA_TAPER_LEVELS
+    int    taperLevels = 2;
+    int    copyStreams = 0;         // NDA_COPY_STREAMS: 0 automatic, 1, 2
+    int    d2hCopyEngine = 0;       // NDA_D2H_COPY_ENGINE: bitmask back by cudaMemcpyAsync instead of SM stores
+    int    collective = 0;          // NDA_COLLECTIVE: 0 automatic (NCCL when it loads), 1 nccl (fail otherwise), 2 host sum
+    int    subpassFrames = 0;       // NDA_SUBPASS_FRAMES: device API in frame sub-passes of this size (0 = one pass)
+    int    compatCuda = 0;          // NDA_COMPAT_CUDA: getWithin also flags every refSel atom (legacy CUDA build, SURVEY B-1)
+    int    nvtx = 1;                // NDA_NVTX=0 switches the NVTX ranges off
+};
+static Config g_cfg;
+static std::once_flag g_cfg_once;
+static std::mutex g_cfg_mutex;
+
+static const char *const kOptionNames[] = {
+    "NDA_FILTER", "NDA_TC_RANGE_FACTOR", "NDA_TC_MAX_FRACTION", "NDA_TC_ALLOW_PADDING", "NDA_NO_CELL_CACHE",
+    "NDA_STRICT_SLOW", "NDA_TC_NO_SURE", "NDA_TC_TRACE", "NDA_CTAS_PER_SM", "NDA_DEBUG", "NDA_HOST_THREADS",
+    "NDA_UPLOAD_CHUNKS", "NDA_WITHIN_CHUNKS", "NDA_NO_TAPER", "NDA_TAPER_LEVELS", "NDA_COPY_STREAMS",
+    "NDA_D2H_COPY_ENGINE", "NDA_COLLECTIVE", "NDA_SUBPASS_FRAMES", "NDA_COMPAT_CUDA", "NDA_NVTX"};
+
+// value == nullptr or "": back to the default
+static bool apply_option(Config &c, const char *name, const char *v)
+{
+    const Config d;
+    const bool has = v && *v;
+    auto flag = [&](int &dst, int dflt) { dst = has ? (strcmp(v, "0") != 0) : dflt; };     // present and not "0"
+    auto num = [&](int &dst, int dflt, int lo, int hi) { dst = dflt; if (has) { const int x = atoi(v); if (x >= lo && x <= hi) dst = x; } };
+    if (!strcmp(name, "NDA_FILTER")) {
+        c.filterTc = !has || !strcmp(v, "tc");
+        c.filterKind = d.filterKind;
+        if (has && !strcmp(v, "rint")) c.filterKind = kFilterRint;
+        else if (has && !strcmp(v, "fold")) c.filterKind = kFilterFold;
+        else if (has && !strncmp(v, "fold2a", 6) && v[6] >= '0' && v[6] <= '3') c.filterKind = kFilterFold2 + (v[6] - '0');
+    } else if (!strcmp(name, "NDA_TC_RANGE_FACTOR")) { c.tcRangeFactor = d.tcRangeFactor; if (has && atof(v) > 0.0) c.tcRangeFactor = atof(v); }
+    else if (!strcmp(name, "NDA_TC_MAX_FRACTION")) { c.tcMaxFraction = 0.0; if (has && atof(v) > 0.0) c.tcMaxFraction = atof(v); }
+    else if (!strcmp(name, "NDA_TC_ALLOW_PADDING")) flag(c.tcAllowPadding, 0);
+    else if (!strcmp(name, "NDA_NO_CELL_CACHE")) flag(c.noCellCache, 0);
+    else if (!strcmp(name, "NDA_STRICT_SLOW")) flag(c.strictSlow, 0);
+    else if (!strcmp(name, "NDA_TC_NO_SURE")) flag(c.tcNoSure, 0);
+    else if (!strcmp(name, "NDA_TC_TRACE")) num(c.tcTrace, 0, 0, 1);
+    else if (!strcmp(name, "NDA_CTAS_PER_SM")) num(c.ctasPerSM, 0, 1, 32);
+    else if (!strcmp(name, "NDA_DEBUG")) num(c.debug, 0, 0, 9);
+    else if (!strcmp(name, "NDA_HOST_THREADS")) num(c.hostThreads, 0, 1, 256);
+    else if (!strcmp(name, "NDA_UPLOAD_CHUNKS")) num(c.uploadChunks, 0, 1, 1 << 20);
+    else if (!strcmp(name, "NDA_WITHIN_CHUNKS")) num(c.withinChunks, 0, 1, 1 << 20);
+    else if (!strcmp(name, "NDA_NO_TAPER")) flag(c.noTaper, 0);
+    else if (!strcmp(name, "NDA_TAPER_LEVELS")) num(c.taperLevels, 2, 1, 4);
+    else if (!strcmp(name, "NDA_COPY_STREAMS")) num(c.copyStreams, 0, 0, 2);
+    else if (!strcmp(name, "NDA_D2H_COPY_ENGINE")) flag(c.d2hCopyEngine, 0);
+    else if (!strcmp(name, "NDA_COLLECTIVE")) {
+        c.collective = 0;
+        if (has && !strcmp(v, "nccl")) c.collective = 1;
+        else if (has && !strcmp(v, "host")) c.collective = 2;
+    }
+    else if (!strcmp(name, "NDA_SUBPASS_FRAMES")) num(c.subpassFrames, 0, 1, 1 << 30);
+    else if (!strcmp(name, "NDA_COMPAT_CUDA")) flag(c.compatCuda, 0);
+    else if (!strcmp(name, "NDA_NVTX")) num(c.nvtx, 1, 0, 1);
+    else return false;
+    return true;
+}
+
+static void config_init()
+{
+    std::call_once(g_cfg_once, [] {
+        std::lock_guard<std::mutex> lk(g_cfg_mutex);
+        for (const char *n : kOptionNames)
+            if (const char *e = getenv(n)) apply_option(g_cfg, n, e);
+    });
+}
+
+// a call works on a snapshot, so an option changed by another thread never splits one call
+static Config config_get()
+{
+    config_init();
+    std::lock_guard<std::mutex> lk(g_cfg_mutex);
+    return g_cfg;
+}
+
+// NVTX ranges around the phases of a call (upload / pack / pair kernel / all-reduce): free when no tool listens
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char *name, bool enabled = true) : on(enabled) { if (on) nvtxRangePushA(name); }
+    ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 
 static int fail(int code, const char *fmt, ...)
 {
@@ -83,6 +191,9 @@ struct RowRun { int dstRow, srcRow, stride, count; };
 struct Ctx {
     int dev = -1;
     bool ready = false;
+    std::mutex mu;                                // one call at a time per DEVICE (contexts of different devices run concurrently)
+    Config cfg;                                   // option snapshot of the call in progress
+    int hostThreads = 1;                          // host threads this call may use (gather, scatter)
     int numSMs = 0;
     size_t smemOptin = 0;
     cudaStream_t stream = nullptr, copyStream = nullptr, copyStream2 = nullptr;
@@ -102,7 +213,13 @@ struct Ctx {
     // two LANES = two compute streams with their own pass buffers: consecutive frame chunks of the
     // host entry points run on alternating lanes so the head of chunk k+1's persistent kernel fills
     // the tail of chunk k's.  ctl: [0..1] work counter (u32 x2), stats u64 x2 at +16.
-    struct Lane { DevBuf packA, packB, packAw, packBw, fp, maxAbs, ctl, embA, embB, thrDot; cudaStream_t stream = nullptr; };
+    struct Lane {
+        DevBuf packA, packB, packAw, packBw, fp, maxAbs, ctl, embA, embB, thrDot;
+        cudaStream_t stream = nullptr;
+        // recorded after the last kernel that touches the lane's scratch; the next user (any stream) waits on it,
+        // so two calls on different caller streams cannot race on the scratch buffers
+        cudaEvent_t evBusy = nullptr;
+    };
     Lane lane[2];
     cudaEvent_t evSetup = nullptr, evLaneJoin = nullptr, evSetupCopy = nullptr;
     void *setupStage = nullptr;                   // pinned staging for the small per-call arrays (cell, selections)
@@ -148,26 +265,27 @@ struct Ctx {
 };
 
 static Ctx g_ctx[16];
+static std::mutex g_ctx_init_mutex;
+// devices of the calling thread: [0] serves the device-pointer API; with more than one the host entry
+// points shard their frames over all of them (nda_set_devices)
+static thread_local std::vector<int> g_devs;
 static thread_local int g_dev = -1;
+static int default_host_threads();
 
-static int ctx_get(Ctx **out)
+static int ctx_for(int dev, Ctx **out)
 {
-    if (g_dev < 0) {
-        int cur = 0;
-        cudaError_t e = cudaGetDevice(&cur);
-        if (e != cudaSuccess) return fail(NDA_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
-        g_dev = cur;
-    }
-    if (g_dev >= 16) return fail(NDA_ERR_ARG, "device index %d not supported", g_dev);
-    Ctx &c = g_ctx[g_dev];
-    CK(cudaSetDevice(g_dev));
+    if (dev < 0 || dev >= 16) return fail(NDA_ERR_ARG, "device index %d not supported", dev);
+    Ctx &c = g_ctx[dev];
+    CK(cudaSetDevice(dev));
+    std::lock_guard<std::mutex> lk(g_ctx_init_mutex);
     if (!c.ready) {
+        config_init();
         cudaDeviceProp prop;
-        CK(cudaGetDeviceProperties(&prop, g_dev));
+        CK(cudaGetDeviceProperties(&prop, dev));
         if (prop.major != 10)
             return fail(NDA_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
-                        g_dev, prop.major, prop.minor);
-        c.dev = g_dev;
+                        dev, prop.major, prop.minor);
+        c.dev = dev;
         c.numSMs = prop.multiProcessorCount;
         c.smemOptin = prop.sharedMemPerBlockOptin;
         CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
@@ -185,25 +303,9 @@ static int ctx_get(Ctx **out)
             CK(cudaEventCreateWithFlags(&c.evCopied[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c.evDone[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c.evBits[i], cudaEventDisableTiming));
-        }
-        CK(c.lane[0].ctl.reserve(256));
-        CK(c.lane[1].ctl.reserve(256));
-        CK(cudaMemset(c.lane[0].ctl.p, 0, 256));
-        CK(cudaMemset(c.lane[1].ctl.p, 0, 256));
-        {
-            unsigned hw = std::thread::hardware_concurrency();
-            // gathering pageable rows is memory-bound host work: 16 threads reach ~50 GB/s on the 16-core
-            // GPU hosts measured (8: 33 GB/s, more threads than cores: slower)
-            int t = (int)std::max(1u, std::min(16u, hw));
-            // one process per GPU: the ranks of a node share its cores, and OpenMP teams that outnumber the cores
-            // spin against each other (2 ranks x 16 threads on 16 cores: 10x slower end to end, measured)
-            for (const char *name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE"}) {
-                const char *e = getenv(name);
-                const int ranks = e ? atoi(e) : 0;
-                if (ranks > 1) { t = std::max(1, std::min(t, (int)hw / ranks)); break; }
-            }
-            if (const char *e = getenv("NDA_HOST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) t = v; }
-            g_host_threads = t;
+            CK(cudaEventCreateWithFlags(&c.lane[i].evBusy, cudaEventDisableTiming));
+            CK(c.lane[i].ctl.reserve(256));
+            CK(cudaMemset(c.lane[i].ctl.p, 0, 256));
         }
         c.ready = true;
     }
@@ -211,14 +313,54 @@ static int ctx_get(Ctx **out)
     return NDA_OK;
 }
 
-static inline void begin_call(Ctx &c) { c.kevUsed = 0; }
+// context of the calling thread's (first) device
+static int ctx_get(Ctx **out)
+{
+    if (g_dev < 0) {
+        int cur = 0;
+        cudaError_t e = cudaGetDevice(&cur);
+        if (e != cudaSuccess) return fail(NDA_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+        g_dev = cur;
+    }
+    return ctx_for(g_dev, out);
+}
+
+// gathering pageable rows is memory-bound host work: 16 threads reach ~50 GB/s on the 16-core GPU hosts
+// measured (8: 33 GB/s, more threads than cores: slower).  One process per GPU: the ranks of a node share
+// its cores, and OpenMP teams that outnumber the cores spin against each other (2 ranks x 16 threads on 16
+// cores: 10x slower end to end, measured).  Read once.
+static int default_host_threads()
+{
+    static const int cached = [] {
+        const unsigned hw = std::thread::hardware_concurrency();
+        int t = (int)std::max(1u, std::min(16u, hw));
+        for (const char *name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE"}) {
+            const char *e = getenv(name);
+            const int ranks = e ? atoi(e) : 0;
+            if (ranks > 1) { t = std::max(1, std::min(t, (int)hw / ranks)); break; }
+        }
+        return t;
+    }();
+    return cached;
+}
+
+// every entry point: lock the device's context, snapshot the options; `share` = how many devices of this
+// call divide the host's threads among themselves
+static inline void begin_call(Ctx &c, int share = 1)
+{
+    c.kevUsed = 0;
+    c.cfg = config_get();
+    const int t = c.cfg.hostThreads > 0 ? c.cfg.hostThreads : default_host_threads();
+    c.hostThreads = std::max(1, t / std::max(1, share));
+}
+static inline cudaError_t lane_acquire(Ctx::Lane &L, cudaStream_t st) { return cudaStreamWaitEvent(st, L.evBusy, 0); }
+static inline cudaError_t lane_release(Ctx::Lane &L, cudaStream_t st) { return cudaEventRecord(L.evBusy, st); }
 static cudaError_t reset_stats(Ctx &c, cudaStream_t st);
 
 // tuning override for experiments: NDA_CTAS_PER_SM=<n> caps the persistent grid at n CTAs per SM
-static int tuned_ctas(int occ)
+static int tuned_ctas(const Config &cfg, int occ)
 {
-    const char *e = getenv("NDA_CTAS_PER_SM");
-    if (e && *e) { int v = atoi(e); if (v >= 1 && v < occ) return v; }
+    if (cfg.ctasPerSM >= 1 && cfg.ctasPerSM < occ) return cfg.ctasPerSM;
     return occ < 1 ? 1 : occ;
 }
 
@@ -234,6 +376,7 @@ static int launch_pack(Ctx &c, cudaStream_t st, const float *src, int nFtot, con
     const long long tiles = (long long)(nPad / 32) * ((nFc + 31) / 32);
     if (tiles > 0x7fffffffLL) return fail(NDA_ERR_ARG, "internal: pack tile count overflows");
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)c.numSMs * 5));
+    NvtxRange nv("nda:pack_kernel", c.cfg.nvtx);
     pack_kernel<<<grid, 256, 0, st>>>(src, nFtot, gather, n, nPad, f0, nFc, gid, dst, maxAbs, cell, dstW, pairLayout, embA);
     LAUNCHED();
     return NDA_OK;
@@ -242,12 +385,6 @@ static int launch_pack(Ctx &c, cudaStream_t st, const float *src, int nFtot, con
 // NDA_FILTER=tc (default): the tensor-core filter (nda_tc.cuh) whenever every frame of the call is
 // eligible, the packed-FP32 fold2 filter otherwise.  NDA_FILTER=rint|fold|fold2|fold2a0..3 forces an
 // FP32 filter.
-static bool filter_tc_requested()
-{
-    const char *e = getenv("NDA_FILTER");
-    return !e || !*e || !strcmp(e, "tc");
-}
-
 // Host-side mirror of prep_tc_kernel with a 10 % margin: true when no frame of [fb, fe) would be
 // sent to the all-exact path by the tensor-core filter.  T = in-range limit on r2.
 // maxFraction: optional cap on the expected in-range fraction (cut-off sphere over cell volume).  Measured on
@@ -259,31 +396,25 @@ static bool filter_tc_requested()
 // the range (S saturates at 4 P) and the candidate path takes over: measured on small water boxes
 // (tools/range_sweep.py, 14.9 A) the tensor filter is 1.44x / 1.2x / 1.24x ahead of the FP32 filter at
 // range / c = 0.22 / 0.28 / 0.34 and behind (0.75x, 0.84x) at 0.40 and 0.48.  Results are identical at
-// every range; NDA_TC_RANGE_FACTOR overrides.
-static double tc_range_factor()
-{
-    if (const char *e = getenv("NDA_TC_RANGE_FACTOR")) { const double v = atof(e); if (v > 0.0) return v; }
-    return 1.5;
-}
-
+// every range; NDA_TC_RANGE_FACTOR (Config::tcRangeFactor) overrides.
 // nStream / nResident: the tensor kernels pad the streamed selection to 128 and the resident one to 256
 // atoms; with more than ~4x padding the packed-FP32 kernel (5.4x slower per pair) wins.
-static bool tc_frames_eligible(const float *cell, int fb, int fe, double T, double maxFraction,
+static bool tc_frames_eligible(const Config &cfg, const float *cell, int fb, int fe, double T, double maxFraction,
                                int nStream, int nResident)
 {
     const double k = 0.15915494309189535;
     {
         const double padded = (double)round_up(nStream, 256) * (double)round_up(nResident, 256);
-        if (padded > 4.0 * (double)nStream * (double)nResident && !getenv("NDA_TC_ALLOW_PADDING")) return false;
+        if (padded > 4.0 * (double)nStream * (double)nResident && !cfg.tcAllowPadding) return false;
     }
-    if (const char *e = getenv("NDA_TC_MAX_FRACTION")) { const double v = atof(e); if (v > 0.0) maxFraction = v; }
+    if (cfg.tcMaxFraction > 0.0) maxFraction = cfg.tcMaxFraction;
     for (int f = fb; f < fe; ++f) {
         const double cx = fabs((double)cell[3 * (size_t)f]), cy = fabs((double)cell[3 * (size_t)f + 1]), cz = fabs((double)cell[3 * (size_t)f + 2]);
         if (!(cx > 0.0 && cy > 0.0 && cz > 0.0) || !(cx < 1.0e30 && cy < 1.0e30 && cz < 1.0e30)) return false;
         const double P = (cx * cx + cy * cy + cz * cz) * k * k;
         const double Eb = P * (4.8828125e-04 * 1.01 + 3.814697265625e-06) + 1.0e-6;
         const double thr = T * 1.001 + 1.0e-6;
-        if (!(2.5 * Eb * 1.1 <= thr && thr * 1.1 <= tc_range_factor() * P * 1.2 && P < 2.5e4)) return false;
+        if (!(2.5 * Eb * 1.1 <= thr && thr * 1.1 <= cfg.tcRangeFactor * P * 1.2 && P < 2.5e4)) return false;
         const double sphere = 4.1887902047863905 * T * sqrt(T);
         if (sphere > maxFraction * cx * cy * cz) return false;
     }
@@ -300,7 +431,7 @@ static int host_cell_view(Ctx &c, cudaStream_t st, const float *h_cell, const fl
 {
     if (h_cell) { *out = h_cell; return NDA_OK; }
     const bool hit = c.hostCellPtr == d_cell && fb >= c.hostCellFb && fe <= c.hostCellFe && ++c.hostCellUses < 64 &&
-                     !getenv("NDA_NO_CELL_CACHE");
+                     !c.cfg.noCellCache;
     if (!hit) {
         c.hostCell.resize((size_t)3 * fe);
         CK(cudaMemcpyAsync(c.hostCell.data() + 3 * (size_t)fb, d_cell + 3 * (size_t)fb, (size_t)(fe - fb) * 12, cudaMemcpyDeviceToHost, st));
@@ -309,16 +440,6 @@ static int host_cell_view(Ctx &c, cudaStream_t st, const float *h_cell, const fl
     }
     *out = c.hostCell.data();
     return NDA_OK;
-}
-
-// which FP32 filter the pair kernels run (NDA_FILTER=rint|fold|fold2, default fold2)
-static int filter_kind()
-{
-    const char *e = getenv("NDA_FILTER");
-    if (e && !strcmp(e, "rint")) return kFilterRint;
-    if (e && !strcmp(e, "fold")) return kFilterFold;
-    if (e && !strncmp(e, "fold2a", 6) && e[6] >= '0' && e[6] <= '3') return kFilterFold2 + (e[6] - '0');
-    return kFilterFold2 + 1;
 }
 
 // frames per pass so that the packed copies stay within a fixed HBM budget
@@ -370,13 +491,18 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
                       const int *d_idx1, const int *d_idx2, double T)
 {
     const bool grouped = d_gid != nullptr;
-    const size_t H = (size_t)nGroups * nBins;
     const size_t base = tc_smem_base();
     const size_t budget = c.smemOptin > base ? c.smemOptin - base : 0;
-    int copies = (int)std::min<size_t>(TC_EPI_WARPS, budget / (H * 4));
-    if (copies < 1)
-        return fail(NDA_ERR_ARG, "nGroups*outSize = %zu histogram cells do not fit in shared memory (max %zu)", H, budget / 4);
-    const size_t smem = base + (size_t)copies * H * 4;
+    // The [groups][bins] histogram lives in shared memory.  When all groups do not fit (a protein of more than
+    // ~230 residues at 149 bins) the pair kernel runs once per BATCH of groups over the same packed frames: atoms
+    // of other groups are filtered like any other and dropped at the histogram (the reference makes one full
+    // call per residue, dataAnalysis/RadialDensity.py:84-103).
+    if ((size_t)nBins * 4 > budget)
+        return fail(NDA_ERR_ARG, "outSize = %d histogram cells do not fit in shared memory (max %zu)", nBins, budget / 4);
+    const int groupsPerBatch = (int)std::min<size_t>((size_t)nGroups, budget / ((size_t)nBins * 4));
+    const size_t Hb = (size_t)groupsPerBatch * nBins;
+    const int copies = (int)std::max<size_t>(1, std::min<size_t>(TC_EPI_WARPS, budget / (Hb * 4)));
+    const size_t smem = base + (size_t)copies * Hb * 4;
     // sel1 is streamed in 128-atom blocks (TMEM lanes), sel2 is resident in 256-atom chunks (columns)
     const int n1Pad = round_up(n1, TC_SPS * TC_SBLK);          // whole two-block stages (= TC_RBLK)
     const int n2Pad = sameSel ? n1Pad : round_up(n2, TC_RBLK);
@@ -401,9 +527,9 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
     g.stats = stats;
     g.origInStage = 1;
     g.trace = nullptr;
-    a.counts = d_counts; a.nBins = nBins; a.nGroups = nGroups; a.histCopies = copies;
+    a.counts = d_counts; a.nBins = nBins; a.nGroups = groupsPerBatch; a.groupBase = 0; a.histCopies = copies;
     a.dr = dr;
-    a.fastStrict = getenv("NDA_STRICT_SLOW") ? 0 : 1;
+    a.fastStrict = c.cfg.strictSlow ? 0 : 1;
     tc_chunking(g, c.numSMs, pass, 8);
     const void *kfn = grouped ? (const void *)rdf_tc_kernel<true> : (const void *)rdf_tc_kernel<false>;
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -423,7 +549,7 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
         g.A = L.packA.as<float4>();
         g.B = sameSel ? g.A : L.packB.as<float4>();
         prep_frames_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T, L.fp.as<FrameParams>(),
-                                                                -1.0, tc_range_factor() * 1.2, L.thrDot.as<TcFrame>(), stats);
+                                                                -1.0, c.cfg.tcRangeFactor * 1.2, L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
         rc = launch_embed(st, g.B, n2Pad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embB.as<__half>(), 0);
         if (rc) return rc;
@@ -433,11 +559,17 @@ static int dev_rdf_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1
         if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
         g.nItems = (unsigned)items;
         const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)c.numSMs);
-        CK(c.kev_record(st));
-        if (grouped) rdf_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
-        else         rdf_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
-        LAUNCHED();
-        CK(c.kev_record(st));
+        for (int g0 = 0; g0 < nGroups; g0 += groupsPerBatch) {
+            a.groupBase = g0;
+            a.nGroups = std::min(groupsPerBatch, nGroups - g0);
+            a.counts = d_counts + (size_t)g0 * nBins;
+            NvtxRange nv("nda:rdf_tc_kernel", c.cfg.nvtx);
+            CK(c.kev_record(st));
+            if (grouped) rdf_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(a);
+            else         rdf_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(a);
+            LAUNCHED();
+            CK(c.kev_record(st));
+        }
     }
     return NDA_OK;
 }
@@ -451,7 +583,10 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
     const int nAPad = round_up(outSize, TC_SPS * TC_SBLK);     // whole two-block stages
     const int nBPad = round_up(refSize, TC_RBLK);
     const size_t bytesPerFrame = ((size_t)nAPad + nBPad) * (16 + 32);
-    const int pass = frames_per_pass(bytesPerFrame, fe - fb);
+    int pass = frames_per_pass(bytesPerFrame, fe - fb);
+    // NDA_SUBPASS_FRAMES: frame sub-passes small enough that what pack / embed write is still in the 126 MB L2
+    // when the pair kernel reads it, and is overwritten there by the next sub-pass before it reaches DRAM
+    if (c.cfg.subpassFrames > 0) pass = std::min(pass, c.cfg.subpassFrames);
     CK(L.packA.reserve((size_t)nAPad * pass * sizeof(float4)));
     CK(L.packB.reserve((size_t)nBPad * pass * sizeof(float4)));
     CK(L.embA.reserve((size_t)nAPad * pass * 32));
@@ -470,12 +605,10 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
     g.stats = stats;
     g.origInStage = 0;
     g.trace = nullptr;
-    if (const char *e = getenv("NDA_TC_TRACE")) {              // debugging aid: clock64 trace of CTA 0 (tools/tc_trace.py)
-        if (atoi(e) == 1) {
-            CK(c.sum.reserve(256 * 32 * 8));
-            CK(cudaMemsetAsync(c.sum.p, 0, 256 * 32 * 8, st));
-            g.trace = c.sum.as<long long>();
-        }
+    if (c.cfg.tcTrace == 1) {                                  // debugging aid: clock64 trace of CTA 0 (tools/tc_trace.py)
+        CK(c.sum.reserve(256 * 32 * 8));
+        CK(cudaMemsetAsync(c.sum.p, 0, 256 * 32 * 8, st));
+        g.trace = c.sum.as<long long>();
     }
     tc_chunking(g, c.numSMs, pass, 16, TC_WITHIN_MAX_STEPS);   // a warp records at most one (step, lanes) entry per step
     a.wordsPerFrame = words;
@@ -499,9 +632,9 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
         g.B = L.packB.as<float4>();
         // the "sure" shortcut needs the pure predicate to be what the reference computes: with the literal
         // per-axis early-outs (getWithin.cpp:64-71) that holds for distance >= 1 (SURVEY B-2)
-        const double sureD2 = (!a.literal || d2 >= 1.0f) && !getenv("NDA_TC_NO_SURE") ? (double)d2 : -1.0;
+        const double sureD2 = (!a.literal || d2 >= 1.0f) && !c.cfg.tcNoSure ? (double)d2 : -1.0;
         prep_frames_tc_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T, L.fp.as<FrameParams>(),
-                                                                sureD2, tc_range_factor() * 1.2, L.thrDot.as<TcFrame>(), stats);
+                                                                sureD2, c.cfg.tcRangeFactor * 1.2, L.thrDot.as<TcFrame>(), stats);
         LAUNCHED();
         rc = launch_embed(st, g.B, nBPad, nFc, d_cell, f0, L.thrDot.as<TcFrame>(), L.embB.as<__half>(), 0);
         if (rc) return rc;
@@ -511,10 +644,13 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
         if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
         g.nItems = (unsigned)items;
         const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)c.numSMs);
-        CK(c.kev_record(st));
-        within_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
-        LAUNCHED();
-        CK(c.kev_record(st));
+        {
+            NvtxRange nv("nda:within_tc_kernel", c.cfg.nvtx);
+            CK(c.kev_record(st));
+            within_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+            LAUNCHED();
+            CK(c.kev_record(st));
+        }
     }
     return NDA_OK;
 }
@@ -529,14 +665,14 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
     if (nGroups < 1) nGroups = 1;
     const bool grouped = d_gid != nullptr;
     if (!grouped) nGroups = 1;
-    if (filter_tc_requested()) {
+    if (c.cfg.filterTc) {
         const double lim0 = (double)nBins * fabs((double)dr);
         const double T0 = lim0 * lim0 * (1.0 + 9.5367431640625e-07);
         const float *hc = nullptr;
         int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
         if (rc0) return rc0;
-        const bool okTc = tc_frames_eligible(hc, fb, fe, T0, 1.0, n1, n2);
-        if (getenv("NDA_DEBUG")) fprintf(stderr, "[nda] rdf: tensor filter %s (T %.3f, frames %d..%d, cell0 %.2f %.2f %.2f)\n",
+        const bool okTc = tc_frames_eligible(c.cfg, hc, fb, fe, T0, 1.0, n1, n2);
+        if (c.cfg.debug) fprintf(stderr, "[nda] rdf: tensor filter %s (T %.3f, frames %d..%d, cell0 %.2f %.2f %.2f)\n",
                                          okTc ? "on" : "off", T0, fb, fe, hc[3 * (size_t)fb], hc[3 * (size_t)fb + 1], hc[3 * (size_t)fb + 2]);
         if (okTc) {
             g_last_filter.store(100);
@@ -544,21 +680,23 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
                               sameSel, dr, d_idx1, d_idx2, T0);
         }
     }
-    const size_t H = (size_t)nGroups * nBins;
     // shared memory: as many warp-private histogram copies as still allow PAIR_MIN_CTAS CTAs per SM
     const size_t perCta = ((size_t)227 * 1024) / PAIR_MIN_CTAS - 1024;
     const int bTile = grouped ? PAIR_BTILE_GROUPED : PAIR_BTILE;
     const size_t base = pair_smem_base(bTile);
     size_t histBudget = (perCta > base) ? perCta - base : 0;
-    int copies = (int)std::min<size_t>(PAIR_WARPS, histBudget / (H * 4));
+    // groups in batches that fit the shared histogram (see dev_rdf_tc)
+    const size_t maxCells = (c.smemOptin > base ? c.smemOptin - base : 0) / 4;
+    if ((size_t)nBins > maxCells)
+        return fail(NDA_ERR_ARG, "outSize = %d histogram cells do not fit in shared memory (max %zu)", nBins, maxCells);
+    const int groupsPerBatch = (int)std::min<size_t>((size_t)nGroups, maxCells / (size_t)nBins);
+    const size_t Hb = (size_t)groupsPerBatch * nBins;
+    int copies = (int)std::min<size_t>(PAIR_WARPS, histBudget / (Hb * 4));
     if (copies < 1) copies = 1;
-    const size_t smem = base + (size_t)copies * H * 4;
-    if (smem > c.smemOptin)
-        return fail(NDA_ERR_ARG, "nGroups*outSize = %zu histogram cells do not fit in shared memory (max %zu)",
-                    H, (c.smemOptin - base) / 4);
+    const size_t smem = base + (size_t)copies * Hb * 4;
     const int n1Pad = sameSel ? round_up(n1, PAIR_BTILE) : round_up(n1, PAIR_ATILE);
     const int n2Pad = sameSel ? n1Pad : round_up(n2, PAIR_BTILE);
-    const int filter = filter_kind();
+    const int filter = c.cfg.filterKind;
     g_last_filter.store(filter);
     const bool fold = filter != kFilterRint;                 // wrapped copies needed
     const int pairLayout = is_fold2(filter) ? 1 : 0;
@@ -585,9 +723,9 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
     a.n1 = n1; a.n1Pad = n1Pad; a.n2 = n2; a.n2Pad = n2Pad;
     a.nATiles = (n1 + PAIR_ATILE - 1) / PAIR_ATILE;
     a.nBTiles = (n2 + bTile - 1) / bTile;
-    a.counts = d_counts; a.nBins = nBins; a.nGroups = nGroups; a.histCopies = copies;
+    a.counts = d_counts; a.nBins = nBins; a.nGroups = groupsPerBatch; a.groupBase = 0; a.histCopies = copies;
     a.sameSel = sameSel ? 1 : 0; a.dr = dr;
-    a.fastStrict = getenv("NDA_STRICT_SLOW") ? 0 : 1;
+    a.fastStrict = c.cfg.strictSlow ? 0 : 1;
     a.workCounter = work; a.stats = stats;
 
     int ctasPerSM = 0;
@@ -598,7 +736,7 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
 #undef NDA_RDF_CASE
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kfn, PAIR_THREADS, smem));
-    ctasPerSM = tuned_ctas(ctasPerSM);
+    ctasPerSM = tuned_ctas(c.cfg, ctasPerSM);
     // B chunk per work item: aim at >= 16 items per resident CTA so the dynamic scheduler can
     // balance the triangular (sameSel) workload, but keep an item >= 2 tiles (~1e6 pairs)
     {
@@ -635,13 +773,20 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
         if (items > 0xfffffff0ull) return fail(NDA_ERR_ARG, "too many work items in one pass");
         a.nItems = (unsigned)items;
         const int grid = (int)std::min<unsigned long long>(items, (unsigned long long)ctasPerSM * c.numSMs);
-        CK(c.kev_record(st));
 #define NDA_RDF_LAUNCH(G, F) case F: rdf_kernel<G, F><<<grid, PAIR_THREADS, smem, st>>>(a); break;
-        if (grouped) switch (filter) { NDA_RDF_LAUNCH(true, 0) NDA_RDF_LAUNCH(true, 1) NDA_RDF_LAUNCH(true, 2) NDA_RDF_LAUNCH(true, 3) NDA_RDF_LAUNCH(true, 4) NDA_RDF_LAUNCH(true, 5) }
-        else         switch (filter) { NDA_RDF_LAUNCH(false, 0) NDA_RDF_LAUNCH(false, 1) NDA_RDF_LAUNCH(false, 2) NDA_RDF_LAUNCH(false, 3) NDA_RDF_LAUNCH(false, 4) NDA_RDF_LAUNCH(false, 5) }
+        for (int g0 = 0; g0 < nGroups; g0 += groupsPerBatch) {
+            a.groupBase = g0;
+            a.nGroups = std::min(groupsPerBatch, nGroups - g0);
+            a.counts = d_counts + (size_t)g0 * nBins;
+            if (g0 > 0) CK(cudaMemsetAsync(work, 0, 8, st));
+            NvtxRange nv("nda:rdf_kernel", c.cfg.nvtx);
+            CK(c.kev_record(st));
+            if (grouped) switch (filter) { NDA_RDF_LAUNCH(true, 0) NDA_RDF_LAUNCH(true, 1) NDA_RDF_LAUNCH(true, 2) NDA_RDF_LAUNCH(true, 3) NDA_RDF_LAUNCH(true, 4) NDA_RDF_LAUNCH(true, 5) }
+            else         switch (filter) { NDA_RDF_LAUNCH(false, 0) NDA_RDF_LAUNCH(false, 1) NDA_RDF_LAUNCH(false, 2) NDA_RDF_LAUNCH(false, 3) NDA_RDF_LAUNCH(false, 4) NDA_RDF_LAUNCH(false, 5) }
+            LAUNCHED();
+            CK(c.kev_record(st));
+        }
 #undef NDA_RDF_LAUNCH
-        LAUNCHED();
-        CK(c.kev_record(st));
     }
     return NDA_OK;
 }
@@ -655,13 +800,13 @@ static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all,
     if (outSize <= 0 || fe <= fb) return NDA_OK;
     const int words = (outSize + 31) / 32;
     bool doneTc = false;
-    if (refSize > 0 && filter_tc_requested()) {
+    if (refSize > 0 && c.cfg.filterTc) {
         const float d2t = distance * distance;
         const double Tt = (double)d2t * (1.0 + 9.5367431640625e-07);
         const float *hc = nullptr;
         int rc0 = host_cell_view(c, st, h_cell, d_cell, fb, fe, &hc);
         if (rc0) return rc0;
-        if (tc_frames_eligible(hc, fb, fe, Tt, 1.0, outSize, refSize)) {
+        if (tc_frames_eligible(c.cfg, hc, fb, fe, Tt, 1.0, outSize, refSize)) {
             rc0 = dev_within_tc(c, L, st, d_all, nF, d_refSel, refSize, d_outSel, outSize, d_bits, d_cell, d2t, Tt, fb, fe);
             if (rc0) return rc0;
             doneTc = true;
@@ -674,7 +819,7 @@ static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all,
     } else {
         const int nAPad = round_up(outSize, PAIR_ATILE);
         const int nBPad = round_up(refSize, PAIR_BTILE);
-        const int filter = filter_kind();
+        const int filter = c.cfg.filterKind;
         g_last_filter.store(filter);
         const bool fold = filter != kFilterRint;             // wrapped copies needed
         const int pairLayout = is_fold2(filter) ? 1 : 0;
@@ -715,7 +860,7 @@ static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all,
         CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int ctasPerSM = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSM, kfn, PAIR_THREADS, smem));
-        ctasPerSM = tuned_ctas(ctasPerSM);
+        ctasPerSM = tuned_ctas(c.cfg, ctasPerSM);
 
         for (int f0 = fb; f0 < fe; f0 += pass) {
             const int nFc = std::min(pass, fe - f0);
@@ -766,12 +911,26 @@ static int dev_distances(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, c
                          const int *d_idx1 = nullptr, const int *d_idx2 = nullptr)
 {
     if (n1 <= 0 || n2 <= 0 || fe <= fb) return NDA_OK;
-    const int chunks = (fe - fb + DIST_FCHUNK - 1) / DIST_FCHUNK;
     const int zt = (n1 + DIST_NA - 1) / DIST_NA;
-    if (chunks > 65535 || zt > 65535) return fail(NDA_ERR_ARG, "selection or frame range too large for one launch");
-    dim3 grid((n2 + 7) / 8, chunks, zt);
+    if (zt > 65535) return fail(NDA_ERR_ARG, "selection too large for one launch");
+    const void *kfn = (const void *)distances_kernel;
+    const size_t smem = sizeof(DistSmem);
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, DIST_JT, smem));
+    const long long slots = (long long)std::max(occ, 1) * c.numSMs;
+    // frames per work item: as long as possible (the pipeline prologue and the atomics are per item)
+    // while every resident block still gets >= 3 items
+    const long long jTiles = (n2 + DIST_JT - 1) / DIST_JT;
+    int stages = 16;
+    while (stages > 1 && jTiles * zt * (((long long)(fe - fb) + stages * DIST_FS - 1) / (stages * DIST_FS)) < 3 * slots) stages >>= 1;
+    const long long nFChunks = ((long long)(fe - fb) + (long long)stages * DIST_FS - 1) / ((long long)stages * DIST_FS);
+    const long long items = jTiles * nFChunks;
+    if (items > 0xfffffff0ll) return fail(NDA_ERR_ARG, "too many work items in one launch");
+    dim3 grid((unsigned)std::min<long long>(items, std::max<long long>(1, slots / zt)), zt);
     CK(c.kev_record(st));
-    distances_kernel<<<grid, 256, 0, st>>>(d_sel1, n1, d_sel2, n2, d_cell, nF, fb, fe, sameSel ? 1 : 0, d_sum, d_idx1, d_idx2);
+    distances_kernel<<<grid, DIST_JT, smem, st>>>(d_sel1, n1, d_sel2, n2, d_cell, nF, fb, fe, sameSel ? 1 : 0, d_sum,
+                                                  d_idx1, d_idx2, stages, (int)nFChunks, (unsigned)items, -0.0f);
     LAUNCHED();
     CK(c.kev_record(st));
     return NDA_OK;
@@ -893,7 +1052,7 @@ struct Uploader {
     }
 
     // choose the chunking, reserve device / staging buffers, mark both buffers free
-    int begin(int maxChunks, const char *envOverride)
+    int begin(int maxChunks, int chunkOverride)
     {
         const int nFc = fe - fb;
         size_t bytesPerFrame = 0;
@@ -902,7 +1061,7 @@ struct Uploader {
         // ~20 MB per chunk: with the tensor-core kernels a chunk's compute is a fraction of its copy, and
         // every chunk costs ~30 us of copy set-up (measured: 110 MB in 5-6 chunks 2.6 ms, in 16 chunks 3.0 ms)
         nChunks = (int)std::min<size_t>((size_t)maxChunks, std::max<size_t>(1, bytesPerFrame * nFc / ((size_t)20 << 20)));
-        if (envOverride) if (const char *e = getenv(envOverride)) { int v = atoi(e); if (v >= 1) nChunks = v; }
+        if (chunkOverride >= 1) nChunks = chunkOverride;
         nChunks = std::max(1, std::min(nChunks, nFc));
         chunk = (nFc + nChunks - 1) / nChunks;
         const int maxChunk = (int)std::max<size_t>(1, ((size_t)3 << 30) / bytesPerFrame);   // <= 3 GB per buffer
@@ -913,8 +1072,8 @@ struct Uploader {
         // The copies are the bottleneck, so what the caller waits for after the last byte has arrived is the
         // compute (and the host post-processing) of the LAST chunk: taper the tail -- one more chunk, the last
         // two of 1/2 and 1/4 of the regular size (NDA_NO_TAPER=1 keeps them uniform).
-        static const bool noTaper = getenv("NDA_NO_TAPER") != nullptr;
-        static const int taperLevels = getenv("NDA_TAPER_LEVELS") ? std::max(1, std::min(4, atoi(getenv("NDA_TAPER_LEVELS")))) : 2;
+        const bool noTaper = c.cfg.noTaper != 0;
+        const int taperLevels = c.cfg.taperLevels;
         if (taperTail && !noTaper && nChunks >= 3 && nChunks < maxChunks + 1 && chunk * 4 <= maxChunk * 3 && nFc >= 16 * nChunks) {
             // regular chunks of one unit, then `levels` chunks of 1/2, 1/4, ... of a unit (the last one takes what is left)
             const int levels = std::min(taperLevels, nChunks - 1);
@@ -961,6 +1120,7 @@ struct Uploader {
     // enqueue the upload of chunk k on the copy stream (gathering on the host first if pageable)
     int issue(int k)
     {
+        NvtxRange nv("nda:upload_chunk", c.cfg.nvtx);
         const int b = k & 1, a0 = f0(k), wc = f1(k) - a0;
         const size_t w = (size_t)wc * 12;
         bool anyStage = false;
@@ -973,7 +1133,7 @@ struct Uploader {
             const float *src = a.host;
             const int nRuns = (int)a.runs.size();
             const long long nFl = nF;
-            #pragma omp parallel num_threads(g_host_threads) if (a.nRows * w > (1u << 20))
+            #pragma omp parallel num_threads(c.hostThreads) if (a.nRows * w > (1u << 20))
             {
                 #pragma omp for schedule(static) nowait
                 for (int r = 0; r < a.nRows; ++r) {
@@ -990,7 +1150,7 @@ struct Uploader {
         // strided 2-D DMA from pinned memory runs at about half the link rate on one copy engine,
         // so the rows of every run are split over two copy streams (NDA_COPY_STREAMS=1 disables)
         // (rows of >= 2 KB reach the link rate on one engine; NDA_COPY_STREAMS=1|2 overrides)
-        static const int csEnv = getenv("NDA_COPY_STREAMS") ? atoi(getenv("NDA_COPY_STREAMS")) : 0;
+        const int csEnv = c.cfg.copyStreams;
         const bool twoStreams = csEnv == 2 || (csEnv != 1 && w < 2048);
         bool usedSecond = false;
         for (size_t i = 0; i < arr.size(); ++i) {
@@ -1079,10 +1239,9 @@ struct HostTrace {
     const char *what;
     std::chrono::steady_clock::time_point t0, last;
     std::string line;
-    explicit HostTrace(const char *w) : what(w)
+    HostTrace(const char *w, int debugLevel) : what(w)
     {
-        static const bool e = getenv("NDA_DEBUG") && atoi(getenv("NDA_DEBUG")) >= 2;
-        on = e;
+        on = debugLevel >= 2;
         if (on) t0 = last = std::chrono::steady_clock::now();
     }
     void mark(const char *name)
@@ -1103,8 +1262,461 @@ struct HostTrace {
 };
 
 // ------------------------------------------------------------------------------------------
+// several devices in ONE process: one host thread and one context per device, frames split
+// [floor(g nF / G), floor((g+1) nF / G)), every device pulling only its frame columns over its own
+// link; the partial histograms / float64 sums are merged by ONE ncclAllReduce on the compute streams
+// (ncclCommInitAll; NCCL is dlopen()ed so the library carries no link-time dependency on it).
+// within needs no collective: devices own disjoint frame columns of the mask.
+// ------------------------------------------------------------------------------------------
+struct NcclApi {
+    bool tried = false, ok = false;
+    void *handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::map<std::vector<int>, std::vector<ncclComm_t>> comms;
+    std::mutex mu;
+};
+static NcclApi g_nccl;
+
+static bool nccl_load()
+{
+    NcclApi &n = g_nccl;
+    if (n.tried) return n.ok;
+    n.tried = true;
+    // the copy torch (or the application) has already mapped wins: two NCCL builds in one process do not mix
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+        n.handle = dlopen(name, RTLD_NOW | RTLD_NOLOAD);
+        if (n.handle) break;
+    }
+    if (!n.handle)
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            n.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (n.handle) break;
+        }
+    if (!n.handle) return false;
+    n.CommInitAll = reinterpret_cast<decltype(n.CommInitAll)>(dlsym(n.handle, "ncclCommInitAll"));
+    n.CommDestroy = reinterpret_cast<decltype(n.CommDestroy)>(dlsym(n.handle, "ncclCommDestroy"));
+    n.AllReduce = reinterpret_cast<decltype(n.AllReduce)>(dlsym(n.handle, "ncclAllReduce"));
+    n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(dlsym(n.handle, "ncclGetErrorString"));
+    n.ok = n.CommInitAll && n.CommDestroy && n.AllReduce && n.GetErrorString;
+    return n.ok;
+}
+
+// communicators of a device list, created on first use; nullptr: no NCCL (the caller sums on the host)
+static const std::vector<ncclComm_t> *nccl_comms(const std::vector<int> &devs, const Config &cfg, int *rcOut)
+{
+    *rcOut = NDA_OK;
+    if (cfg.collective == 2) return nullptr;
+    std::lock_guard<std::mutex> lk(g_nccl.mu);
+    if (!nccl_load()) {
+        if (cfg.collective == 1) *rcOut = fail(NDA_ERR_CUDA, "NDA_COLLECTIVE=nccl but libnccl.so.2 could not be loaded: %s", dlerror());
+        return nullptr;
+    }
+    auto it = g_nccl.comms.find(devs);
+    if (it == g_nccl.comms.end()) {
+        std::vector<ncclComm_t> cs(devs.size());
+        const ncclResult_t r = g_nccl.CommInitAll(cs.data(), (int)devs.size(), devs.data());
+        if (r != ncclSuccess) {
+            if (cfg.collective == 1) *rcOut = fail(NDA_ERR_CUDA, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(r));
+            return nullptr;
+        }
+        it = g_nccl.comms.emplace(devs, std::move(cs)).first;
+    }
+    return &it->second;
+}
+
+struct HostBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int n, waiting = 0, gen = 0;
+    explicit HostBarrier(int n_) : n(n_) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const int g = gen;
+        if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+// devices of the calling thread (nda_set_devices / nda_set_device / NDA_DEVICES / the current device)
+static int devices_of_thread(std::vector<int> &out)
+{
+    if (g_devs.empty()) {
+        static const std::vector<int> fromEnv = [] {
+            std::vector<int> v;
+            const char *e = getenv("NDA_DEVICES");
+            if (!e || !*e) return v;
+            int n = 0;
+            if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return v; }
+            if (!strcmp(e, "all")) { for (int i = 0; i < n; ++i) v.push_back(i); return v; }
+            for (const char *p = e; *p;) {
+                char *end = nullptr;
+                const long d = strtol(p, &end, 10);
+                if (end == p) break;
+                if (d >= 0 && d < n && std::find(v.begin(), v.end(), (int)d) == v.end()) v.push_back((int)d);
+                p = (*end == ',') ? end + 1 : end;
+            }
+            return v;
+        }();
+        if (!fromEnv.empty() && g_dev < 0) { g_devs = fromEnv; g_dev = g_devs[0]; }
+        else {
+            Ctx *c;
+            const int rc = ctx_get(&c);
+            if (rc) return rc;
+            g_devs.assign(1, g_dev);
+        }
+    }
+    out = g_devs;
+    return NDA_OK;
+}
+
+struct Shard { int dev, fb, fe; };
+
+// frames [fb, fe) over the thread's devices (no more devices than frames)
+static int plan_shards(int fb, int fe, std::vector<Shard> &sh)
+{
+    std::vector<int> devs;
+    const int rc = devices_of_thread(devs);
+    if (rc) return rc;
+    const int nFc = fe - fb;
+    const int G = (int)std::max<size_t>(1, std::min<size_t>(devs.size(), (size_t)std::max(nFc, 1)));
+    sh.clear();
+    for (int g = 0; g < G; ++g)
+        sh.push_back({devs[g], fb + (int)((long long)g * nFc / G), fb + (int)((long long)(g + 1) * nFc / G)});
+    return NDA_OK;
+}
+
+// one host thread per shard; fn(g, ctx) runs with the shard's device current and its context locked.
+// Returns the first failure (message copied into the caller's nda_last_error()).
+template <class Fn>
+static int run_shards(const std::vector<Shard> &sh, Fn fn)
+{
+    const int G = (int)sh.size();
+    std::vector<int> rcs((size_t)G, NDA_OK);
+    std::vector<std::string> errs((size_t)G);
+    const int callerDev = g_dev;
+    auto body = [&](int g) {
+        g_dev = sh[g].dev;
+        Ctx *c = nullptr;
+        int rc = ctx_for(sh[g].dev, &c);
+        if (!rc) {
+            std::lock_guard<std::mutex> lk(c->mu);
+            begin_call(*c, G);
+            rc = fn(g, *c);
+        }
+        rcs[g] = rc;
+        if (rc) errs[g] = g_err;
+    };
+    if (G == 1) body(0);
+    else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g) th.emplace_back(body, g);
+        for (auto &t : th) t.join();
+    }
+    g_dev = callerDev;
+    if (callerDev >= 0) cudaSetDevice(callerDev);
+    for (int g = 0; g < G; ++g)
+        if (rcs[g]) { g_err = errs[g]; return rcs[g]; }
+    return NDA_OK;
+}
+
+// merge of per-device partials that sit in device buffers buf[g] (count elements of type T: u64 or f64) and
+// delivery into `host`: ONE ncclAllReduce per device on its compute stream, then device 0 copies out; without
+// NCCL every device copies its partial out and the host adds.  Called by every shard's thread.
+struct Merge {
+    const std::vector<ncclComm_t> *comms = nullptr;
+    HostBarrier *bar = nullptr;
+    std::atomic<int> failed{0};
+    std::vector<std::vector<unsigned char>> parts;       // host-sum route
+};
+
+template <class T>
+static int merge_partials(Merge &m, int g, int G, Ctx &c, cudaStream_t st, T *d_buf, size_t count, T *host, int rcSoFar)
+{
+    if (G == 1) {
+        if (rcSoFar) return rcSoFar;
+        CK(cudaMemcpyAsync(host, d_buf, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return NDA_OK;
+    }
+    if (rcSoFar) m.failed.store(1);
+    m.bar->wait();                                         // every device's work is enqueued (or has failed)
+    if (m.failed.load()) return rcSoFar ? rcSoFar : fail(NDA_ERR_CUDA, "another device of this call failed");
+    if (m.comms) {
+        NvtxRange nv("nda:allreduce", c.cfg.nvtx);
+        const ncclDataType_t dt = sizeof(T) == 8 && std::is_floating_point<T>::value ? ncclFloat64 : ncclUint64;
+        const ncclResult_t r = g_nccl.AllReduce(d_buf, d_buf, count, dt, ncclSum, (*m.comms)[g], st);
+        if (r != ncclSuccess) return fail(NDA_ERR_CUDA, "ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+        if (g == 0) CK(cudaMemcpyAsync(host, d_buf, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        g_last_collective.store(1);
+    } else {
+        m.parts[g].resize(count * sizeof(T));
+        cudaError_t e = cudaMemcpyAsync(m.parts[g].data(), d_buf, count * sizeof(T), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) m.failed.store(1);
+        m.bar->wait();
+        if (e != cudaSuccess) return fail(NDA_ERR_CUDA, "copy of a partial result failed: %s", cudaGetErrorString(e));
+        if (m.failed.load()) return fail(NDA_ERR_CUDA, "another device of this call failed");
+        if (g == 0) {
+            for (size_t i = 0; i < count; ++i) {
+                T acc = 0;
+                for (int q = 0; q < G; ++q) acc += reinterpret_cast<const T *>(m.parts[q].data())[i];
+                host[i] = acc;
+            }
+        }
+        g_last_collective.store(2);
+    }
+    return NDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the three host paths on ONE device and ONE frame range (the multi-device entry points call them per shard)
+// ------------------------------------------------------------------------------------------
+// histogram of frames [fb, fe) accumulated into c.counts (device, zeroed here); stays on the device
+static int rdf_shard(Ctx &c, const float *sel1, int n1, const float *sel2, int n2, const int *groupId, int nGroups,
+                     int outSize, const float *cellDims, int nF, int fb, int fe, int sameSel, float dr, float *msOut)
+{
+    cudaStream_t st = c.stream;
+    const size_t H = (size_t)nGroups * outSize;
+    CK(c.counts.reserve(H * 8));
+    CK(c.cell.reserve((size_t)nF * 12));
+    CK(lane_acquire(c.lane[0], st));
+    CK(lane_acquire(c.lane[1], c.lane[1].stream));
+    CK(cudaMemsetAsync(c.counts.p, 0, H * 8, st));
+    CK(reset_stats(c, st));
+    if (fe <= fb) return NDA_OK;
+    if (groupId) CK(c.gid.reserve((size_t)n2 * 4));
+    {
+        const SetupItem items[2] = {{c.cell.p, cellDims, (size_t)nF * 12},
+                                    {groupId ? c.gid.p : nullptr, groupId, groupId ? (size_t)n2 * 4 : 0}};
+        int rc = upload_setup(c, items, 2);
+        if (rc) return rc;
+        CK(cudaStreamWaitEvent(st, c.evSetupCopy, 0));
+    }
+    // frame chunks: the upload of chunk k+1 overlaps pack + kernel of chunk k
+    Uploader up(c, nF, fb, fe);
+    up.add(sel1, n1);
+    if (!sameSel) up.add(sel2, n2);
+    int rc = up.begin(8, c.cfg.uploadChunks);
+    if (rc) return rc;
+    CK(cudaEventRecord(c.ev0, st));
+    CK(cudaEventRecord(c.evSetup, st));                    // lane 1 must see counts / cell / gid initialised
+    CK(cudaStreamWaitEvent(c.lane[1].stream, c.evSetup, 0));
+    rc = up.issue(0);
+    if (rc) return rc;
+    for (int k = 0; k < up.nChunks; ++k) {
+        const int wc = up.f1(k) - up.f0(k);
+        Ctx::Lane &L = c.lane[k & 1];                      // alternate lanes: kernel k+1 fills the tail of kernel k
+        rc = up.acquire(k, L.stream);
+        if (rc) return rc;
+        rc = dev_rdf(c, L, L.stream, up.dev(0, k), n1, sameSel ? up.dev(0, k) : up.dev(1, k), n2,
+                     groupId ? c.gid.as<int>() : nullptr, nGroups, c.counts.as<unsigned long long>(), outSize,
+                     c.cell.as<float>() + (size_t)up.f0(k) * 3, wc, 0, wc, sameSel, dr, nullptr, nullptr,
+                     cellDims + (size_t)up.f0(k) * 3);
+        if (rc) return rc;
+        rc = up.release(k, L.stream);
+        if (rc) return rc;
+        if (k + 1 < up.nChunks) { rc = up.issue(k + 1); if (rc) return rc; }
+    }
+    CK(lane_release(c.lane[1], c.lane[1].stream));
+    CK(cudaEventRecord(c.evLaneJoin, c.lane[1].stream));
+    CK(cudaStreamWaitEvent(st, c.evLaneJoin, 0));
+    CK(lane_release(c.lane[0], st));
+    CK(cudaEventRecord(c.ev1, st));
+    if (msOut) {
+        CK(cudaEventSynchronize(c.ev1));
+        CK(cudaEventElapsedTime(msOut, c.ev0, c.ev1));
+    }
+    return NDA_OK;
+}
+
+// float64 sums of frames [fb, fe) accumulated into c.sum (device, zeroed here); stays on the device
+static int distances_shard(Ctx &c, const float *sel1, int n1, const float *sel2, int n2, const float *cellDims,
+                           int nF, int fb, int fe, int sameSel)
+{
+    cudaStream_t st = c.stream;
+    const size_t M = (size_t)n1 * n2;
+    CK(c.sum.reserve(M * 8));
+    CK(c.cell.reserve((size_t)nF * 12));
+    CK(cudaMemsetAsync(c.sum.p, 0, M * 8, st));
+    if (fe <= fb) return NDA_OK;
+    {
+        const SetupItem items[1] = {{c.cell.p, cellDims, (size_t)nF * 12}};
+        int rc = upload_setup(c, items, 1);
+        if (rc) return rc;
+        CK(cudaStreamWaitEvent(st, c.evSetupCopy, 0));
+    }
+    Uploader up(c, nF, fb, fe);
+    up.add(sel1, n1);
+    if (!sameSel) up.add(sel2, n2);
+    int rc = up.begin(8, c.cfg.uploadChunks);
+    if (rc) return rc;
+    rc = up.issue(0);
+    if (rc) return rc;
+    for (int k = 0; k < up.nChunks; ++k) {
+        const int wc = up.f1(k) - up.f0(k);
+        rc = up.acquire(k, st);
+        if (rc) return rc;
+        NvtxRange nv("nda:distances_kernel", c.cfg.nvtx);
+        rc = dev_distances(c, st, up.dev(0, k), n1, sameSel ? up.dev(0, k) : up.dev(1, k), n2,
+                           c.sum.as<double>(), c.cell.as<float>() + (size_t)up.f0(k) * 3, wc, 0, wc, sameSel);
+        if (rc) return rc;
+        rc = up.release(k, st);
+        if (rc) return rc;
+        if (k + 1 < up.nChunks) { rc = up.issue(k + 1); if (rc) return rc; }
+    }
+    return NDA_OK;
+}
+
+// cut-off bitmask of frames [fb, fe): rows [0, fe - fb) of `bits` (may be NULL) and columns [fb, fe) of `out`
+// (may be NULL) are written; everything is back on the host when this returns
+static int within_shard(Ctx &c, const float *allAtoms, int nAtoms, int nF, const int *refSel, int refSize,
+                        const int *outSel, int outSelSize, uint32_t *bits, int *out, const float *cellDims,
+                        float distance, int fb, int fe)
+{
+    cudaStream_t st = c.stream;
+    HostTrace ht("within", c.cfg.debug);
+    const int nFc = fe - fb;
+    const int words = (outSelSize + 31) / 32;
+    if (nFc <= 0) return NDA_OK;
+
+    // ---- which rows travel, and the selections re-expressed in uploaded-row numbers
+    Ctx::WithinPlan &pl = c.plan;
+    const bool samePlan = pl.nAtoms == nAtoms && (int)pl.refSel.size() == refSize && (int)pl.outSel.size() == outSelSize &&
+                          (refSize == 0 || memcmp(pl.refSel.data(), refSel, (size_t)refSize * 4) == 0) &&
+                          memcmp(pl.outSel.data(), outSel, (size_t)outSelSize * 4) == 0;
+    if (!samePlan) {
+        pl.nAtoms = -1;
+        plan_rows(refSel, refSize, outSel, outSelSize, nAtoms, pl.remap, pl.runs, pl.nRows);
+        pl.ref2.resize((size_t)std::max(refSize, 1));
+        pl.out2.resize((size_t)outSelSize);
+        for (int i = 0; i < refSize; ++i) pl.ref2[i] = pl.remap[refSel[i]];
+        for (int i = 0; i < outSelSize; ++i) pl.out2[i] = pl.remap[outSel[i]];
+        pl.refSel.assign(refSel, refSel + refSize);
+        pl.outSel.assign(outSel, outSel + outSelSize);
+        pl.nAtoms = nAtoms;
+    }
+    const std::vector<int> &ref2 = pl.ref2, &out2 = pl.out2;
+    const int nRows = pl.nRows;
+
+    // ---- frame chunks: copy of chunk k+1 overlaps pack + kernel of chunk k (two raw buffers)
+    Uploader up(c, nF, fb, fe);
+    up.add(allAtoms, nRows, pl.runs);
+    int rc = up.begin(6, c.cfg.withinChunks);
+    if (rc) return rc;
+    const int nChunks = up.nChunks;
+    ht.mark("plan");
+    CK(c.cell.reserve((size_t)nF * 12));
+    CK(c.idx1.reserve((size_t)std::max(refSize, 1) * 4));
+    CK(c.idx2.reserve((size_t)outSelSize * 4));
+    {                                                       // ~60 KB on the copy stream, then the first chunk
+        const SetupItem items[3] = {{c.cell.p, cellDims, (size_t)nF * 12},
+                                    {c.idx1.p, ref2.data(), (size_t)refSize * 4},
+                                    {c.idx2.p, out2.data(), (size_t)outSelSize * 4}};
+        rc = upload_setup(c, items, 3);
+        if (rc) return rc;
+    }
+    rc = up.issue(0);                                       // the link is the bottleneck: start it first
+    if (rc) return rc;
+    ht.mark("issue0");
+
+    CK(c.bits.reserve((size_t)nFc * words * 4));
+    CK(c.pinned_reserve((size_t)nFc * words * 4));
+    uint32_t *hbits = reinterpret_cast<uint32_t *>(c.pinned);
+
+    CK(lane_acquire(c.lane[0], st));
+    CK(lane_acquire(c.lane[1], c.lane[1].stream));
+    CK(reset_stats(c, st));
+    CK(cudaStreamWaitEvent(st, c.evSetupCopy, 0));
+    CK(cudaEventRecord(c.ev0, st));
+
+    const int hostThreads = c.hostThreads;
+    (void)hostThreads;                                      // (used by the OpenMP pragma below)
+    auto scatter = [&](int k) {                             // host: set the 1s of chunk k
+        if (!out) return;
+        const int f0 = up.f0(k) - fb, f1 = up.f1(k) - fb;
+        // ~6e5 cache-missing stores for config 2: spread the frames over the host threads
+        #pragma omp parallel for schedule(static) num_threads(hostThreads) if (f1 - f0 >= 16)
+        for (int f = f0; f < f1; ++f) {
+            const uint32_t *row = hbits + (size_t)f * words;
+            for (int w = 0; w < words; ++w) {
+                uint32_t v = row[w];
+                while (v) {                                  // the reference only ever stores 1 (getWithin.cpp:77,83)
+                    const int b = __builtin_ctz(v);
+                    v &= v - 1;
+                    out[(size_t)outSel[w * 32 + b] * nF + fb + f] = 1;
+                }
+            }
+        }
+    };
+
+    CK(cudaEventRecord(c.evSetup, st));                     // lane 1 must see cell / selections uploaded
+    CK(cudaStreamWaitEvent(c.lane[1].stream, c.evSetup, 0));
+    ht.mark("setup");
+    for (int k = 0; k < nChunks; ++k) {
+        const int f0 = up.f0(k), wc = up.f1(k) - f0, buf = k & 1;
+        Ctx::Lane &L = c.lane[buf];                         // alternate lanes: kernel k+1 fills the tail of kernel k
+        cudaStream_t ls = L.stream;
+        rc = up.acquire(k, ls);
+        if (rc) return rc;
+        rc = dev_within(c, L, ls, up.dev(0, k), nRows, wc, c.idx1.as<int>(), refSize, c.idx2.as<int>(), outSelSize,
+                        c.bits.as<unsigned>() + (size_t)(f0 - fb) * words, nullptr,
+                        c.cell.as<float>() + (size_t)f0 * 3, distance, 0, wc, cellDims + (size_t)f0 * 3);
+        if (rc) return rc;
+        rc = up.release(k, ls);
+        if (rc) return rc;
+        if (c.cfg.d2hCopyEngine) {                           // A/B switch: the old way
+            CK(cudaMemcpyAsync(hbits + (size_t)(f0 - fb) * words, c.bits.as<unsigned>() + (size_t)(f0 - fb) * words,
+                               (size_t)wc * words * 4, cudaMemcpyDeviceToHost, ls));
+        } else {                                             // SMs write the pinned buffer: no copy-engine queueing
+            const size_t nW = (size_t)wc * words;
+            copy_words_kernel<<<(unsigned)std::min<size_t>((nW + 255) / 256, 296), 256, 0, ls>>>(
+                c.bits.as<unsigned>() + (size_t)(f0 - fb) * words, hbits + (size_t)(f0 - fb) * words, nW);
+            LAUNCHED();
+        }
+        CK(cudaEventRecord(c.evBits[buf], ls));
+        if (k + 1 < nChunks) { rc = up.issue(k + 1); if (rc) return rc; }   // host gathers k+1 while the GPU works on k
+        ht.mark("enq");
+        if (k > 0) {                                         // ... and scatters chunk k-1
+            CK(cudaEventSynchronize(c.evBits[buf ^ 1]));
+            ht.mark("wait");
+            scatter(k - 1);
+            ht.mark("scat");
+        }
+    }
+    CK(lane_release(c.lane[1], c.lane[1].stream));
+    CK(cudaEventRecord(c.evLaneJoin, c.lane[1].stream));
+    CK(cudaStreamWaitEvent(st, c.evLaneJoin, 0));
+    CK(lane_release(c.lane[0], st));
+    CK(cudaEventRecord(c.ev1, st));
+    ht.mark("loop");
+    CK(cudaStreamSynchronize(st));
+    ht.mark("sync");
+    scatter(nChunks - 1);
+    ht.mark("scatter");
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+    rc = read_stats(c, (double)refSize * outSelSize * nFc, ms);
+    if (rc) return rc;
+    if (bits) memcpy(bits, hbits, (size_t)nFc * words * 4);
+    return NDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
+// lock the calling thread's (first) device for a device-pointer / single-device call
+#define NDA_ENTER()                                                                           \
+    Ctx *c;                                                                                   \
+    int rc = ctx_get(&c);                                                                     \
+    if (rc) return rc;                                                                        \
+    std::lock_guard<std::mutex> lk(c->mu);                                                    \
+    begin_call(*c)
+
 extern "C" {
 
 const char *nda_last_error(void) { return g_err.c_str(); }
@@ -1122,19 +1734,100 @@ int nda_set_device(int device)
     int n = nda_device_count();
     if (device < 0 || device >= n) return fail(NDA_ERR_ARG, "device %d out of range (%d visible)", device, n);
     g_dev = device;
+    g_devs.assign(1, device);
     CK(cudaSetDevice(device));
     return NDA_OK;
 }
 
+int nda_set_devices(const int *devices, int n)
+{
+    const int nd = nda_device_count();
+    if (!devices || n < 1 || n > 16) return fail(NDA_ERR_ARG, "need 1..16 devices");
+    std::vector<int> v;
+    for (int i = 0; i < n; ++i) {
+        if (devices[i] < 0 || devices[i] >= nd) return fail(NDA_ERR_ARG, "device %d out of range (%d visible)", devices[i], nd);
+        if (std::find(v.begin(), v.end(), devices[i]) != v.end()) return fail(NDA_ERR_ARG, "device %d listed twice", devices[i]);
+        v.push_back(devices[i]);
+    }
+    g_devs = v;
+    g_dev = v[0];
+    CK(cudaSetDevice(g_dev));
+    return NDA_OK;
+}
+
+int nda_get_devices(int *devices, int capacity)
+{
+    std::vector<int> v;
+    const int rc = devices_of_thread(v);
+    if (rc) return -1;
+    for (int i = 0; i < (int)v.size() && i < capacity; ++i) devices[i] = v[i];
+    return (int)v.size();
+}
+
 int nda_get_device(void) { return g_dev; }
 int nda_last_filter(void) { return g_last_filter.load(); }
+int nda_last_collective(void) { return g_last_collective.load(); }
 
-// debugging aid (NDA_TC_TRACE=1): copies the clock64 trace of the last within call, 256 x 32 values
+int nda_set_option(const char *name, const char *value)
+{
+    if (!name) return fail(NDA_ERR_ARG, "null option name");
+    config_init();
+    std::lock_guard<std::mutex> lk(g_cfg_mutex);
+    if (!apply_option(g_cfg, name, value)) return fail(NDA_ERR_ARG, "unknown option %s", name);
+    return NDA_OK;
+}
+
+// releases every device buffer, pinned staging area, stream, event and communicator the library holds;
+// the next call builds them again
+int nda_shutdown(void)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_nccl.mu);
+        for (auto &kv : g_nccl.comms)
+            for (ncclComm_t cm : kv.second) g_nccl.CommDestroy(cm);
+        g_nccl.comms.clear();
+    }
+    std::lock_guard<std::mutex> lkInit(g_ctx_init_mutex);
+    for (int d = 0; d < 16; ++d) {
+        Ctx &c = g_ctx[d];
+        if (!c.ready) continue;
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaDeviceSynchronize();
+        auto freeBuf = [](DevBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
+        for (auto &L : c.lane) {
+            for (DevBuf *b : {&L.packA, &L.packB, &L.packAw, &L.packBw, &L.fp, &L.maxAbs, &L.ctl, &L.embA, &L.embB, &L.thrDot}) freeBuf(*b);
+            if (L.evBusy) cudaEventDestroy(L.evBusy);
+            L.evBusy = nullptr;
+        }
+        for (auto &r : c.raw) for (auto &b : r) freeBuf(b);
+        for (DevBuf *b : {&c.cell, &c.idx1, &c.idx2, &c.gid, &c.counts, &c.bits, &c.sum}) freeBuf(*b);
+        for (void **h : {&c.pinned, &c.setupStage, &c.stage[0], &c.stage[1]}) { if (*h) cudaFreeHost(*h); *h = nullptr; }
+        c.pinnedCap = c.setupCap = c.stageCap[0] = c.stageCap[1] = 0;
+        for (cudaEvent_t *e : {&c.evJoin, &c.ev0, &c.ev1, &c.evCopied[0], &c.evCopied[1], &c.evDone[0], &c.evDone[1],
+                               &c.evBits[0], &c.evBits[1], &c.evSetup, &c.evLaneJoin, &c.evSetupCopy}) {
+            if (*e) cudaEventDestroy(*e);
+            *e = nullptr;
+        }
+        for (cudaEvent_t e : c.kev) cudaEventDestroy(e);
+        c.kev.clear();
+        c.kevUsed = 0;
+        if (c.lane[1].stream) cudaStreamDestroy(c.lane[1].stream);
+        for (cudaStream_t *s : {&c.stream, &c.copyStream, &c.copyStream2}) { if (*s) cudaStreamDestroy(*s); *s = nullptr; }
+        c.lane[0].stream = c.lane[1].stream = nullptr;
+        c.plan = Ctx::WithinPlan();
+        c.hostCell.clear();
+        c.hostCellPtr = nullptr;
+        c.statsPending = false;
+        c.ready = false;
+    }
+    return NDA_OK;
+}
+
+// debugging aid (trace builds, tools/): copies the clock64 trace of the last within call, 256 x 32 values
 int nda_debug_tc_trace(long long *out)
 {
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     if (!c->sum.p || c->sum.cap < 256 * 32 * 8) return fail(NDA_ERR_ARG, "no trace recorded");
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out, c->sum.p, 256 * 32 * 8, cudaMemcpyDeviceToHost));
@@ -1149,6 +1842,7 @@ int nda_last_stats(double stats[4])
     Ctx *c;
     int rc = ctx_get(&c);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
     rc = fetch_stats(*c);
     if (rc) return rc;
     memcpy(stats, c->stats, sizeof c->stats);
@@ -1158,10 +1852,10 @@ int nda_last_stats(double stats[4])
 int nda_last_kernel_ms(double *ms, int *launches)
 {
     if (!ms) return fail(NDA_ERR_ARG, "null pointer argument");
-    std::lock_guard<std::mutex> lk(g_mutex);
     Ctx *c;
     int rc = ctx_get(&c);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
     double tot = 0.0;
     int n = 0;
     for (int i = 0; i + 1 < c->kevUsed; i += 2) {
@@ -1177,6 +1871,8 @@ int nda_last_kernel_ms(double *ms, int *launches)
 }
 
 // ---- device-pointer entry points -----------------------------------------------------------
+// All of them share the context's lane-0 scratch buffers; a per-lane event orders consecutive calls even
+// when they arrive on different caller streams.
 int nda_dev_radial_nbr_counts(const float *d_sel1, int n1, const float *d_sel2, int n2,
                               const int *d_groupId, int nGroups, unsigned long long *d_counts, int outSize,
                               const float *d_cellDims, int nF, int fb, int fe, int sameSel, float dr, void *stream)
@@ -1184,15 +1880,13 @@ int nda_dev_radial_nbr_counts(const float *d_sel1, int n1, const float *d_sel2, 
     if (!d_sel1 || !d_sel2 || !d_counts || !d_cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
     if (n1 < 0 || n2 < 0 || outSize < 0 || nF < 0 || fb < 0 || fe > nF) return fail(NDA_ERR_ARG, "bad size / frame range");
     if (sameSel && (d_sel1 != d_sel2 || n1 != n2)) return fail(NDA_ERR_ARG, "sameSel requires sel2 == sel1");
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    begin_call(*c);
+    CK(lane_acquire(c->lane[0], st));
     CK(reset_stats(*c, st));
     rc = dev_rdf(*c, c->lane[0], st, d_sel1, n1, d_sel2, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr);
     if (rc) return rc;
+    CK(lane_release(c->lane[0], st));
     return read_stats(*c, (sameSel ? 0.5 * (double)n1 * ((double)n1 - 1.0) : (double)n1 * (double)n2) * (fe - fb), 0.f);
 }
 
@@ -1203,16 +1897,14 @@ int nda_dev_within(const float *d_allAtoms, int nAtoms, int nF, const int *d_ref
     if (!d_allAtoms || !d_bits || !d_cellDims || (refSize > 0 && !d_refSel) || (outSelSize > 0 && !d_outSel))
         return fail(NDA_ERR_ARG, "null pointer argument");
     if (nAtoms < 0 || nF < 0 || refSize < 0 || outSelSize < 0 || fb < 0 || fe > nF) return fail(NDA_ERR_ARG, "bad size / frame range");
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    begin_call(*c);
+    CK(lane_acquire(c->lane[0], st));
     CK(reset_stats(*c, st));
     rc = dev_within(*c, c->lane[0], st, d_allAtoms, nAtoms, nF, d_refSel, refSize, d_outSel, outSelSize, d_bits, d_out,
                     d_cellDims, distance, fb, fe);
     if (rc) return rc;
+    CK(lane_release(c->lane[0], st));
     return read_stats(*c, (double)refSize * outSelSize * (fe - fb), 0.f);
 }
 
@@ -1222,12 +1914,8 @@ int nda_dev_distances_sum(const float *d_sel1, int n1, const float *d_sel2, int 
     if (!d_sel1 || !d_sel2 || !d_sum || !d_cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
     if (n1 < 0 || n2 < 0 || nF < 0 || fb < 0 || fe > nF) return fail(NDA_ERR_ARG, "bad size / frame range");
     if (sameSel && n1 != n2) return fail(NDA_ERR_ARG, "sameSel requires sel2 == sel1");
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    begin_call(*c);
     return dev_distances(*c, st, d_sel1, n1, d_sel2, n2, d_sum, d_cellDims, nF, fb, fe, sameSel);
 }
 
@@ -1240,16 +1928,14 @@ int nda_dev_radial_nbr_counts_sel(const float *d_all, int nAtoms, const int *d_i
     if (!d_all || !d_idx1 || !d_idx2 || !d_counts || !d_cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
     if (nAtoms < 0 || n1 < 0 || n2 < 0 || outSize < 0 || nF < 0 || fb < 0 || fe > nF) return fail(NDA_ERR_ARG, "bad size / frame range");
     if (sameSel && (d_idx1 != d_idx2 || n1 != n2)) return fail(NDA_ERR_ARG, "sameSel requires idx2 == idx1");
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    begin_call(*c);
+    CK(lane_acquire(c->lane[0], st));
     CK(reset_stats(*c, st));
     rc = dev_rdf(*c, c->lane[0], st, d_all, n1, d_all, n2, d_groupId, nGroups, d_counts, outSize, d_cellDims, nF, fb, fe, sameSel, dr,
                  d_idx1, d_idx2);
     if (rc) return rc;
+    CK(lane_release(c->lane[0], st));
     return read_stats(*c, (sameSel ? 0.5 * (double)n1 * ((double)n1 - 1.0) : (double)n1 * (double)n2) * (fe - fb), 0.f);
 }
 
@@ -1259,12 +1945,8 @@ int nda_dev_distances_sum_sel(const float *d_all, int nAtoms, const int *d_idx1,
     if (!d_all || !d_idx1 || !d_idx2 || !d_sum || !d_cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
     if (nAtoms < 0 || n1 < 0 || n2 < 0 || nF < 0 || fb < 0 || fe > nF) return fail(NDA_ERR_ARG, "bad size / frame range");
     if (sameSel && n1 != n2) return fail(NDA_ERR_ARG, "sameSel requires idx2 == idx1");
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    begin_call(*c);
     return dev_distances(*c, st, d_all, n1, d_all, n2, d_sum, d_cellDims, nF, fb, fe, sameSel, d_idx1, d_idx2);
 }
 
@@ -1278,66 +1960,37 @@ int nda_get_radial_nbr_counts(const float *sel1, int n1, const float *sel2, int 
     if (!groupId) nGroups = 1;
     if (nGroups < 1) return fail(NDA_ERR_ARG, "nGroups must be >= 1");
     if (sameSel && n1 != n2) return fail(NDA_ERR_ARG, "sameSel requires sel2 to be sel1");
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
-    cudaStream_t st = c->stream;
-    begin_call(*c);
+    if (groupId)
+        for (int i = 0; i < n2; ++i)
+            if (groupId[i] < 0 || groupId[i] >= nGroups) return fail(NDA_ERR_ARG, "groupId[%d] = %d outside [0, %d)", i, groupId[i], nGroups);
     const size_t H = (size_t)nGroups * outSize;
     std::vector<unsigned long long> h(H, 0ull);
-    float ms = 0.f;
     if (H && n1 && n2 && fe > fb) {
-        const int nFc = fe - fb;
-        CK(c->counts.reserve(H * 8));
-        CK(c->cell.reserve((size_t)nF * 12));
-        CK(cudaMemsetAsync(c->counts.p, 0, H * 8, st));
-        CK(reset_stats(*c, st));
-        if (groupId) {
-            for (int i = 0; i < n2; ++i)
-                if (groupId[i] < 0 || groupId[i] >= nGroups) return fail(NDA_ERR_ARG, "groupId[%d] = %d outside [0, %d)", i, groupId[i], nGroups);
-            CK(c->gid.reserve((size_t)n2 * 4));
-        }
-        {
-            const SetupItem items[2] = {{c->cell.p, cellDims, (size_t)nF * 12},
-                                        {groupId ? c->gid.p : nullptr, groupId, groupId ? (size_t)n2 * 4 : 0}};
-            rc = upload_setup(*c, items, 2);
-            if (rc) return rc;
-            CK(cudaStreamWaitEvent(st, c->evSetupCopy, 0));
-        }
-        // frame chunks: the upload of chunk k+1 overlaps pack + kernel of chunk k
-        Uploader up(*c, nF, fb, fe);
-        up.add(sel1, n1);
-        if (!sameSel) up.add(sel2, n2);
-        rc = up.begin(8, "NDA_UPLOAD_CHUNKS");
+        std::vector<Shard> sh;
+        int rc = plan_shards(fb, fe, sh);
         if (rc) return rc;
-        CK(cudaEventRecord(c->ev0, st));
-        CK(cudaEventRecord(c->evSetup, st));                // lane 1 must see counts / cell / gid initialised
-        CK(cudaStreamWaitEvent(c->lane[1].stream, c->evSetup, 0));
-        rc = up.issue(0);
-        if (rc) return rc;
-        for (int k = 0; k < up.nChunks; ++k) {
-            const int wc = up.f1(k) - up.f0(k);
-            Ctx::Lane &L = c->lane[k & 1];                  // alternate lanes: kernel k+1 fills the tail of kernel k
-            rc = up.acquire(k, L.stream);
+        const int G = (int)sh.size();
+        Merge m;
+        HostBarrier bar(G);
+        m.bar = &bar;
+        m.parts.resize((size_t)G);
+        g_last_collective.store(0);
+        if (G > 1) {
+            std::vector<int> devs;
+            for (const Shard &s : sh) devs.push_back(s.dev);
+            m.comms = nccl_comms(devs, config_get(), &rc);
             if (rc) return rc;
-            rc = dev_rdf(*c, L, L.stream, up.dev(0, k), n1, sameSel ? up.dev(0, k) : up.dev(1, k), n2,
-                         groupId ? c->gid.as<int>() : nullptr, nGroups, c->counts.as<unsigned long long>(), outSize,
-                         c->cell.as<float>() + (size_t)up.f0(k) * 3, wc, 0, wc, sameSel, dr, nullptr, nullptr,
-                         cellDims + (size_t)up.f0(k) * 3);
-            if (rc) return rc;
-            rc = up.release(k, L.stream);
-            if (rc) return rc;
-            if (k + 1 < up.nChunks) { rc = up.issue(k + 1); if (rc) return rc; }
         }
-        CK(cudaEventRecord(c->evLaneJoin, c->lane[1].stream));
-        CK(cudaStreamWaitEvent(st, c->evLaneJoin, 0));
-        CK(cudaEventRecord(c->ev1, st));
-        CK(cudaMemcpyAsync(h.data(), c->counts.p, H * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         const double perFrame = sameSel ? 0.5 * (double)n1 * ((double)n1 - 1.0) : (double)n1 * (double)n2;
-        rc = read_stats(*c, perFrame * nFc, ms);
+        rc = run_shards(sh, [&](int g, Ctx &c) -> int {
+            float ms = 0.f;
+            int r = rdf_shard(c, sel1, n1, sel2, n2, groupId, nGroups, outSize, cellDims, nF, sh[g].fb, sh[g].fe, sameSel, dr,
+                              G == 1 ? nullptr : &ms);
+            r = merge_partials<unsigned long long>(m, g, G, c, c.stream, c.counts.as<unsigned long long>(), H, h.data(), r);
+            if (r) return r;
+            if (G == 1) CK(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+            return read_stats(c, perFrame * (sh[g].fe - sh[g].fb), ms);
+        });
         if (rc) return rc;
     }
     if (counts) for (size_t i = 0; i < H; ++i) counts[i] = (uint64_t)h[i];
@@ -1350,7 +2003,15 @@ int nda_get_radial_nbr_density(const float *sel1, int n1, const float *sel2, int
 {
     (void)maxR;                                             // unused by the reference as well (SURVEY B-9)
     if (!out) return fail(NDA_ERR_ARG, "null pointer argument");
-    return nda_get_radial_nbr_counts(sel1, n1, sel2, n2, nullptr, 1, nullptr, out, outSize, cellDims, nF, 0, nF, sameSel, dr);
+    if (outSize < 0) return fail(NDA_ERR_ARG, "bad size");
+    // the reference ACCUMULATES into out (getRadialNbrDensity.cpp:40-41: out[idx] += 1 / nbrFrames per pair);
+    // here the integer count is divided once and added once -- equal for the zero-initialised array every stock
+    // caller passes (RadialDensity.py:205, 76), and a caller that reuses `out` still gets a sum
+    std::vector<float> d((size_t)outSize, 0.f);
+    const int rc = nda_get_radial_nbr_counts(sel1, n1, sel2, n2, nullptr, 1, nullptr, d.data(), outSize, cellDims, nF, 0, nF, sameSel, dr);
+    if (rc) return rc;
+    for (int i = 0; i < outSize; ++i) out[i] += d[i];
+    return NDA_OK;
 }
 
 int nda_get_distances_sum(const float *sel1, int n1, const float *sel2, int n2, double *sum,
@@ -1359,50 +2020,38 @@ int nda_get_distances_sum(const float *sel1, int n1, const float *sel2, int n2, 
     if (!sel1 || !sel2 || !sum || !cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
     if (n1 < 0 || n2 < 0 || nF <= 0 || fb < 0 || fe > nF || fb > fe) return fail(NDA_ERR_ARG, "bad size / frame range");
     if (sameSel && n1 != n2) return fail(NDA_ERR_ARG, "sameSel requires sel2 to be sel1");
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
-    cudaStream_t st = c->stream;
-    begin_call(*c);
     const size_t M = (size_t)n1 * n2;
     if (M == 0) return NDA_OK;
     if (fe == fb) { memset(sum, 0, M * 8); return NDA_OK; }
-    CK(c->sum.reserve(M * 8));
-    CK(c->cell.reserve((size_t)nF * 12));
-    CK(cudaMemsetAsync(c->sum.p, 0, M * 8, st));
-    {
-        const SetupItem items[1] = {{c->cell.p, cellDims, (size_t)nF * 12}};
-        rc = upload_setup(*c, items, 1);
-        if (rc) return rc;
-        CK(cudaStreamWaitEvent(st, c->evSetupCopy, 0));
-    }
-    Uploader up(*c, nF, fb, fe);
-    up.add(sel1, n1);
-    if (!sameSel) up.add(sel2, n2);
-    rc = up.begin(8, "NDA_UPLOAD_CHUNKS");
+    std::vector<Shard> sh;
+    int rc = plan_shards(fb, fe, sh);
     if (rc) return rc;
-    rc = up.issue(0);
-    if (rc) return rc;
-    for (int k = 0; k < up.nChunks; ++k) {
-        const int wc = up.f1(k) - up.f0(k);
-        rc = up.acquire(k, st);
+    const int G = (int)sh.size();
+    Merge m;
+    HostBarrier bar(G);
+    m.bar = &bar;
+    m.parts.resize((size_t)G);
+    g_last_collective.store(0);
+    if (G > 1) {
+        std::vector<int> devs;
+        for (const Shard &s : sh) devs.push_back(s.dev);
+        m.comms = nccl_comms(devs, config_get(), &rc);
         if (rc) return rc;
-        rc = dev_distances(*c, st, up.dev(0, k), n1, sameSel ? up.dev(0, k) : up.dev(1, k), n2,
-                           c->sum.as<double>(), c->cell.as<float>() + (size_t)up.f0(k) * 3, wc, 0, wc, sameSel);
-        if (rc) return rc;
-        rc = up.release(k, st);
-        if (rc) return rc;
-        if (k + 1 < up.nChunks) { rc = up.issue(k + 1); if (rc) return rc; }
     }
-    if (sameSel) {
-        dim3 grid((n1 + 255) / 256, std::min(n1, 4096));
-        symmetrize_kernel<<<grid, 256, 0, st>>>(c->sum.as<double>(), n1);
-        LAUNCHED();
-    }
-    CK(cudaMemcpyAsync(sum, c->sum.p, M * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return NDA_OK;
+    return run_shards(sh, [&](int g, Ctx &c) -> int {
+        int r = distances_shard(c, sel1, n1, sel2, n2, cellDims, nF, sh[g].fb, sh[g].fe, sameSel);
+        if (!r && sameSel && G == 1) {
+            dim3 grid((n1 + 255) / 256, std::min(n1, 4096));
+            symmetrize_kernel<<<grid, 256, 0, c.stream>>>(c.sum.as<double>(), n1);
+            LAUNCHED();
+        }
+        r = merge_partials<double>(m, g, G, c, c.stream, c.sum.as<double>(), M, sum, r);
+        if (r) return r;
+        if (sameSel && G > 1 && g == 0)                     // mirror the merged upper triangle (cheap, host side)
+            for (int i = 0; i < n1; ++i)
+                for (int j = i + 1; j < n1; ++j) sum[(size_t)j * n1 + i] = sum[(size_t)i * n1 + j];
+        return NDA_OK;
+    });
 }
 
 int nda_get_distances(const float *sel1, int n1, const float *sel2, int n2, float *out,
@@ -1425,142 +2074,27 @@ int nda_get_within_bits(const float *allAtoms, int nAtoms, int nF, const int *re
         return fail(NDA_ERR_ARG, "null pointer argument");
     if (nAtoms < 0 || nF <= 0 || refSize < 0 || outSelSize < 0 || fb < 0 || fe > nF || fb > fe)
         return fail(NDA_ERR_ARG, "bad size / frame range");
-    if (outSelSize == 0 || fe == fb) {
+    for (int i = 0; i < refSize; ++i)
+        if (refSel[i] < 0 || refSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "refSel[%d] = %d outside [0, %d)", i, refSel[i], nAtoms);
+    for (int i = 0; i < outSelSize; ++i)
+        if (outSel[i] < 0 || outSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "outSel[%d] = %d outside [0, %d)", i, outSel[i], nAtoms);
+    const Config cfg = config_get();
+    // SURVEY B-1: the legacy CUDA build (lib/cuda/src/getWithin.cu:27-28) marks every refSel atom in every
+    // frame whether or not it belongs to outSel; the OpenMP build (the oracle) does not.  Opt-in.
+    if (cfg.compatCuda && out && fe > fb) {
         for (int i = 0; i < refSize; ++i)
-            if (refSel[i] < 0 || refSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "refSel[%d] = %d outside [0, %d)", i, refSel[i], nAtoms);
-        for (int i = 0; i < outSelSize; ++i)
-            if (outSel[i] < 0 || outSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "outSel[%d] = %d outside [0, %d)", i, outSel[i], nAtoms);
-        return NDA_OK;
+            for (int f = fb; f < fe; ++f) out[(size_t)refSel[i] * nF + f] = 1;
     }
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
-    cudaStream_t st = c->stream;
-    begin_call(*c);
-    HostTrace ht("within");
-    const int nFc = fe - fb;
+    if (outSelSize == 0 || fe == fb) return NDA_OK;
     const int words = (outSelSize + 31) / 32;
-
-    // ---- which rows travel, and the selections re-expressed in uploaded-row numbers
-    Ctx::WithinPlan &pl = c->plan;
-    const bool samePlan = pl.nAtoms == nAtoms && (int)pl.refSel.size() == refSize && (int)pl.outSel.size() == outSelSize &&
-                          (refSize == 0 || memcmp(pl.refSel.data(), refSel, (size_t)refSize * 4) == 0) &&
-                          memcmp(pl.outSel.data(), outSel, (size_t)outSelSize * 4) == 0;
-    if (!samePlan) {
-        pl.nAtoms = -1;
-        for (int i = 0; i < refSize; ++i)
-            if (refSel[i] < 0 || refSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "refSel[%d] = %d outside [0, %d)", i, refSel[i], nAtoms);
-        for (int i = 0; i < outSelSize; ++i)
-            if (outSel[i] < 0 || outSel[i] >= nAtoms) return fail(NDA_ERR_ARG, "outSel[%d] = %d outside [0, %d)", i, outSel[i], nAtoms);
-        plan_rows(refSel, refSize, outSel, outSelSize, nAtoms, pl.remap, pl.runs, pl.nRows);
-        pl.ref2.resize((size_t)std::max(refSize, 1));
-        pl.out2.resize((size_t)outSelSize);
-        for (int i = 0; i < refSize; ++i) pl.ref2[i] = pl.remap[refSel[i]];
-        for (int i = 0; i < outSelSize; ++i) pl.out2[i] = pl.remap[outSel[i]];
-        pl.refSel.assign(refSel, refSel + refSize);
-        pl.outSel.assign(outSel, outSel + outSelSize);
-        pl.nAtoms = nAtoms;
-    }
-    const std::vector<int> &ref2 = pl.ref2, &out2 = pl.out2;
-    const int nRows = pl.nRows;
-
-    // ---- frame chunks: copy of chunk k+1 overlaps pack + kernel of chunk k (two raw buffers)
-    Uploader up(*c, nF, fb, fe);
-    up.add(allAtoms, nRows, pl.runs);
-    rc = up.begin(6, "NDA_WITHIN_CHUNKS");
+    std::vector<Shard> sh;
+    int rc = plan_shards(fb, fe, sh);
     if (rc) return rc;
-    const int nChunks = up.nChunks;
-    ht.mark("plan");
-    CK(c->cell.reserve((size_t)nF * 12));
-    CK(c->idx1.reserve((size_t)std::max(refSize, 1) * 4));
-    CK(c->idx2.reserve((size_t)outSelSize * 4));
-    {                                                       // ~60 KB on the copy stream, then the first chunk
-        const SetupItem items[3] = {{c->cell.p, cellDims, (size_t)nF * 12},
-                                    {c->idx1.p, ref2.data(), (size_t)refSize * 4},
-                                    {c->idx2.p, out2.data(), (size_t)outSelSize * 4}};
-        rc = upload_setup(*c, items, 3);
-        if (rc) return rc;
-    }
-    rc = up.issue(0);                                       // the link is the bottleneck: start it first
-    if (rc) return rc;
-    ht.mark("issue0");
-
-    CK(c->bits.reserve((size_t)nFc * words * 4));
-    CK(c->pinned_reserve((size_t)nFc * words * 4));
-    uint32_t *hbits = reinterpret_cast<uint32_t *>(c->pinned);
-
-    CK(reset_stats(*c, st));
-    CK(cudaStreamWaitEvent(st, c->evSetupCopy, 0));
-    CK(cudaEventRecord(c->ev0, st));
-
-    auto scatter = [&](int k) {                             // host: set the 1s of chunk k
-        if (!out) return;
-        const int f0 = up.f0(k) - fb, f1 = up.f1(k) - fb;
-        // ~6e5 cache-missing stores for config 2: spread the frames over the host threads
-        #pragma omp parallel for schedule(static) num_threads(g_host_threads) if (f1 - f0 >= 16)
-        for (int f = f0; f < f1; ++f) {
-            const uint32_t *row = hbits + (size_t)f * words;
-            for (int w = 0; w < words; ++w) {
-                uint32_t v = row[w];
-                while (v) {                                  // the reference only ever stores 1 (getWithin.cpp:77,83)
-                    const int b = __builtin_ctz(v);
-                    v &= v - 1;
-                    out[(size_t)outSel[w * 32 + b] * nF + fb + f] = 1;
-                }
-            }
-        }
-    };
-
-    CK(cudaEventRecord(c->evSetup, st));                    // lane 1 must see cell / selections uploaded
-    CK(cudaStreamWaitEvent(c->lane[1].stream, c->evSetup, 0));
-    ht.mark("setup");
-    for (int k = 0; k < nChunks; ++k) {
-        const int f0 = up.f0(k), wc = up.f1(k) - f0, buf = k & 1;
-        Ctx::Lane &L = c->lane[buf];                        // alternate lanes: kernel k+1 fills the tail of kernel k
-        cudaStream_t ls = L.stream;
-        rc = up.acquire(k, ls);
-        if (rc) return rc;
-        rc = dev_within(*c, L, ls, up.dev(0, k), nRows, wc, c->idx1.as<int>(), refSize, c->idx2.as<int>(), outSelSize,
-                        c->bits.as<unsigned>() + (size_t)(f0 - fb) * words, nullptr,
-                        c->cell.as<float>() + (size_t)f0 * 3, distance, 0, wc, cellDims + (size_t)f0 * 3);
-        if (rc) return rc;
-        rc = up.release(k, ls);
-        if (rc) return rc;
-        static const bool d2hEngine = getenv("NDA_D2H_COPY_ENGINE") != nullptr;   // A/B switch: the old way
-        if (d2hEngine) {
-            CK(cudaMemcpyAsync(hbits + (size_t)(f0 - fb) * words, c->bits.as<unsigned>() + (size_t)(f0 - fb) * words,
-                               (size_t)wc * words * 4, cudaMemcpyDeviceToHost, ls));
-        } else {                                             // SMs write the pinned buffer: no copy-engine queueing
-            const size_t nW = (size_t)wc * words;
-            copy_words_kernel<<<(unsigned)std::min<size_t>((nW + 255) / 256, 296), 256, 0, ls>>>(
-                c->bits.as<unsigned>() + (size_t)(f0 - fb) * words, hbits + (size_t)(f0 - fb) * words, nW);
-            LAUNCHED();
-        }
-        CK(cudaEventRecord(c->evBits[buf], ls));
-        if (k + 1 < nChunks) { rc = up.issue(k + 1); if (rc) return rc; }   // host gathers k+1 while the GPU works on k
-        ht.mark("enq");
-        if (k > 0) {                                         // ... and scatters chunk k-1
-            CK(cudaEventSynchronize(c->evBits[buf ^ 1]));
-            ht.mark("wait");
-            scatter(k - 1);
-            ht.mark("scat");
-        }
-    }
-    CK(cudaEventRecord(c->evLaneJoin, c->lane[1].stream));
-    CK(cudaStreamWaitEvent(st, c->evLaneJoin, 0));
-    CK(cudaEventRecord(c->ev1, st));
-    ht.mark("loop");
-    CK(cudaStreamSynchronize(st));
-    ht.mark("sync");
-    scatter(nChunks - 1);
-    ht.mark("scatter");
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    rc = read_stats(*c, (double)refSize * outSelSize * nFc, ms);
-    if (rc) return rc;
-    if (bits) memcpy(bits, hbits, (size_t)nFc * words * 4);
-    return NDA_OK;
+    g_last_collective.store(0);
+    return run_shards(sh, [&](int g, Ctx &c) -> int {
+        return within_shard(c, allAtoms, nAtoms, nF, refSel, refSize, outSel, outSelSize,
+                            bits ? bits + (size_t)(sh[g].fb - fb) * words : nullptr, out, cellDims, distance, sh[g].fb, sh[g].fe);
+    });
 }
 
 int nda_get_within(const float *allAtoms, int nAtoms, int nF, const int *refSel, int refSize,
@@ -1592,12 +2126,8 @@ int nda_set_water_dist_pbc(float *water, int sizeW, const float *prot, int sizeP
     if (!water || !prot || !cellDims) return fail(NDA_ERR_ARG, "null pointer argument");
     if (sizeW < 0 || sizeP < 0 || nF <= 0 || nbrWAtoms <= 0) return fail(NDA_ERR_ARG, "bad size");
     if (sizeW == 0) return NDA_OK;
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     cudaStream_t st = c->stream;
-    begin_call(*c);
     Ctx::Lane &L = c->lane[0];
     const size_t wBytes = (size_t)sizeW * nbrWAtoms * nF * 12;
     CK(c->raw[0][0].reserve(wBytes + 16));
@@ -1635,12 +2165,8 @@ int nda_water_orient_at_surface(float *waterO, int sizeO, const float *watVec, c
     if (sizeO < 0 || sizeP < 0 || nF <= 0) return fail(NDA_ERR_ARG, "bad size");
     if (maxN < 1 || maxN > SURF_MAXN) return fail(NDA_ERR_ARG, "maxN = %d outside [1, %d]", maxN, SURF_MAXN);
     if (sizeO == 0) return NDA_OK;
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     cudaStream_t st = c->stream;
-    begin_call(*c);
     Ctx::Lane &L = c->lane[0];
     const size_t wBytes = (size_t)sizeO * nF * 12;
     CK(c->raw[0][0].reserve(wBytes + 16));
@@ -1681,12 +2207,8 @@ int nda_get_hb_counts(const float *acceptors, int nA, int nF, const float *donor
     if (nA < 0 || nD < 0 || nH < nD || nF <= 0) return fail(NDA_ERR_ARG, "bad size (every donor needs its hydrogen)");
     for (int dt = 0; dt < nF; ++dt) counts[dt] = 0;
     if (nA == 0 || nD == 0) return NDA_OK;
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     cudaStream_t st = c->stream;
-    begin_call(*c);
     const float cosAngle = cosf(minAngle);                  // getHydrogenBonds.cpp:16, the host's libm like the reference
     CK(c->raw[0][0].reserve((size_t)nA * nF * 12 + 16));
     CK(c->raw[0][1].reserve((size_t)nD * nF * 12 + 16));
@@ -1767,7 +2289,7 @@ int nda_dcd_get_coor(const char *fileName, const int *frames, int nbrFrames, int
     const char sys = *reinterpret_cast<const char *>(&probe) ? '<' : '>';
     const bool swap = (byteorder == '<' || byteorder == '>') && byteorder != sys;
     int err = 0;
-    #pragma omp parallel num_threads(g_host_threads > 0 ? g_host_threads : 1)
+    #pragma omp parallel num_threads(default_host_threads())
     {
         std::vector<uint32_t> rec((size_t)nbrAtoms);
         #pragma omp for schedule(dynamic, 1)
@@ -1830,10 +2352,7 @@ int nda_dev_synth_water_box(float *d_xyz, float *d_cellDims, int n_side, int nF,
     if (!d_xyz || !d_cellDims || n_side <= 0 || n_side > 1024 || fb < 0 || fe > nF || fb > fe)
         return fail(NDA_ERR_ARG, "bad argument");
     if (fe == fb) return NDA_OK;
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const unsigned n = (unsigned)n_side * n_side * n_side;
     for (int f0 = fb; f0 < fe; f0 += 32768) {
@@ -1848,10 +2367,7 @@ int nda_dev_synth_water_box(float *d_xyz, float *d_cellDims, int n_side, int nF,
 int nda_measure_fp32_peak(int variant, double *tflops)
 {
     if (!tflops) return fail(NDA_ERR_ARG, "null pointer argument");
-    std::lock_guard<std::mutex> lk(g_mutex);
-    Ctx *c;
-    int rc = ctx_get(&c);
-    if (rc) return rc;
+    NDA_ENTER();
     cudaStream_t st = c->stream;
     CK(c->bits.reserve(64));
     const int iters = 4096, blocks = c->numSMs * 8;
@@ -1869,6 +2385,65 @@ int nda_measure_fp32_peak(int variant, double *tflops)
         if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
     }
     *tflops = best;
+    return NDA_OK;
+}
+
+// One production tcgen05.mma on caller-supplied fp16 operands (A [128][16], B [256][16], raw bits) and the
+// production packed read-back: out uint32 [128][128], out[row][cq * 32 + n] = register n of columns 64 cq ..
+int nda_debug_tc_probe(const uint16_t *A, const uint16_t *B, uint32_t *out)
+{
+    if (!A || !B || !out) return fail(NDA_ERR_ARG, "null pointer argument");
+    NDA_ENTER();
+    cudaStream_t st = c->stream;
+    CK(c->raw[0][0].reserve(TC_SBLK * 32 + TC_RBLK * 32));
+    CK(c->bits.reserve(128 * 128 * 4));
+    __half *dA = c->raw[0][0].as<__half>(), *dB = dA + TC_SBLK * 16;
+    CK(cudaMemcpyAsync(dA, A, TC_SBLK * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dB, B, TC_RBLK * 32, cudaMemcpyHostToDevice, st));
+    const size_t smem = TC_SEMB_BYTES + TC_REMB_BYTES + 64;
+    CK(cudaFuncSetAttribute((const void *)tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_probe_kernel<<<1, 512, smem, st>>>(dA, dB, c->bits.as<uint32_t>());
+    LAUNCHED();
+    CK(cudaMemcpyAsync(out, c->bits.p, 128 * 128 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return NDA_OK;
+}
+
+// Platform ceiling of the end-to-end path: `bytes` of CONTIGUOUS pinned host memory copied to every device of
+// the calling thread at the same time (one plain cudaMemcpyAsync each, one host thread per device), `reps`
+// times; returns the aggregate GB/s of the slowest repetition-averaged device (max over devices of the time).
+int nda_measure_h2d(size_t bytes, int reps, double *gbps)
+{
+    if (!gbps || bytes == 0 || reps < 1) return fail(NDA_ERR_ARG, "bad argument");
+    std::vector<Shard> sh;
+    int rc = plan_shards(0, 1 << 20, sh);
+    if (rc) return rc;
+    const int G = (int)sh.size();
+    std::vector<double> ms((size_t)G, 0.0);
+    HostBarrier bar(G);
+    rc = run_shards(sh, [&](int g, Ctx &c) -> int {
+        void *h = nullptr;
+        cudaError_t e = cudaMallocHost(&h, bytes);
+        if (e == cudaSuccess) e = c.raw[0][0].reserve(bytes);
+        if (e == cudaSuccess) { memset(h, 1, bytes); e = cudaMemcpyAsync(c.raw[0][0].p, h, bytes, cudaMemcpyHostToDevice, c.copyStream); }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.copyStream);
+        bar.wait();                                          // every device warmed up: start together
+        if (e == cudaSuccess) e = cudaEventRecord(c.ev0, c.copyStream);
+        for (int r = 0; r < reps && e == cudaSuccess; ++r)
+            e = cudaMemcpyAsync(c.raw[0][0].p, h, bytes, cudaMemcpyHostToDevice, c.copyStream);
+        if (e == cudaSuccess) e = cudaEventRecord(c.ev1, c.copyStream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.copyStream);
+        float t = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, c.ev0, c.ev1);
+        ms[g] = t;
+        if (h) cudaFreeHost(h);
+        if (e != cudaSuccess) return fail(NDA_ERR_CUDA, "H2D measurement failed: %s", cudaGetErrorString(e));
+        return NDA_OK;
+    });
+    if (rc) return rc;
+    double worst = 0.0;
+    for (double t : ms) worst = std::max(worst, t);
+    *gbps = worst > 0.0 ? (double)bytes * reps * G / (worst * 1e-3) / 1e9 : 0.0;
     return NDA_OK;
 }
 

@@ -681,7 +681,8 @@ struct TcEpi {
 struct RdfTcArgs {
     TcGeom g;                   // A = sel1 (streamed), B = sel2 (resident; its w component = group id)
     unsigned long long *counts;
-    int nBins, nGroups, histCopies;
+    int nBins, nGroups, histCopies;   // nGroups = groups of THIS launch (a batch), counts points at the batch's first row
+    int groupBase;                    // first group id of the batch
     float dr;
     int fastStrict;
 };
@@ -740,7 +741,10 @@ rdf_tc_kernel(const RdfTcArgs p)
                         if (!geo.sameSel || (row > col)) {
                             const float r2 = strict_r2(a.x, a.y, a.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
                             const int idx = strict_bin(r2, p.dr, p.nBins);
-                            if (idx >= 0) atomicAdd(&myHist[(kGrouped ? __float_as_int(b.w) : 0) * p.nBins + idx], 1u);
+                            {
+                                const int gq = kGrouped ? __float_as_int(b.w) - p.groupBase : 0;
+                                if (idx >= 0 && (!kGrouped || (unsigned)gq < (unsigned)p.nGroups)) atomicAdd(&myHist[gq * p.nBins + idx], 1u);
+                            }
                         }
                     }
                 }
@@ -764,7 +768,10 @@ rdf_tc_kernel(const RdfTcArgs p)
                     const float r2 = p.fastStrict ? strict_r2_fastpath(a.x, a.y, a.z, b.x, b.y, b.z, fpar)
                                                   : strict_r2(a.x, a.y, a.z, b.x, b.y, b.z, fpar.cx, fpar.cy, fpar.cz);
                     const int idx = strict_bin(r2, p.dr, p.nBins);
-                    if (idx >= 0) atomicAdd(&myHist[(kGrouped ? __float_as_int(b.w) : 0) * p.nBins + idx], 1u);
+                    {
+                                const int gq = kGrouped ? __float_as_int(b.w) - p.groupBase : 0;
+                                if (idx >= 0 && (!kGrouped || (unsigned)gq < (unsigned)p.nGroups)) atomicAdd(&myHist[gq * p.nBins + idx], 1u);
+                            }
                     ++nCand;
                 }
                 qhead = (qhead + n) % TC_QCAP;
@@ -1026,4 +1033,60 @@ within_tc_kernel(const WithinTcArgs p)
         if (lane == 0 && nCand) atomicAdd(&geo.stats[0], (unsigned long long)nCand);
     }
     tc_teardown(tmem);
+}
+
+// ------------------------------------------------------------------------------------------
+// tc_probe_kernel: ONE production MMA (same instruction descriptor, operand layout, fp16 accumulators and
+// tcgen05.ld.pack::16b read-back as within_tc_kernel / rdf_tc_kernel) on caller-supplied fp16 operands.
+// The parity suite uses it to pin the two hardware properties the filter's correctness rests on
+// (tests/test_gpu_tensor_filter.py): the fp16 accumulator is the correctly rounded EXACT sum -- so the sign
+// of D = dot - thrDot is the sign of the exact sum whenever that is not within the slack E -- and
+// register n of the packed load holds columns 2n (low half) and 2n + 1 (high half).
+// A [128][16], B [256][16] row-major fp16 bits; out [128][128] raw registers: out[row][cq * 32 + n] =
+// register n of the warp that owns columns 64 cq .. 64 cq + 63.  grid 1, block 512.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512, 1)
+tc_probe_kernel(const __half *__restrict__ A, const __half *__restrict__ B, uint32_t *__restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __half *sA = reinterpret_cast<__half *>(smem_raw);                       // [2][128][8]
+    __half *sB = reinterpret_cast<__half *>(smem_raw + TC_SEMB_BYTES);       // [2][256][8]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + TC_SEMB_BYTES + TC_REMB_BYTES);
+    uint32_t *tmemPtr = reinterpret_cast<uint32_t *>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < TC_SBLK * 16; i += blockDim.x) {
+        const int row = i / 16, k = i % 16;
+        sA[(k / 8) * TC_SBLK * 8 + row * 8 + (k % 8)] = A[i];
+    }
+    for (int i = tid; i < TC_RBLK * 16; i += blockDim.x) {
+        const int row = i / 16, k = i % 16;
+        sB[(k / 8) * TC_RBLK * 8 + row * 8 + (k % 8)] = B[i];
+    }
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic-proxy stores -> async proxy (MMA)
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" :: "r"(smem_u32(tmemPtr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmemPtr;
+    if (warp == 0) {
+        if (tc_elect_one()) {
+            tc_mma(tmem, tc_smem_desc(smem_u32(sA), TC_SBLK * 16), tc_smem_desc(smem_u32(sB), TC_RBLK * 16));
+            tc_commit(smem_u32(bar));
+        }
+        __syncwarp();
+    }
+    bar_wait(smem_u32(bar), 0);
+    tc_fence_after();
+    const int q = warp & 3, cq = warp >> 2;
+    uint32_t r[32];
+    tc_ld64p(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cq * 64), r);
+    #pragma unroll
+    for (int n = 0; n < 32; ++n) out[(size_t)(q * 32 + lane) * 128 + cq * 32 + n] = r[n];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" :: "r"(tmem) : "memory");
 }

@@ -41,6 +41,9 @@ class ResidentTrajectory:
         self._st = ctypes.c_void_p(self.stream.cuda_stream)
 
     def _frames(self, frames):
+        # the library's device is per calling thread: a query from another thread, or after a second
+        # ResidentTrajectory was created on another device, must re-select this trajectory's device
+        _capi.check(self.lib.nda_set_device(self.dev.index))
         if frames is None:
             return 0, self.nFrames
         fb, fe = frames

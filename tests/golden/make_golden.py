@@ -4,7 +4,8 @@
 Run in the BUILD container only (needs /root/reference and oracle/_ref, i.e.
 `make -C oracle ref`):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # golden_ref_strict.npz, ubq_ws_fixture.npz
+    python tests/golden/make_golden.py --full     # golden_ref_strict_full.npz (configs 2 and 5 at full size, ~3 min)
 
 What it writes
   ubq_ws_fixture.npz   inputs taken from the reference's own test trajectory
@@ -180,5 +181,43 @@ def main():
         print("%-22s %-12s %s" % (k, v.dtype, v.shape))
 
 
+def bitmask_words(m, outSel):
+    """int32 mask [nAtoms][nF] -> the library's bitmask uint32 [nF][ceil(nOut/32)]: bit (a & 31) of word a >> 5 = outSel[a]"""
+    flags = np.ascontiguousarray(m[outSel].T).astype(np.uint8)             # [nF][nOut]
+    words = (outSel.size + 31) // 32
+    pad = np.zeros((flags.shape[0], words * 32), np.uint8)
+    pad[:, :outSel.size] = flags
+    return np.packbits(pad, axis=1, bitorder="little").view("<u4")
+
+
+def main_full():
+    """golden_ref_strict_full.npz: the two BASELINE workloads whose full size the GPU suite can afford to pin --
+    config 2 at all 1000 frames (hits per frame + CRC of the bitmask) and config 5 at 69^3 = 328 509 atoms,
+    one frame (5.4e10 pairs: about a minute of the reference's OpenMP code here)."""
+    from namdanalyzer_b200 import synth
+    from oracle.ref import RefLib
+    ref = RefLib("strict")
+    nb = synth.n_bins(0.1, 15.0)
+    out = {}
+    c = synth.config2(n_frames=1000)
+    out["c2full_crc"] = crc(c["allAtoms"], c["cellDims"])
+    m = ref.within(c["allAtoms"], c["refSel"], c["outSel"], c["cellDims"], c["distance"])
+    assert m.shape == (25000, 1000)
+    out["c2full_hits_per_frame"] = m.sum(0).astype(np.int32)
+    bits = bitmask_words(m, c["outSel"])
+    out["c2full_bits_crc"] = crc(bits)
+    out["c2full_bits_frame_crc"] = np.array([zlib.crc32(bits[f].tobytes()) for f in range(1000)], np.uint32)
+    del m, c
+    c = synth.config5(n_side=69, n_frames=1)
+    out["c5full_crc"] = crc(c["sel1"], c["cellDims"])
+    out["c5full_counts"] = ref.rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, nb, 0.1, 15.0)
+    np.savez_compressed(os.path.join(HERE, "golden_ref_strict_full.npz"), **out)
+    for k, v in out.items():
+        print("%-24s %-12s %s" % (k, v.dtype, v.shape))
+
+
 if __name__ == "__main__":
-    main()
+    if "--full" in sys.argv:
+        main_full()
+    else:
+        main()

@@ -5,7 +5,7 @@ oracle assembled the way the reference's Python glue assembles it."""
 import numpy as np
 import pytest
 
-from namdanalyzer_b200 import synth
+from namdanalyzer_b200 import synth, _capi
 from namdanalyzer_b200.Dataset import ArrayDataset
 from namdanalyzer_b200.dataAnalysis.RadialDensity import RadialNumberDensity, ResidueWiseWaterDensity
 from oracle import port
@@ -202,7 +202,7 @@ def test_dcd_file_to_resident_trajectory(tmp_path):
 
 
 @pytest.mark.parametrize("pinned", [False, True])
-def test_upload_pipeline_chunk_boundaries(monkeypatch, pinned):
+def test_upload_pipeline_chunk_boundaries(pinned):
     """The host entry points cut the frames into chunks (tapered tail); force many
     small chunks on a small system so that every boundary, both staging buffers, the pinned (strided
     DMA) and the pageable (gathered) upload and the per-chunk mask scatter are exercised, and compare
@@ -217,7 +217,7 @@ def test_upload_pipeline_chunk_boundaries(monkeypatch, pinned):
         cell = torch.from_numpy(cell).pin_memory().numpy()
     want = port.within(c["allAtoms"], r, o, c["cellDims"], 3.0)
     for chunks in ("7", "3", "1"):
-        monkeypatch.setenv("NDA_WITHIN_CHUNKS", chunks)
+        _capi.set_option("NDA_WITHIN_CHUNKS", chunks)
         for rep in range(2):
             out = np.zeros(xyz.shape[:2], np.int32)
             plf.py_getWithin(xyz, r, o, out, cell, 3.0)
@@ -227,11 +227,13 @@ def test_upload_pipeline_chunk_boundaries(monkeypatch, pinned):
     plf.py_getWithin(xyz, r, o2, out, cell, 3.0)
     assert np.array_equal(out, port.within(c["allAtoms"], r, o2, c["cellDims"], 3.0))
     # RDF and distances share the uploader
-    monkeypatch.setenv("NDA_UPLOAD_CHUNKS", "5")
+    _capi.set_option("NDA_WITHIN_CHUNKS", None)
+    _capi.set_option("NDA_UPLOAD_CHUNKS", "5")
     w = np.ascontiguousarray(xyz[o[:300]])
     pr = np.ascontiguousarray(xyz[r[:200]])
     got = plf.py_getRadialNbrCounts(w, pr, cell, 0, 40, 0.1)
     assert np.array_equal(got, port.rdf_counts(w, pr, c["cellDims"], 0, 40, 0.1))
     d = plf.py_getDistancesSum(w[:5], pr, cell, 0)
     dw = port.distances_sum(w[:5], pr, c["cellDims"], 0)
+    _capi.set_option("NDA_UPLOAD_CHUNKS", None)
     assert np.max(np.abs(d - dw) / np.maximum(dw, 1e-30)) < 1e-12

@@ -20,16 +20,9 @@ TC = 100
 
 @pytest.fixture()
 def force_tc():
-    old = {k: os.environ.get(k) for k in ("NDA_FILTER", "NDA_TC_MAX_FRACTION", "NDA_TC_ALLOW_PADDING")}
-    os.environ["NDA_FILTER"] = "tc"
-    os.environ["NDA_TC_MAX_FRACTION"] = "1.0"
-    os.environ["NDA_TC_ALLOW_PADDING"] = "1"
-    yield _capi.load()
-    for k, v in old.items():
-        if v is None:
-            os.environ.pop(k, None)
-        else:
-            os.environ[k] = v
+    # the library reads NDA_* from the environment once; afterwards nda_set_option is the switch
+    with _capi.options(NDA_FILTER="tc", NDA_TC_MAX_FRACTION="1.0", NDA_TC_ALLOW_PADDING="1"):
+        yield _capi.load()
 
 
 def rdf_counts(a, b, cell, same, nb, dr, **kw):
@@ -119,20 +112,20 @@ def test_within_pairs_on_both_sides_of_the_cutoff(dist):
     r = np.arange(0, n_ref, dtype=np.int32)
     o = np.arange(n_ref, xyz.shape[0], dtype=np.int32)
     want = port.within(xyz, r, o, cell, dist)
-    os.environ["NDA_TC_ALLOW_PADDING"] = "1"                            # few ref atoms: keep the tensor path anyway
+    _capi.set_option("NDA_TC_ALLOW_PADDING", "1")                       # few ref atoms: keep the tensor path anyway
     try:
         got = within_mask(xyz, r, o, cell, dist)
         assert lib.nda_last_filter() == TC
         assert np.array_equal(got, want)
         frac = want[n_ref:].mean()
         assert 0.2 < frac < 0.8                                         # both sides of the cut-off are populated
-        os.environ["NDA_TC_NO_SURE"] = "1"                              # same masks without the shortcut
+        _capi.set_option("NDA_TC_NO_SURE", "1")                         # same masks without the shortcut
         try:
             assert np.array_equal(within_mask(xyz, r, o, cell, dist), want)
         finally:
-            del os.environ["NDA_TC_NO_SURE"]
+            _capi.set_option("NDA_TC_NO_SURE", None)
     finally:
-        del os.environ["NDA_TC_ALLOW_PADDING"]
+        _capi.set_option("NDA_TC_ALLOW_PADDING", None)
 
 
 def test_within_literal_early_out_below_one_angstrom_on_tensor_path():
@@ -170,12 +163,9 @@ def test_filter_routing():
     want = port.within(xyz, r, o, cell, 3.0)
     assert np.array_equal(within_mask(xyz, r, o, cell, 3.0), want)
     assert lib.nda_last_filter() == TC
-    os.environ["NDA_FILTER"] = "fold2"
-    try:
+    with _capi.options(NDA_FILTER="fold2"):
         assert np.array_equal(within_mask(xyz, r, o, cell, 3.0), want)
         assert 2 <= lib.nda_last_filter() <= 5
-    finally:
-        del os.environ["NDA_FILTER"]
     nocell = np.full((2, 3), 100000.0, np.float32)                      # dcdCell.py:85-89
     assert np.array_equal(within_mask(xyz, r, o, nocell, 3.0), port.within(xyz, r, o, nocell, 3.0))
     assert lib.nda_last_filter() != TC
@@ -184,12 +174,9 @@ def test_filter_routing():
     assert lib.nda_last_filter() != TC                                  # 25 A in a 60 A cell: beyond ~0.34 c
     assert np.array_equal(rdf_counts(a, a, cell, 1, 149, 0.1), port.rdf_counts(a, a, cell, 1, 149, 0.1).astype(np.int64))
     assert lib.nda_last_filter() == TC                                  # 6.5 % of the pairs in range: still tensor
-    os.environ["NDA_TC_MAX_FRACTION"] = "0.01"                          # ... unless a density cap is asked for
-    try:
+    with _capi.options(NDA_TC_MAX_FRACTION="0.01"):                     # ... unless a density cap is asked for
         assert np.array_equal(rdf_counts(a, a, cell, 1, 149, 0.1), port.rdf_counts(a, a, cell, 1, 149, 0.1).astype(np.int64))
         assert lib.nda_last_filter() != TC
-    finally:
-        del os.environ["NDA_TC_MAX_FRACTION"]
     assert np.array_equal(rdf_counts(a, a, cell, 1, 30, 0.1), port.rdf_counts(a, a, cell, 1, 30, 0.1).astype(np.int64))
     assert lib.nda_last_filter() == TC                                  # 0.05 %: sparse
     tiny = np.arange(0, 9, dtype=np.int32)                              # 9 ref atoms would be padded to 256 columns
@@ -272,7 +259,7 @@ def test_long_ranges_up_to_half_the_cell(force_tc):
     cell = np.array([[31.0, 33.0, 30.5], [32.0, 31.5, 31.0]], np.float32)
     a = rng.uniform(-40, 70, (700, 2, 3)).astype(np.float32)
     b = rng.uniform(-40, 70, (300, 2, 3)).astype(np.float32)
-    os.environ["NDA_TC_RANGE_FACTOR"] = "3.9"
+    _capi.set_option("NDA_TC_RANGE_FACTOR", "3.9")
     try:
         for nb in (100, 149):                                           # 10 A and 14.9 A in a ~31 A cell
             assert np.array_equal(rdf_counts(a, a, cell, 1, nb, 0.1), port.rdf_counts(a, a, cell, 1, nb, 0.1).astype(np.int64))
@@ -285,4 +272,4 @@ def test_long_ranges_up_to_half_the_cell(force_tc):
             assert np.array_equal(within_mask(allA, r, o, cell, dist), port.within(allA, r, o, cell, dist))
             assert force_tc.nda_last_filter() == TC
     finally:
-        del os.environ["NDA_TC_RANGE_FACTOR"]
+        _capi.set_option("NDA_TC_RANGE_FACTOR", None)

@@ -221,3 +221,24 @@ def test_port_hb_corr_equals_reference(continuous):
     assert want[0] > 20 and want[-1] < want[0]               # bonds exist at t = 0 and decay
     if continuous:
         assert np.all(np.diff(want) <= 0)                    # an unbroken count can only go down
+
+
+def test_port_against_full_size_config2_golden():
+    """tests/golden/golden_ref_strict_full.npz (reference's own code on all 1000 frames of config 2): the C port
+    on every 10th frame -- hit counts and the CRC of the frame's bitmask words"""
+    import os
+    import zlib
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_ref_strict_full.npz")))
+    c = synth.config2(n_frames=1000)
+    assert crc(c["allAtoms"], c["cellDims"]) == g["c2full_crc"]
+    frames = np.arange(0, 1000, 10)
+    xyz = np.ascontiguousarray(c["allAtoms"][:, frames])
+    m = port.within(xyz, c["refSel"], c["outSel"], c["cellDims"][frames], c["distance"])
+    assert np.array_equal(m.sum(0), g["c2full_hits_per_frame"][frames])
+    flags = np.ascontiguousarray(m[c["outSel"]].T).astype(np.uint8)
+    words = (c["outSel"].size + 31) // 32
+    pad = np.zeros((frames.size, words * 32), np.uint8)
+    pad[:, :c["outSel"].size] = flags
+    bits = np.packbits(pad, axis=1, bitorder="little")
+    got = np.array([zlib.crc32(bits[i].tobytes()) for i in range(frames.size)], np.uint32)
+    assert np.array_equal(got, g["c2full_bits_frame_crc"][frames])

@@ -18,9 +18,9 @@ pairs = 20000.0 * 1231 * nF
 for nb in (30, 60, 100, 149, 200, 230):
     row = []
     for filt, frac in (("tc", "1.0"), ("fold2", None)):
-        os.environ["NDA_FILTER"] = filt
+        _capi.set_option("NDA_FILTER", filt)
         if frac:
-            os.environ["NDA_TC_MAX_FRACTION"] = frac
+            _capi.set_option("NDA_TC_MAX_FRACTION", frac)
         counts = torch.zeros((76, nb), dtype=torch.int64, device=dev)
         for _ in range(2):
             counts.zero_()

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Short, deterministic run of the three pair kernels for ncu (one launch each after a warm-up).
 
-    python tools/profile_run.py [within|rdf|dist|all]
+    python tools/profile_run.py [within|rdf|rdf3|dist|all] [frames] [--lib tools/variants/libnda_b200_<tag>.so]
 """
 import ctypes
 import sys
@@ -10,6 +10,9 @@ import torch
 
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from namdanalyzer_b200 import synth, _capi  # noqa: E402
+from tools import _lib  # noqa: E402
+
+_lib.use_variant()                     # --lib PATH: an experiment build of tools/build_variants.py
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 WITHIN_FRAMES = int(sys.argv[2]) if len(sys.argv) > 2 else 200

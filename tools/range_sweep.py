@@ -18,7 +18,7 @@ for n_side, nF in ((10, 100), (12, 100), (14, 60), (17, 40), (22, 20)):
     pairs = 0.5 * n * (n - 1.0) * nF
     row = []
     for filt in ("tc", "fold2"):
-        os.environ["NDA_FILTER"] = filt
+        _capi.set_option("NDA_FILTER", filt)
         counts = torch.zeros(149, dtype=torch.int64, device=dev)
         for _ in range(3):
             counts.zero_()

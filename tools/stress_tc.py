@@ -24,7 +24,7 @@ for it in range(n_iter):
     dist = float(rng.uniform(1.0, 0.25 * L))
     res = []
     for filt in ("tc", "fold2"):
-        os.environ["NDA_FILTER"] = filt
+        _capi.set_option("NDA_FILTER", filt)
         out = np.zeros(xyz.shape[:2], np.int32)
         plf.py_getWithin(xyz, r, o, out, cell, dist)
         if filt == "tc":

@@ -1,8 +1,7 @@
 #!/usr/bin/env python
 """Pipeline timeline of the tensor-core within kernel (CTA 0).  Needs a trace build of the library:
 
-    NDA_TC_TRACE_BUILD=1 python -m namdanalyzer_b200.build --force && python tools/tc_trace.py
-    python -m namdanalyzer_b200.build --force        # back to the production build
+    python tools/build_variants.py trace && python tools/tc_trace.py --lib tools/variants/libnda_b200_trace.so
 
 
 Per step g: when the MMA warp got its TMEM buffer back and had committed, when epilogue warps 0 and 15
@@ -13,6 +12,8 @@ import torch
 os.environ["NDA_TC_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from namdanalyzer_b200 import synth, _capi  # noqa: E402
+from tools import _lib  # noqa: E402
+_lib.use_variant()
 lib = _capi.load()
 dev = torch.device("cuda", 0)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
