@@ -919,11 +919,12 @@ static int dev_distances(Ctx &c, cudaStream_t st, const float *d_sel1, int n1, c
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, DIST_JT, smem));
     const long long slots = (long long)std::max(occ, 1) * c.numSMs;
-    // frames per work item: as long as possible (the pipeline prologue and the atomics are per item)
-    // while every resident block still gets >= 3 items
+    // frames per work item: ONE wave of equal items (every resident block gets exactly one, so nothing waits for a
+    // straggler), each as long as that allows -- the pipeline prologue and the atomics are per item
     const long long jTiles = (n2 + DIST_JT - 1) / DIST_JT;
-    int stages = 16;
-    while (stages > 1 && jTiles * zt * (((long long)(fe - fb) + stages * DIST_FS - 1) / (stages * DIST_FS)) < 3 * slots) stages >>= 1;
+    const long long wantChunks = std::max<long long>(1, slots / (jTiles * zt));
+    long long stagesLL = (((long long)(fe - fb) + wantChunks - 1) / wantChunks + DIST_FS - 1) / DIST_FS;
+    const int stages = (int)std::max<long long>(1, std::min<long long>(stagesLL, 1 << 20));
     const long long nFChunks = ((long long)(fe - fb) + (long long)stages * DIST_FS - 1) / ((long long)stages * DIST_FS);
     const long long items = jTiles * nFChunks;
     if (items > 0xfffffff0ll) return fail(NDA_ERR_ARG, "too many work items in one launch");

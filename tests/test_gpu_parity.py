@@ -40,10 +40,13 @@ def test_rdf_config1_full_golden(golden):
     got = rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, NB, 0.1)
     mism = np.flatnonzero(got != golden["c1_counts"])
     assert mism.size == 0, "edge-pair list not empty: bins %s" % mism
-    # the reference-shaped call: float32 density = count / nFrames, written in place
-    out = np.full(NB, 7.0, np.float32)
+    # the reference-shaped call: float32 density = count / nFrames, ADDED to what out holds (getRadialNbrDensity.cpp:40-41)
+    out = np.zeros(NB, np.float32)
     plf.py_getRadialNbrDensity(c["sel1"], c["sel1"], out, c["cellDims"], 1, 15.0, 0.1)
     assert np.array_equal(out, (golden["c1_counts"] / 100.0).astype(np.float32))
+    out = np.full(NB, 7.0, np.float32)
+    plf.py_getRadialNbrDensity(c["sel1"], c["sel1"], out, c["cellDims"], 1, 15.0, 0.1)
+    assert np.array_equal(out, np.float32(7.0) + (golden["c1_counts"] / 100.0).astype(np.float32))
 
 
 def test_rdf_two_selections_and_odd_bin_width_golden(golden):

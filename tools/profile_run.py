@@ -58,7 +58,7 @@ if what in ("rdf", "all"):
     st4 = (ctypes.c_double * 4)()
     print("rdf: %.3f ms, %.3e pairs/s, in-range %d" % (t, pairs / t * 1e3, int(counts.sum().item())))
 
-if what in ("rdf3",):
+if what in ("rdf3", "all"):
     nF = 60
     c = synth.config3(n_frames=nF)
     w_, p_ = torch.from_numpy(c["waters"]).to(dev), torch.from_numpy(c["protein"]).to(dev)
@@ -74,7 +74,7 @@ if what in ("rdf3",):
     print("rdf3 (grouped, config 3): %.3f ms, %.3e pairs/s, in-range %d" % (t, pairs / t * 1e3, int(counts.sum().item())))
 
 if what in ("dist", "all"):
-    nF = 2000
+    nF = 10000                                      # config 4 at full size
     c = synth.config4(n_frames=nF)
     a, b = torch.from_numpy(c["sel1"]).to(dev), torch.from_numpy(c["sel2"]).to(dev)
     cell = torch.from_numpy(c["cellDims"]).to(dev)
