@@ -690,6 +690,22 @@ def multi_gpu_legs(E, cfg):
                 plf.py_getWithin(xyz_np, rs, os_, out_np, cell_np, 3.0)
             all_ms = timed_calls(lambda: plf.py_getWithin(xyz_np, rs, os_, out_np, cell_np, 3.0), 8, torch.cuda.synchronize) * 1e3
             bits_all = plf.py_getWithinBits(xyz_np, rs, os_, cell_np, 3.0)
+            # the same call on the same array after namdanalyzer_b200.pin(): every device DMAs its own frame columns
+            # over its own link, no gather through host staging (which is bounded by the host's memory bandwidth)
+            import namdanalyzer_b200 as nda
+            nda.pin(xyz_np)
+            try:
+                for _ in range(2):
+                    plf.py_getWithin(xyz_np, rs, os_, out_np, cell_np, 3.0)
+                pin_all_ms = timed_calls(lambda: plf.py_getWithin(xyz_np, rs, os_, out_np, cell_np, 3.0), 8, torch.cuda.synchronize) * 1e3
+                bits_pin = plf.py_getWithinBits(xyz_np, rs, os_, cell_np, 3.0)
+                capi.check(lib.nda_set_device(E.local_rank))
+                for _ in range(2):
+                    plf.py_getWithin(xyz_np, rs, os_, out_np, cell_np, 3.0)
+                pin_one_ms = timed_calls(lambda: plf.py_getWithin(xyz_np, rs, os_, out_np, cell_np, 3.0), 5, torch.cuda.synchronize) * 1e3
+                capi.set_devices(list(range(world)))
+            finally:
+                nda.unpin(xyz_np)
             c1 = synth.config1()
             nb = synth.n_bins(c1["dr"], c1["maxR"])
             h_all = plf.py_getRadialNbrCounts(c1["sel1"], c1["sel1"], c1["cellDims"], 1, nb, c1["dr"])
@@ -705,6 +721,12 @@ def multi_gpu_legs(E, cfg):
         drop = {"api": "nda_set_devices(0..%d) + py_getWithin / py_getRadialNbrCounts / py_getDistancesSum, plain numpy, ONE process" % (world - 1),
                 "within_config2_e2e_ms": all_ms, "within_config2_e2e_pairs_per_s": pairs2 / (all_ms * 1e-3),
                 "within_config2_one_gpu_e2e_ms": one_ms, "speedup_vs_one_gpu": one_ms / all_ms,
+                "note": "pageable input: the rows are gathered into pinned staging by host threads, a host-memory-bandwidth "
+                        "bound that more GPUs cannot lift; page-locked input (namdanalyzer_b200.pin) is pulled by every device "
+                        "over its own link",
+                "pinned": {"within_config2_e2e_ms": pin_all_ms, "within_config2_e2e_pairs_per_s": pairs2 / (pin_all_ms * 1e-3),
+                           "within_config2_one_gpu_e2e_ms": pin_one_ms, "speedup_vs_one_gpu": pin_one_ms / pin_all_ms,
+                           "within_bits_equal_one_gpu": bool(np.array_equal(bits_one, bits_pin))},
                 "distances_config4_e2e_ms": d_ms, "distances_config4_one_gpu_e2e_ms": d1_ms,
                 "collective": {0: "none", 1: "ncclAllReduce (ncclCommInitAll)", 2: "host sum"}.get(coll, str(coll)),
                 "parity": {"within_bits_equal_one_gpu": bool(np.array_equal(bits_one, bits_all)),

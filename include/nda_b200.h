@@ -257,6 +257,13 @@ int nda_measure_fp32_peak(int variant, double *tflops);
  * [2] frames that ran in all-exact mode (cut-off >= half the box), [3] kernel ms. */
 int nda_last_stats(double stats[4]);
 
+/* Page-lock (cudaHostRegister) a caller's array so that the host entry points DMA it directly with
+ * strided 2-D copies -- no gather through pinned staging, which is bounded by the host's memory
+ * bandwidth and does not scale with the number of devices.  The array must stay alive until
+ * nda_host_unregister(ptr).  Python: namdanalyzer_b200.pin(array) / unpin(array). */
+int nda_host_register(const void *ptr, size_t bytes);
+int nda_host_unregister(const void *ptr);
+
 /* Platform ceiling for the end-to-end numbers: `bytes` of contiguous pinned host memory copied to EVERY
  * device of the calling thread at the same time (one plain cudaMemcpyAsync each, `reps` times, one host
  * thread per device); *gbps = aggregate rate over the slowest device's time. */

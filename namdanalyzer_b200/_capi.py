@@ -31,6 +31,8 @@ SIGNATURES = {
     "nda_shutdown": (c_int, []),
     "nda_debug_tc_probe": (c_int, [ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_uint16), c_u32p]),
     "nda_measure_h2d": (c_int, [ctypes.c_size_t, c_int, c_f64p]),
+    "nda_host_register": (c_int, [c_void_p, ctypes.c_size_t]),
+    "nda_host_unregister": (c_int, [c_void_p]),
     "nda_launch_count": (ctypes.c_uint64, []),
     "nda_launch_count_reset": (None, []),
     "nda_set_within_pure_predicate": (c_int, [c_int]),

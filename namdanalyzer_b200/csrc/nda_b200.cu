@@ -22,6 +22,7 @@
 #include <type_traits>
 #include <dlfcn.h>
 #include <condition_variable>
+#include <functional>
 #include <map>
 
 #include "../../include/nda_b200.h"
@@ -614,7 +615,7 @@ static int dev_within_tc(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_a
     a.wordsPerFrame = words;
     a.d2 = d2;
     a.literal = g_within_pure.load() ? 0 : 1;
-    const size_t smem = tc_smem_base();
+    const size_t smem = tc_smem_base() + TC_WITHIN_STAGE_BYTES;
     CK(cudaFuncSetAttribute((const void *)within_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int f0 = fb; f0 < fe; f0 += pass) {
@@ -1390,8 +1391,64 @@ static int plan_shards(int fb, int fe, std::vector<Shard> &sh)
     return NDA_OK;
 }
 
-// one host thread per shard; fn(g, ctx) runs with the shard's device current and its context locked.
-// Returns the first failure (message copied into the caller's nda_last_error()).
+// One PERSISTENT host thread per device (started on first use, parked on a condition variable between calls):
+// a fresh std::thread per call would also make libgomp build a fresh thread team for the row gather on every
+// call (its pools belong to the thread that opens the parallel region) -- measured: a 2-device call took 5.5 ms
+// against 3.7 ms on one device before the workers were made persistent.
+struct DeviceWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool hasJob = false, done = false, quit = false, started = false;
+    void loop()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return hasJob || quit; });
+            if (quit) return;
+            lk.unlock();
+            job();
+            lk.lock();
+            hasJob = false;
+            done = true;
+            cv.notify_all();
+        }
+    }
+    void post(std::function<void()> f)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        if (!started) { started = true; th = std::thread([this] { loop(); }); }
+        job = std::move(f);
+        done = false;
+        hasJob = true;
+        cv.notify_all();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return done; });
+    }
+    void stop()
+    {
+        {
+            std::unique_lock<std::mutex> lk(m);
+            if (!started) return;
+            quit = true;
+            cv.notify_all();
+        }
+        th.join();
+        started = false;
+        quit = false;
+    }
+    ~DeviceWorker() { stop(); }
+};
+static DeviceWorker g_workers[16];
+static std::mutex g_workers_mutex;                          // one multi-device call at a time uses the workers
+
+// fn(g, ctx) runs on the worker of shard g's device, with that device current and its context locked; a
+// single shard runs on the calling thread.  Returns the first failure (message copied into the caller's
+// nda_last_error()).
 template <class Fn>
 static int run_shards(const std::vector<Shard> &sh, Fn fn)
 {
@@ -1413,9 +1470,9 @@ static int run_shards(const std::vector<Shard> &sh, Fn fn)
     };
     if (G == 1) body(0);
     else {
-        std::vector<std::thread> th;
-        for (int g = 0; g < G; ++g) th.emplace_back(body, g);
-        for (auto &t : th) t.join();
+        std::lock_guard<std::mutex> lk(g_workers_mutex);
+        for (int g = 0; g < G; ++g) g_workers[sh[g].dev].post([&body, g] { body(g); });
+        for (int g = 0; g < G; ++g) g_workers[sh[g].dev].wait();
     }
     g_dev = callerDev;
     if (callerDev >= 0) cudaSetDevice(callerDev);
@@ -1782,6 +1839,10 @@ int nda_set_option(const char *name, const char *value)
 // the next call builds them again
 int nda_shutdown(void)
 {
+    {
+        std::lock_guard<std::mutex> lk(g_workers_mutex);
+        for (auto &w : g_workers) w.stop();
+    }
     {
         std::lock_guard<std::mutex> lk(g_nccl.mu);
         for (auto &kv : g_nccl.comms)
@@ -2386,6 +2447,31 @@ int nda_measure_fp32_peak(int variant, double *tflops)
         if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
     }
     *tflops = best;
+    return NDA_OK;
+}
+
+// Page-lock a caller's array (cudaHostRegister) so the host entry points DMA it directly -- strided 2-D copies
+// straight from the array, no gather through staging -- which is what lets several devices pull their frame
+// columns at link rate at the same time.  The caller keeps the array alive until nda_host_unregister.
+int nda_host_register(const void *ptr, size_t bytes)
+{
+    if (!ptr || bytes == 0) return fail(NDA_ERR_ARG, "null pointer / empty range");
+    Ctx *c;
+    int rc = ctx_get(&c);
+    if (rc) return rc;
+    cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+    if (e != cudaSuccess) {                                 // read-only registration is not available on every platform
+        cudaGetLastError();
+        e = cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterPortable);
+    }
+    if (e != cudaSuccess) return fail(NDA_ERR_CUDA, "cudaHostRegister of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return NDA_OK;
+}
+
+int nda_host_unregister(const void *ptr)
+{
+    if (!ptr) return fail(NDA_ERR_ARG, "null pointer");
+    CK(cudaHostUnregister(const_cast<void *>(ptr)));
     return NDA_OK;
 }
 

@@ -53,6 +53,13 @@ constexpr int TC_TMA_WARP  = TC_EPI_WARPS + 1;                 // warp 17 issues
 #endif
 constexpr bool TC_RDF_UNROLL_GROUPED = NDA_TC_RDF_UNROLL_GROUPED != 0;
 constexpr int TC_WITHIN_MAX_STEPS = 128;   // within: streamed blocks per work item <= (step, lanes) records a warp can hold (TC_QCAP * 2)
+#ifndef NDA_TC_WITHIN_STAGED
+#define NDA_TC_WITHIN_STAGED 8
+#endif
+// within: original coordinates of the first N flagged steps of an item are copied to shared memory (cp.async) when the
+// step is flagged, so that resolve() at the item boundary does not sit in one L2 round trip per flagged step
+constexpr int TC_WITHIN_STAGED = NDA_TC_WITHIN_STAGED;
+constexpr size_t TC_WITHIN_STAGE_BYTES = (size_t)TC_WITHIN_STAGED * 32 * 16 * 16;   // per CTA: 16 warps x N steps x 32 lanes x float4
 constexpr int TC_STAGE_FREE_WARP = 2;      // within kernel: the epilogue warp that releases a stage once its MMAs are done
 constexpr int TC_THREADS   = (TC_EPI_WARPS + 2) * 32;          // 576
 constexpr int TC_SBLK      = 128;                              // streamed atoms per step (MMA M)
@@ -279,6 +286,28 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity)
                      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
+
+// polling wait: mbarrier.test_wait never suspends the warp, so the waiter sees the phase flip a few clocks after it
+// happens instead of after try_wait's suspend / wake-up round (experiment switches NDA_TC_MMA_SPIN / NDA_TC_EPI_SPIN)
+__device__ __forceinline__ void bar_spin(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+#ifdef NDA_TC_MMA_SPIN
+#define TC_MMA_WAIT bar_spin
+#else
+#define TC_MMA_WAIT bar_wait
+#endif
+#ifdef NDA_TC_EPI_SPIN
+#define TC_EPI_WAIT bar_spin
+#else
+#define TC_EPI_WAIT bar_wait
+#endif
 
 __device__ __forceinline__ void tma_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -531,7 +560,7 @@ __device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem, cons
     unsigned kt = 0, slot = 0, sphase = 0, g = 0;
     for (;;) {
         tc_stamp(trace, g, 2);                                   // trace: about to wait for the stage
-        bar_wait(full0 + slot * 8, sphase);
+        TC_MMA_WAIT(full0 + slot * 8, sphase);
         tc_stamp(trace, g, 3);                                   // trace: stage has landed
         const unsigned info = s.info[slot];
         if (info & TC_INFO_STOP) break;
@@ -542,7 +571,7 @@ __device__ __forceinline__ void tc_mma_warp(const TcSmem &s, uint32_t tmem, cons
             const unsigned h = g & 1u;
             const uint64_t da = tc_smem_desc(sBase + slot * TC_STAGE_BYTES + u * TC_SEMB_BYTES, TC_SBLK * 16);
             tc_stamp(trace, g, 6);                               // trace: about to wait for the TMEM buffer
-            bar_wait(tempty0 + h * 8, ((g >> 1) & 1u) ^ 1u);     // epilogue has read this buffer's previous step
+            TC_MMA_WAIT(tempty0 + h * 8, ((g >> 1) & 1u) ^ 1u);  // epilogue has read this buffer's previous step
             tc_fence_after();
             tc_stamp(trace, g, 0);
             if (tc_elect_one()) {
@@ -632,7 +661,7 @@ struct TcEpi {
     __device__ __forceinline__ void load_step_hp(unsigned h, unsigned parity, unsigned g, uint32_t (&r)[32], uint32_t (&gb)[8],
                                                  bool &cand, const long long *trace = nullptr) const
     {
-        bar_wait(tfull0 + h * 8, parity);
+        TC_EPI_WAIT(tfull0 + h * 8, parity);
         tc_fence_after();
 #ifdef NDA_TC_TRACE_BUILD
         if (trace && (cq * 4 + q == 0 || cq * 4 + q == 15)) tc_stamp(trace, g, cq * 4 + q == 0 ? 4 : 8);
@@ -916,6 +945,7 @@ within_tc_kernel(const WithinTcArgs p)
         // with the reference arithmetic at the end of the item (resolve()).
         constexpr int kFlagCap = TC_WITHIN_MAX_STEPS;          // (step, ballot) pairs in this warp's ring space
         uint2 *flags = reinterpret_cast<uint2 *>(s.sQ + warp * TC_QCAP);
+        float4 *staged = reinterpret_cast<float4 *>(s.extra) + (size_t)warp * TC_WITHIN_STAGED * 32;   // [TC_WITHIN_STAGED][32 lanes]
         unsigned g = 0, kt = 0, nCand = 0, slot = 0;
         const bool freesStages = warp == TC_STAGE_FREE_WARP;   // this warp hands finished stages back to the TMA warp
 
@@ -952,13 +982,15 @@ within_tc_kernel(const WithinTcArgs p)
             // recorded (step, lanes): the 64 resident atoms of this warp are re-evaluated with the reference
             // arithmetic, two per lane, for every recorded streamed atom
             auto resolve = [&]() {
+                if (TC_WITHIN_STAGED > 0) asm volatile("cp.async.wait_all;" ::: "memory");   // this lane's staged coordinates have landed
                 __syncwarp();
                 const FrameParams fpar = tfS->fp;
                 const float4 b0 = rOrig[lane], b1 = rOrig[32 + lane];
                 for (int i = 0; i < nf; ++i) {
                     const uint2 fl = flags[i];
                     const int word = (int)fl.x * (TC_SBLK / 32) + ep.q;
-                    const float4 ao = __ldg(&Aglob[(int)fl.x * TC_SBLK + ep.q * 32 + lane]);
+                    const float4 ao = (i < TC_WITHIN_STAGED) ? staged[i * 32 + lane]
+                                                            : __ldg(&Aglob[(int)fl.x * TC_SBLK + ep.q * 32 + lane]);
                     unsigned owners = fl.y, hits = 0u;
                     while (owners) {
                         const int o = __ffs(owners) - 1;
@@ -1012,9 +1044,15 @@ within_tc_kernel(const WithinTcArgs p)
                         // an item has at most kFlagCap steps (the host caps chunkS), so the list cannot overflow
                         if (nf == kFlagCap) __trap();
                         if (lane == 0) flags[nf] = make_uint2((unsigned)sb, bal);
+                        // resolve() will need these 32 atoms' original coordinates: start pulling them in now -- into shared
+                        // memory for the first TC_WITHIN_STAGED flagged steps of the item (each lane copies and later reads
+                        // its own 16 bytes), into L2 for the rest
+                        const float4 *src = &Aglob[sb * TC_SBLK + ep.q * 32 + lane];
+                        if (nf < TC_WITHIN_STAGED)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_u32(&staged[nf * 32 + lane])), "l"(src) : "memory");
+                        else
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(src));
                         ++nf;
-                        // resolve() will need these 32 atoms' original coordinates: start pulling them in now
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(&Aglob[sb * TC_SBLK + ep.q * 32 + lane]));
                     }
                 }
             };

@@ -321,7 +321,17 @@ def test_frames_sharded_over_devices_in_one_process(collective):
             iu = np.triu_indices(7, 1)
             assert np.max(np.abs(ds[iu] - dsw[iu]) / dsw[iu]) < 1e-12 and np.array_equal(ds, ds.T)
             # fewer frames than devices
-            got = plf.py_getRadialNbrCounts(c1["sel1"][:, :1], c1["sel1"][:, :1], c1["cellDims"][:1], 1, nb, c1["dr"])
-            assert np.array_equal(got, port.rdf_counts(c1["sel1"][:, :1], c1["sel1"][:, :1], c1["cellDims"][:1], 1, nb, c1["dr"]))
+            one = np.ascontiguousarray(c1["sel1"][:, :1])
+            got = plf.py_getRadialNbrCounts(one, one, c1["cellDims"][:1], 1, nb, c1["dr"])
+            assert np.array_equal(got, port.rdf_counts(one, one, c1["cellDims"][:1], 1, nb, c1["dr"]))
+            # page-locked input (namdanalyzer_b200.pin): every device DMAs its own frame columns straight from the array
+            import namdanalyzer_b200 as nda
+            xyz = nda.pin(c["allAtoms"].copy())
+            try:
+                out2 = np.zeros_like(out)
+                plf.py_getWithin(xyz, c["refSel"], c["outSel"], out2, c["cellDims"], 3.0)
+                assert np.array_equal(out2, out)
+            finally:
+                nda.unpin(xyz)
     finally:
         _capi.check(lib.nda_set_device(0))
