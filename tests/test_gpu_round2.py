@@ -85,19 +85,30 @@ def test_tc_fp16_accumulator_is_the_rounded_exact_sum():
     rng = np.random.default_rng(20)
     total = near = 0
     worst = 0.0
-    for rep in range(34):
+    for rep in range(44):
         c = np.array([rng.uniform(25, 90), rng.uniform(25, 90), rng.uniform(25, 90)])
         rho2 = (c / (2 * np.pi)) ** 2
         P = rho2.sum()
-        cut = rng.uniform(2.5, 0.2 * c.min())
+        shell = rep % 5 != 4
+        # (shell probes: cut <= 0.06 c, where the chord sum S is within ~1 % of r^2 and D really is near zero at r = cut)
+        cut = rng.uniform(2.5, max(2.6, 0.06 * c.min())) if shell else rng.uniform(2.5, 0.2 * c.min())
         thr = cut * cut
         E = P * (2.0 ** -11 * 1.01 + 2.0 ** -18)
         thrDot = np.float32(P - 0.5 * thr - 1.25 * E)
-        xa = rng.uniform(-2 * c, 3 * c, (128, 3))
-        # every B atom sits at ~cut from some A atom: a shell of relative width 2 %
-        u = rng.standard_normal((256, 3))
-        u /= np.linalg.norm(u, axis=1)[:, None]
-        xb = xa[rng.integers(0, 128, 256)] + u * cut * rng.uniform(0.98, 1.02, (256, 1))
+        if shell:
+            # ALL 128 x 256 pairs at the cut-off: the A atoms on a sphere of radius ~cut around a centre somewhere in
+            # (or many cells away from) the box, the B atoms in a small ball around that centre -> every D is near zero
+            centre = rng.uniform(-2 * c, 3 * c, 3)
+            u = rng.standard_normal((128, 3))
+            u /= np.linalg.norm(u, axis=1)[:, None]
+            xa = centre + u * cut * rng.uniform(0.995, 1.005, (128, 1))
+            xb = centre + rng.uniform(-0.005, 0.005, (256, 3)) * cut
+        else:
+            # a random box (D from -2 P to +thr / 2) with every B atom at ~cut from some A atom, and a few padding atoms
+            xa = rng.uniform(-2 * c, 3 * c, (128, 3))
+            u = rng.standard_normal((256, 3))
+            u /= np.linalg.norm(u, axis=1)[:, None]
+            xb = xa[rng.integers(0, 128, 256)] + u * cut * rng.uniform(0.98, 1.02, (256, 1))
         ea, eb = _embed64(xa, c), _embed64(xb, c)
         A = np.zeros((128, 16), np.float16)
         B = np.zeros((256, 16), np.float16)
@@ -137,7 +148,7 @@ def test_tc_fp16_accumulator_is_the_rounded_exact_sum():
         total += ex.size
         near += int(np.sum(small))
     assert total >= 1_000_000
-    assert near >= 50_000                        # plenty of decisions close to the threshold
+    assert near >= 1_000_000                     # a million decisions within P / 256 of the threshold
     assert worst <= 2.0 ** -16                   # near the decision the accumulator is within 1.6e-5 P of the exact sum (reserve 0.25 E = 1.2e-4 P)
     print("tc probe: %d pairs, %d near the threshold, worst |D - exact| / P there = %.3g" % (total, near, worst))
 
