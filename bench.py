@@ -677,6 +677,8 @@ def multi_gpu_legs(E, cfg):
     # ---- the drop-in call itself sharding over all GPUs inside ONE process (rank 0; the other ranks wait on the host)
     drop = None
     if rank == 0:
+        # the other ranks are parked on a host barrier: this process may use the host threads a single process would
+        capi.set_option("NDA_HOST_THREADS", str(max(1, min(16, os.cpu_count() or 1))))
         c2 = synth.config2(n_frames=1000, seed=1002)
         rs, os_ = c2["refSel"], c2["outSel"]
         xyz_np, cell_np = c2["allAtoms"], c2["cellDims"]
@@ -718,6 +720,7 @@ def multi_gpu_legs(E, cfg):
         h_one = plf.py_getRadialNbrCounts(c1["sel1"], c1["sel1"], c1["cellDims"], 1, nb, c1["dr"])
         s_one = plf.py_getDistancesSum(c4["sel1"], c4["sel2"], c4["cellDims"], 0)
         d1_ms = timed_calls(lambda: plf.py_getDistancesSum(c4["sel1"], c4["sel2"], c4["cellDims"], 0), 3, torch.cuda.synchronize) * 1e3
+        capi.set_option("NDA_HOST_THREADS", None)
         drop = {"api": "nda_set_devices(0..%d) + py_getWithin / py_getRadialNbrCounts / py_getDistancesSum, plain numpy, ONE process" % (world - 1),
                 "within_config2_e2e_ms": all_ms, "within_config2_e2e_pairs_per_s": pairs2 / (all_ms * 1e-3),
                 "within_config2_one_gpu_e2e_ms": one_ms, "speedup_vs_one_gpu": one_ms / all_ms,

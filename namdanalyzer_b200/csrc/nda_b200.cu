@@ -340,7 +340,7 @@ static int default_host_threads()
         for (const char *name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE"}) {
             const char *e = getenv(name);
             const int ranks = e ? atoi(e) : 0;
-            if (ranks > 1) { t = std::max(1, std::min(t, (int)hw / ranks)); break; }
+            if (ranks > 1) { t = std::max(1, std::min(16, (int)hw / ranks)); break; }   // the ranks share the cores, not the cap of 16
         }
         return t;
     }();
