@@ -346,3 +346,27 @@ def test_frames_sharded_over_devices_in_one_process(collective):
                 nda.unpin(xyz)
     finally:
         _capi.check(lib.nda_set_device(0))
+
+
+# ------------------------------------------------------------------------------------------------ stress / determinism
+def _run_tool(name, env):
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", name)], capture_output=True, text=True, timeout=600, env=e, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_stress_random_shapes_tensor_vs_fp32_filter():
+    """tools/stress_tc.py: random shapes / frame counts / ranges, tensor-core filter against the packed-FP32 filter
+    (within masks, two-selection and same-selection histograms must be identical); shakes out hand-over races"""
+    out = _run_tool("stress_tc.py", {"ITERS": "120", "SEED": "5"})
+    assert "stress ok" in out
+
+
+def test_repeated_calls_are_bit_identical():
+    """tools/repeat_check.py: the same 300-frame config-2 call 60 times -- every bitmask identical to the first"""
+    out = _run_tool("repeat_check.py", {"NF": "300", "REPS": "60"})
+    assert "calls with differences: 0" in out, out[-500:]

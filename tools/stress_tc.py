@@ -10,7 +10,7 @@ from namdanalyzer_b200.lib import pylibFuncs as plf
 lib = _capi.load()
 rng = np.random.default_rng(int(os.environ.get("SEED", "1")))
 n_iter = int(os.environ.get("ITERS", "400"))
-os.environ["NDA_TC_ALLOW_PADDING"] = "1"
+_capi.set_option("NDA_TC_ALLOW_PADDING", "1")
 t0 = time.time()
 n_tc = 0
 for it in range(n_iter):
