@@ -1467,6 +1467,13 @@ static int run_shards(const std::vector<Shard> &sh, Fn fn)
     std::vector<int> rcs((size_t)G, NDA_OK);
     std::vector<std::string> errs((size_t)G);
     const int callerDev = g_dev;
+    // every context exists before a worker starts: a device that cannot be set up fails the call here, not inside a
+    // worker whose peers would then wait for it at the merge barrier
+    for (int g = 0; g < G; ++g) {
+        Ctx *c = nullptr;
+        const int rc = ctx_for(sh[g].dev, &c);
+        if (rc) { if (callerDev >= 0) cudaSetDevice(callerDev); return rc; }
+    }
     auto body = [&](int g) {
         g_dev = sh[g].dev;
         Ctx *c = nullptr;
@@ -1474,7 +1481,7 @@ static int run_shards(const std::vector<Shard> &sh, Fn fn)
         if (!rc) {
             std::lock_guard<std::mutex> lk(c->mu);
             begin_call(*c, G);
-            rc = fn(g, *c);
+            rc = fn(g, *c);                                 // fn reaches the merge barrier on every path (merge_partials)
         }
         rcs[g] = rc;
         if (rc) errs[g] = g_err;
@@ -2116,7 +2123,9 @@ int nda_get_distances_sum(const float *sel1, int n1, const float *sel2, int n2, 
         if (!r && sameSel && G == 1) {
             dim3 grid((n1 + 255) / 256, std::min(n1, 4096));
             symmetrize_kernel<<<grid, 256, 0, c.stream>>>(c.sum.as<double>(), n1);
-            LAUNCHED();
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            const cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) r = fail(NDA_ERR_CUDA, "symmetrize_kernel launch failed: %s", cudaGetErrorString(e));
         }
         r = merge_partials<double>(m, g, G, c, c.stream, c.sum.as<double>(), M, sum, r);
         if (r) return r;
