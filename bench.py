@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=1000, help="frames per step (BASELINE: 1000)")
     ap.add_argument("--no-extras", action="store_true", help="headline + e2e only (A/B runs)")
     ap.add_argument("--sustain-s", type=float, default=2.2, help="length of the sustained loop in seconds")
+    ap.add_argument("--rdf-full-frames", type=int, default=10000,
+                    help="frames of the full-length config-5 RDF pass (BASELINE: 10000; ~33 s on one B200; 0 skips it)")
     return ap.parse_args()
 
 
@@ -292,6 +294,13 @@ class Env:
     pass
 
 
+def gen_frames(E, xyz, cell, stride, gfb, gfe, Lbox):
+    """frames [gfb, gfe) of the config-5 generator into a LOCAL array whose column 0 is frame gfb (row stride `stride` frames)"""
+    if gfe > gfb:
+        E.capi.check(E.lib.nda_dev_synth_water_box_slice(xyz.data_ptr(), cell.data_ptr(), N_SIDE5, stride, gfb, gfe - gfb,
+                                                         Lbox, 0.6, 1005, E.st))
+
+
 def kernel_ms(E):
     ms = ctypes.c_double(0.0)
     nl = ctypes.c_int(0)
@@ -429,7 +438,39 @@ def rdf_leg(E, peak_fp32, n_frames=64, e2e_frames=12):
                   "h2d_bytes_per_step": int(h_xyz.nbytes + h_cell.nbytes), "d2h_bytes_per_step": 149 * 8,
                   "api": "namdanalyzer_b200.lib.pylibFuncs.py_getRadialNbrDensity (pageable numpy arrays)",
                   "equals_resident_result": bool(np.array_equal(h_out, want))}
+    hist64 = None
+    go(0, n_frames)
+    hist64 = counts.cpu().numpy().copy()
     del xyz, h_xyz
+    # ---- BASELINE configs[4] at its stated length: 10 000 frames, the whole trajectory resident in HBM
+    nFull = E.args.rdf_full_frames
+    if nFull > 0:
+        torch.cuda.empty_cache()
+        xyz = torch.empty((n, nFull, 3), dtype=torch.float32, device=E.dev)
+        cell = torch.empty((nFull, 3), dtype=torch.float32, device=E.dev)
+        capi.check(lib.nda_dev_synth_water_box(xyz.data_ptr(), cell.data_ptr(), N_SIDE5, nFull, 0, nFull, L, 0.6, 1005, E.st))
+
+        def gof(fb, fe):
+            counts.zero_()
+            capi.check(lib.nda_dev_radial_nbr_counts(xyz.data_ptr(), n, xyz.data_ptr(), n, None, 1, counts.data_ptr(), 149,
+                                                     cell.data_ptr(), nFull, fb, fe, 1, 0.1, E.st))
+        gof(0, min(n_frames, nFull))
+        same = bool(np.array_equal(counts.cpu().numpy(), hist64)) if nFull >= n_frames else None
+        torch.cuda.synchronize()
+        e0.record(E.stream)
+        gof(0, nFull)
+        e1.record(E.stream)
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3
+        kf_ms, kf_n = kernel_ms(E)
+        out["full_size"] = {"workload": "BASELINE configs[4] at its stated length: %d O atoms x %d frames, %.1f GB of coordinates generated and "
+                                        "resident in HBM, ONE call" % (n, nFull, n * nFull * 12 / 1e9),
+                            "pairs": per_frame * nFull, "seconds": sec, "value": per_frame * nFull / sec, "unit": "pairs/s",
+                            "pair_kernel_seconds": kf_ms * 1e-3, "pair_kernel_launches": kf_n,
+                            "counts_total": int(counts.sum().item()),
+                            "first_%d_frames_equal_the_%d_frame_run" % (n_frames, n_frames): same}
+        del xyz, cell
+        torch.cuda.empty_cache()
     return out
 
 
@@ -588,61 +629,100 @@ def multi_gpu_legs(E, cfg):
     del c4
     hbar()
 
-    # ---- RDF, config-5 shape, ONE trajectory of 64 frames generated on the devices: u64 histogram + one NCCL all-reduce
-    n = N_SIDE5 ** 3
-    nF = 64
-    fb, fe = frame_range(nF, rank, world)
-    Lbox = float(np.float32((n / 0.0334) ** (1.0 / 3.0)))
-    own = fe - fb if rank != 0 else nF                      # rank 0 also holds every frame for the parity pass
-    gen_b, gen_e = (fb, fe) if rank != 0 else (0, nF)
-    xyz = torch.empty((n, nF if rank == 0 else own, 3), dtype=torch.float32, device=E.dev)
-    cell = torch.empty((nF if rank == 0 else own, 3), dtype=torch.float32, device=E.dev)
-    if rank == 0:
-        capi.check(lib.nda_dev_synth_water_box(xyz.data_ptr(), cell.data_ptr(), N_SIDE5, nF, 0, nF, Lbox, 0.6, 1005, E.st))
-        lfb, lfe, lnF = fb, fe, nF
-    else:
-        # generate frames [fb, fe) of the same trajectory into a local array that only holds them: the generator writes
-        # frame f at column f, so point it `fb` columns before the local array (only columns [fb, fe) are touched)
-        capi.check(lib.nda_dev_synth_water_box(xyz.data_ptr() - fb * 12, cell.data_ptr() - fb * 12, N_SIDE5, nF, fb, fe, Lbox, 0.6, 1005, E.st)) \
-            if False else None
-        lfb, lfe, lnF = 0, own, own
-    if rank != 0:
-        # the generator's row stride is its nbrFrames argument: generate with nbrFrames = own and a seed-consistent frame offset is
-        # not expressible, so non-zero ranks generate the full-stride array slice by slice instead
-        full = torch.empty((n, nF, 3), dtype=torch.float32, device=E.dev)
-        fcell = torch.empty((nF, 3), dtype=torch.float32, device=E.dev)
-        capi.check(lib.nda_dev_synth_water_box(full.data_ptr(), fcell.data_ptr(), N_SIDE5, nF, fb, fe, Lbox, 0.6, 1005, E.st))
-        xyz, cell, lfb, lfe, lnF = full, fcell, fb, fe, nF
-    counts = torch.zeros(149, dtype=torch.int64, device=E.dev)
-
-    def go():
-        counts.zero_()
-        capi.check(lib.nda_dev_radial_nbr_counts(xyz.data_ptr(), n, xyz.data_ptr(), n, None, 1, counts.data_ptr(), 149,
-                                                 cell.data_ptr(), lnF, lfb, lfe, 1, 0.1, E.st))
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)       # NCCL, on the current (= launching) stream
-    go()
+    # ---- RDF O-O, config 1 (1000 O x 100 frames, FP32 filter) and residue-wise water RDF, config 3 at 5000 frames:
+    #      host arrays, frames sharded, one NCCL all-reduce of the integer histogram each
+    c1 = synth.config1()
+    nb = synth.n_bins(c1["dr"], c1["maxR"])
+    for _ in range(2):
+        h1 = nd.radial_nbr_counts(c1["sel1"], c1["sel1"], c1["cellDims"], 1, nb, c1["dr"])
     hbar()
-    reps = 3
-    e0.record(E.stream)
-    for _ in range(reps):
-        go()
-    e1.record(E.stream)
-    torch.cuda.synchronize()
-    ms = max_over_ranks(E, e0.elapsed_time(e1) / reps)
-    sharded = counts.cpu().numpy().copy()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        h1 = nd.radial_nbr_counts(c1["sel1"], c1["sel1"], c1["cellDims"], 1, nb, c1["dr"])
+    dt = max_over_ranks(E, (time.perf_counter() - t0) / 5)
     parity = None
     if rank == 0:
-        alone = torch.zeros(149, dtype=torch.int64, device=E.dev)
-        capi.check(lib.nda_dev_radial_nbr_counts(xyz.data_ptr(), n, xyz.data_ptr(), n, None, 1, alone.data_ptr(), 149,
-                                                 cell.data_ptr(), nF, 0, nF, 1, 0.1, E.st))
+        parity = bool(np.array_equal(h1, plf.py_getRadialNbrCounts(c1["sel1"], c1["sel1"], c1["cellDims"], 1, nb, c1["dr"]).astype(np.int64)))
+    out["rdf_config1"] = {"workload": "config 1, RDF O-O 1000 atoms x 100 frames split over %d ranks, one NCCL all-reduce of 149 x i64" % world,
+                          "e2e_ms": dt * 1e3, "e2e_pairs_per_s": 0.5 * 1000 * 999 * 100 / dt,
+                          "parity": parity, "parity_how": "all-reduced histogram bit-equal to rank 0 alone"}
+    hbar()
+    c3 = synth.config3(n_frames=5000)
+    g3 = nd.radial_nbr_counts(c3["waters"], c3["protein"], c3["cellDims"], 0, nb, 0.1, groupId=c3["groupId"], nGroups=c3["nGroups"])
+    hbar()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        g3 = nd.radial_nbr_counts(c3["waters"], c3["protein"], c3["cellDims"], 0, nb, 0.1, groupId=c3["groupId"], nGroups=c3["nGroups"])
+    dt = max_over_ranks(E, (time.perf_counter() - t0) / 2)
+    parity = None
+    if rank == 0:
+        alone = plf.py_getRadialNbrCounts(c3["waters"], c3["protein"], c3["cellDims"], 0, nb, 0.1, groupId=c3["groupId"], nGroups=c3["nGroups"])
+        parity = bool(np.array_equal(g3, alone.astype(np.int64)))
+    out["rdf_config3"] = {"workload": "config 3, residue-wise water RDF 20000 x 1231 x 5000 frames (76 groups) split over %d ranks, "
+                                      "one NCCL all-reduce of 76 x 149 x i64" % world,
+                          "e2e_ms": dt * 1e3, "e2e_pairs_per_s": 20000.0 * 1231 * 5000 / dt,
+                          "parity": parity, "parity_how": "all-reduced grouped histogram bit-equal to rank 0 alone"}
+    del c3
+    hbar()
+
+    # ---- RDF, config-5 shape, frames generated on the devices: u64 histogram + one NCCL all-reduce.
+    #      (i) ONE 64-frame trajectory with a parity pass on rank 0; (ii) config 5 at its stated length, 10 000 frames.
+    n = N_SIDE5 ** 3
+    Lbox = float(np.float32((n / 0.0334) ** (1.0 / 3.0)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    counts = torch.zeros(149, dtype=torch.int64, device=E.dev)
+
+    def sharded_pass(nF, reps, parity_pass):
+        fb, fe = frame_range(nF, rank, world)
+        own = fe - fb
+        xyz = torch.empty((n, max(own, 1), 3), dtype=torch.float32, device=E.dev)      # only this rank's frames live here
+        cell = torch.empty((max(own, 1), 3), dtype=torch.float32, device=E.dev)
+        gen_frames(E, xyz, cell, own, fb, fe, Lbox)
+
+        def go():
+            counts.zero_()
+            capi.check(lib.nda_dev_radial_nbr_counts(xyz.data_ptr(), n, xyz.data_ptr(), n, None, 1, counts.data_ptr(), 149,
+                                                     cell.data_ptr(), own, 0, own, 1, 0.1, E.st))
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # NCCL, on the current (= launching) stream
+        if parity_pass:
+            go()                                            # warm-up
+        hbar()
+        e0.record(E.stream)
+        for _ in range(reps):
+            go()
+        e1.record(E.stream)
         torch.cuda.synchronize()
-        parity = bool(np.array_equal(alone.cpu().numpy(), sharded))
-    pairs = 0.5 * n * (n - 1.0) * nF
-    out["rdf_config5"] = {"workload": "config-5 shape: %d O atoms, ONE %d-frame trajectory split over %d ranks, one NCCL all-reduce of 149 x u64"
-                                      % (n, nF, world),
-                          "ms_per_pass": ms, "pairs_per_s": pairs / (ms * 1e-3), "counts_total": int(sharded.sum()),
-                          "parity": parity, "parity_how": "all-reduced histogram bit-equal to rank 0 computing all %d frames alone" % nF}
-    del xyz, cell
+        ms = max_over_ranks(E, e0.elapsed_time(e1) / reps)
+        sharded = counts.cpu().numpy().copy()
+        del xyz, cell
+        parity = None
+        if parity_pass and rank == 0:
+            full = torch.empty((n, nF, 3), dtype=torch.float32, device=E.dev)
+            fcell = torch.empty((nF, 3), dtype=torch.float32, device=E.dev)
+            gen_frames(E, full, fcell, nF, 0, nF, Lbox)
+            alone = torch.zeros(149, dtype=torch.int64, device=E.dev)
+            capi.check(lib.nda_dev_radial_nbr_counts(full.data_ptr(), n, full.data_ptr(), n, None, 1, alone.data_ptr(), 149,
+                                                     fcell.data_ptr(), nF, 0, nF, 1, 0.1, E.st))
+            torch.cuda.synchronize()
+            parity = bool(np.array_equal(alone.cpu().numpy(), sharded))
+            del full, fcell
+        hbar()
+        return ms, sharded, parity
+
+    ms, sharded, parity = sharded_pass(64, 3, True)
+    out["rdf_config5"] = {"workload": "config-5 shape: %d O atoms, ONE 64-frame trajectory split over %d ranks, one NCCL all-reduce of 149 x u64"
+                                      % (n, world),
+                          "ms_per_pass": ms, "pairs_per_s": 0.5 * n * (n - 1.0) * 64 / (ms * 1e-3), "counts_total": int(sharded.sum()),
+                          "parity": parity, "parity_how": "all-reduced histogram bit-equal to rank 0 computing all 64 frames alone"}
+    if E.args.rdf_full_frames > 0:
+        nFull = E.args.rdf_full_frames
+        ms, sharded, _ = sharded_pass(nFull, 1, False)
+        out["rdf_config5_full"] = {"workload": "BASELINE configs[4] at its stated length: %d O atoms x %d frames (%.1f GB of coordinates generated in "
+                                               "HBM, %d frames per rank), one pass, one NCCL all-reduce" % (n, nFull, n * nFull * 12 / 1e9, nFull // world),
+                                   "seconds_per_pass": ms * 1e-3, "pairs_per_s": 0.5 * n * (n - 1.0) * nFull / (ms * 1e-3),
+                                   "counts_total": int(sharded.sum()),
+                                   "counts_per_frame_consistent_with_64_frame_run": bool(abs(sharded.sum() / nFull - out["rdf_config5"]["counts_total"] / 64.0)
+                                                                                         < 2e-3 * sharded.sum() / nFull)}
     hbar()
 
     # ---- the box's concurrent pinned-H2D ceiling: every rank copies 110 MB of contiguous pinned memory at the same time
@@ -783,7 +863,7 @@ def run_ours(args, rank, world, local_rank):
 
     E = Env()
     E.torch, E.dist, E.lib, E.capi, E.plf, E.synth = torch, dist, lib, _capi, plf, synth
-    E.dev, E.stream, E.st, E.rank, E.world, E.local_rank = dev, stream, st, rank, world, local_rank
+    E.dev, E.stream, E.st, E.rank, E.world, E.local_rank, E.args = dev, stream, st, rank, world, local_rank, args
 
     def step_resident():
         _capi.check(lib.nda_dev_within(d_xyz.data_ptr(), nA, nF, d_rs.data_ptr(), rs.size, d_os.data_ptr(), os_.size,
@@ -985,7 +1065,8 @@ def run_ours(args, rank, world, local_rank):
                          "kernel_ms": line["rdf"]["roofline"]["kernel_ms"], "kernel_pairs_per_s": line["rdf"]["roofline"]["kernel_pairs_per_s"],
                          "e2e_pairs_per_s": line["rdf"]["e2e"]["value"], "e2e_frames": line["rdf"]["e2e"]["frames"],
                          "inputs": "frames generated on the device (a 10 000-frame host array would be 39 GB); e2e on %d frames from pageable numpy"
-                                   % line["rdf"]["e2e"]["frames"], "filter": line["rdf"]["filter"]})
+                                   % line["rdf"]["e2e"]["frames"], "filter": line["rdf"]["filter"],
+                         "full_size": line["rdf"].get("full_size")})
             line["configs"] = rows
         threads = os.cpu_count() or 1
         if world == 1:

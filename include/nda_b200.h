@@ -248,6 +248,13 @@ int nda_dev_synth_water_box(float *d_xyz, float *d_cellDims, int n_side, int nbr
                             int frameBegin, int frameEnd, float L, float sigma, uint32_t seed,
                             void *stream);
 
+/* The same generator for a rank that owns frames [firstFrame, firstFrame + nFrames) of a long trajectory:
+ * they are written into columns [0, nFrames) of a LOCAL array d_xyz float32 [n_side^3][strideFrames][3]
+ * (and rows [0, nFrames) of d_cellDims), bit-identical to the corresponding frames of the full array. */
+int nda_dev_synth_water_box_slice(float *d_xyz, float *d_cellDims, int n_side, int strideFrames,
+                                  int firstFrame, int nFrames, float L, float sigma, uint32_t seed,
+                                  void *stream);
+
 /* Dependent-free FFMA loop on every SM: returns the measured FP32 rate in TFLOP/s
  * (FMA = 2 flop).  variant 0 = scalar FFMA, 1 = packed fma.rn.f32x2. */
 int nda_measure_fp32_peak(int variant, double *tflops);

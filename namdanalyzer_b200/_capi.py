@@ -70,6 +70,8 @@ SIGNATURES = {
                                           c_int, c_int, c_int, c_void_p]),
     "nda_dev_synth_water_box": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                         ctypes.c_uint32, c_void_p]),
+    "nda_dev_synth_water_box_slice": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
+                                              ctypes.c_uint32, c_void_p]),
     "nda_measure_fp32_peak": (c_int, [c_int, c_f64p]),
     "nda_last_stats": (c_int, [c_f64p]),
     "nda_last_kernel_ms": (c_int, [c_f64p, c_i32p]),

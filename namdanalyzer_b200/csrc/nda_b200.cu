@@ -2437,10 +2437,32 @@ int nda_dev_synth_water_box(float *d_xyz, float *d_cellDims, int n_side, int nF,
     NDA_ENTER();
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const unsigned n = (unsigned)n_side * n_side * n_side;
-    for (int f0 = fb; f0 < fe; f0 += 32768) {
-        const int nFc = std::min(32768, fe - f0);
-        dim3 grid((n + 255) / 256, nFc);
+    for (int f0 = fb; f0 < fe; f0 += 32768 * SYNTH_FB) {
+        const int nFc = std::min(32768 * SYNTH_FB, fe - f0);
+        dim3 grid((n + 255) / 256, (nFc + SYNTH_FB - 1) / SYNTH_FB);
         synth_water_box_kernel<<<grid, 256, 0, st>>>(d_xyz, d_cellDims, n_side, nF, f0, nFc, L, sigma, seed);
+        LAUNCHED();
+    }
+    return NDA_OK;
+}
+
+// frames [firstFrame, firstFrame + nFrames) of the same generator into columns [0, nFrames) of a LOCAL array with a row
+// stride of strideFrames frames: a rank that owns a frame range of a long trajectory generates only its own frames
+int nda_dev_synth_water_box_slice(float *d_xyz, float *d_cellDims, int n_side, int strideFrames, int firstFrame, int nFrames,
+                                  float L, float sigma, uint32_t seed, void *stream)
+{
+    if (!d_xyz || !d_cellDims || n_side <= 0 || n_side > 1024 || firstFrame < 0 || nFrames < 0 || nFrames > strideFrames)
+        return fail(NDA_ERR_ARG, "bad argument");
+    if (nFrames == 0) return NDA_OK;
+    NDA_ENTER();
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const unsigned n = (unsigned)n_side * n_side * n_side;
+    // the kernel writes frame f at column f: point it firstFrame columns before the local array
+    float *xyz0 = d_xyz - (ptrdiff_t)firstFrame * 3, *cell0 = d_cellDims - (ptrdiff_t)firstFrame * 3;
+    for (int f0 = firstFrame; f0 < firstFrame + nFrames; f0 += 32768 * SYNTH_FB) {
+        const int nFc = std::min(32768 * SYNTH_FB, firstFrame + nFrames - f0);
+        dim3 grid((n + 255) / 256, (nFc + SYNTH_FB - 1) / SYNTH_FB);
+        synth_water_box_kernel<<<grid, 256, 0, st>>>(xyz0, cell0, n_side, strideFrames, f0, nFc, L, sigma, seed);
         LAUNCHED();
     }
     return NDA_OK;
