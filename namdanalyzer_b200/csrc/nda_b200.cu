@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include <nvtx3/nvToolsExt.h>
+#include <omp.h>
 #include <nccl.h>
 #include <type_traits>
 #include <dlfcn.h>
@@ -65,6 +66,7 @@ struct Config {
     int    subpassFrames = 0;       // NDA_SUBPASS_FRAMES: device API in frame sub-passes of this size (0 = one pass)
     int    compatCuda = 0;          // NDA_COMPAT_CUDA: getWithin also flags every refSel atom (legacy CUDA build, SURVEY B-1)
     int    nvtx = 1;                // NDA_NVTX=0 switches the NVTX ranges off
+    int    sideTeam = 0;            // NDA_SIDE_TEAM=1: the mask scatter runs beside the row gather on a quarter of the team (measured: no gain)
     int    headTaper = 0;           // NDA_HEAD_TAPER=1: small head chunks for pageable inputs (measured SLOWER, see Uploader::begin)
 };
 static Config g_cfg;
@@ -75,7 +77,7 @@ static const char *const kOptionNames[] = {
     "NDA_FILTER", "NDA_TC_RANGE_FACTOR", "NDA_TC_MAX_FRACTION", "NDA_TC_ALLOW_PADDING", "NDA_NO_CELL_CACHE",
     "NDA_STRICT_SLOW", "NDA_TC_NO_SURE", "NDA_TC_TRACE", "NDA_CTAS_PER_SM", "NDA_DEBUG", "NDA_HOST_THREADS",
     "NDA_UPLOAD_CHUNKS", "NDA_WITHIN_CHUNKS", "NDA_NO_TAPER", "NDA_TAPER_LEVELS", "NDA_COPY_STREAMS",
-    "NDA_D2H_COPY_ENGINE", "NDA_COLLECTIVE", "NDA_SUBPASS_FRAMES", "NDA_COMPAT_CUDA", "NDA_NVTX", "NDA_HEAD_TAPER"};
+    "NDA_D2H_COPY_ENGINE", "NDA_COLLECTIVE", "NDA_SUBPASS_FRAMES", "NDA_COMPAT_CUDA", "NDA_NVTX", "NDA_HEAD_TAPER", "NDA_SIDE_TEAM"};
 
 // value == nullptr or "": back to the default
 static bool apply_option(Config &c, const char *name, const char *v)
@@ -115,6 +117,7 @@ static bool apply_option(Config &c, const char *name, const char *v)
     else if (!strcmp(name, "NDA_COMPAT_CUDA")) flag(c.compatCuda, 0);
     else if (!strcmp(name, "NDA_NVTX")) num(c.nvtx, 1, 0, 1);
     else if (!strcmp(name, "NDA_HEAD_TAPER")) num(c.headTaper, 0, 0, 1);
+    else if (!strcmp(name, "NDA_SIDE_TEAM")) num(c.sideTeam, 0, 0, 1);
     else return false;
     return true;
 }
@@ -1131,7 +1134,12 @@ struct Uploader {
     float *dev(int i, int k) const { return c.raw[i][k & 1].as<float>(); }
 
     // enqueue the upload of chunk k on the copy stream (gathering on the host first if pageable)
-    int issue(int k)
+    // `side`, if given, is host work that does not depend on this chunk (the within path hands in the mask scatter of an
+    // earlier chunk).  By default the whole team runs it after the gather.  NDA_SIDE_TEAM=1 runs it BESIDE the gather on a
+    // quarter of the team -- measured on a 16-core B200 host (config 2 from plain numpy): 4.05-4.27 ms per call against
+    // 3.92-4.06 ms, the gather loses as much with 12 threads as the overlap wins; kept as a switch for the record.
+    // side(part, parts) must cover part = 0 .. parts - 1.
+    int issue(int k, const std::function<void(int, int)> *side = nullptr)
     {
         NvtxRange nv("nda:upload_chunk", c.cfg.nvtx);
         const int b = k & 1, a0 = f0(k), wc = f1(k) - a0;
@@ -1139,6 +1147,7 @@ struct Uploader {
         bool anyStage = false;
         for (auto &a : arr) anyStage = anyStage || (!a.pinned && a.nRows > 0);
         if (anyStage) CK(cudaEventSynchronize(c.evCopied[b]));           // staging buffer b has been consumed
+        bool sideDone = side == nullptr;
         for (size_t i = 0; i < arr.size(); ++i) {
             UploadArray &a = arr[i];
             if (a.pinned || a.nRows == 0) continue;
@@ -1146,18 +1155,35 @@ struct Uploader {
             const float *src = a.host;
             const int nRuns = (int)a.runs.size();
             const long long nFl = nF;
-            #pragma omp parallel num_threads(c.hostThreads) if (a.nRows * w > (1u << 20))
+            const int nRows = a.nRows;
+            const bool par = (size_t)nRows * w > (1u << 20);
+            const int T = par ? std::max(1, c.hostThreads) : 1;
+            const int S = (!sideDone && c.cfg.sideTeam && T >= 8) ? T / 4 : 0;   // threads that run the side job
+            #pragma omp parallel num_threads(T) if (par)
             {
-                #pragma omp for schedule(static) nowait
-                for (int r = 0; r < a.nRows; ++r) {
-                    // locate the run of uploaded row r (runs are few; a linear scan is enough)
+                const int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+                const int s = (nt == T) ? S : 0;                              // a smaller team than asked for: no split
+                if (tid >= nt - s) {
+                    (*side)(tid - (nt - s), s);
+                } else {
+                    const int g = nt - s;
+                    const int r0 = (int)((long long)nRows * tid / g), r1 = (int)((long long)nRows * (tid + 1) / g);
                     int q = 0;
-                    while (q + 1 < nRuns && a.runs[q + 1].dstRow <= r) ++q;
-                    const long long srcRow = a.runs[q].srcRow + (long long)(r - a.runs[q].dstRow) * a.runs[q].stride;
-                    // (streaming stores were tried here: no faster for 2.5 KB rows, far slower for 24-byte rows)
-                    memcpy(dst + (size_t)r * w, src + (srcRow * nFl + a0) * 3, w);
+                    for (int r = r0; r < r1; ++r) {
+                        // locate the run of uploaded row r (runs are few and r ascends: the scan resumes)
+                        while (q + 1 < nRuns && a.runs[q + 1].dstRow <= r) ++q;
+                        const long long srcRow = a.runs[q].srcRow + (long long)(r - a.runs[q].dstRow) * a.runs[q].stride;
+                        // (streaming stores were tried here: no faster for 2.5 KB rows, far slower for 24-byte rows)
+                        memcpy(dst + (size_t)r * w, src + (srcRow * nFl + a0) * 3, w);
+                    }
                 }
+                if (tid == 0 && s > 0) sideDone = true;                       // (every thread of the side team has been started)
             }
+        }
+        if (!sideDone) {                                                      // no gather to hide behind: the whole team
+            const int T = std::max(1, c.hostThreads);
+            #pragma omp parallel num_threads(T)
+            (*side)(omp_get_thread_num(), omp_get_num_threads());
         }
         CK(cudaStreamWaitEvent(c.copyStream, c.evDone[b], 0));             // device buffer b is free again
         // strided 2-D DMA from pinned memory runs at about half the link rate on one copy engine,
@@ -1710,24 +1736,31 @@ static int within_shard(Ctx &c, const float *allAtoms, int nAtoms, int nF, const
     CK(cudaStreamWaitEvent(st, c.evSetupCopy, 0));
     CK(cudaEventRecord(c.ev0, st));
 
-    const int hostThreads = c.hostThreads;
-    (void)hostThreads;                                      // (used by the OpenMP pragma below)
-    auto scatter = [&](int k) {                             // host: set the 1s of chunk k
+    // host: set the 1s of frames [f0, f1) (relative to fb).  ~6e5 cache-missing stores for config 2, spread over threads:
+    // part p of `parts` takes every parts-th frame block
+    auto scatter_part = [&](int f0, int f1, int part, int parts) {
         if (!out) return;
-        const int f0 = up.f0(k) - fb, f1 = up.f1(k) - fb;
-        // ~6e5 cache-missing stores for config 2: spread the frames over the host threads
-        #pragma omp parallel for schedule(static) num_threads(hostThreads) if (f1 - f0 >= 16)
-        for (int f = f0; f < f1; ++f) {
+        const int n = f1 - f0;
+        const int a = f0 + (int)((long long)n * part / parts), b = f0 + (int)((long long)n * (part + 1) / parts);
+        for (int f = a; f < b; ++f) {
             const uint32_t *row = hbits + (size_t)f * words;
             for (int w = 0; w < words; ++w) {
                 uint32_t v = row[w];
                 while (v) {                                  // the reference only ever stores 1 (getWithin.cpp:77,83)
-                    const int b = __builtin_ctz(v);
+                    const int bpos = __builtin_ctz(v);
                     v &= v - 1;
-                    out[(size_t)outSel[w * 32 + b] * nF + fb + f] = 1;
+                    out[(size_t)outSel[w * 32 + bpos] * nF + fb + f] = 1;
                 }
             }
         }
+    };
+    const int hostThreads = c.hostThreads;
+    (void)hostThreads;                                      // (used by the OpenMP pragma below)
+    auto scatter = [&](int k) {                             // chunk k with the whole team
+        if (!out) return;
+        const int f0 = up.f0(k) - fb, f1 = up.f1(k) - fb;
+        #pragma omp parallel num_threads(hostThreads) if (f1 - f0 >= 16)
+        scatter_part(f0, f1, omp_get_thread_num(), omp_get_num_threads());
     };
 
     CK(cudaEventRecord(c.evSetup, st));                     // lane 1 must see cell / selections uploaded
@@ -1755,11 +1788,23 @@ static int within_shard(Ctx &c, const float *allAtoms, int nAtoms, int nF, const
             LAUNCHED();
         }
         CK(cudaEventRecord(c.evBits[buf], ls));
-        if (k + 1 < nChunks) { rc = up.issue(k + 1); if (rc) return rc; }   // host gathers k+1 while the GPU works on k
-        ht.mark("enq");
-        if (k > 0) {                                         // ... and scatters chunk k-1
+        // host: gather chunk k+1 while the GPU works on k, and -- beside the gather, on a quarter of the team -- set the 1s
+        // of chunk k-1, whose bitmask has long arrived
+        if (k > 0) {
             CK(cudaEventSynchronize(c.evBits[buf ^ 1]));
             ht.mark("wait");
+        }
+        if (k + 1 < nChunks) {
+            if (k > 0 && out) {
+                const int sf0 = up.f0(k - 1) - fb, sf1 = up.f1(k - 1) - fb;
+                const std::function<void(int, int)> side = [&, sf0, sf1](int part, int parts) { scatter_part(sf0, sf1, part, parts); };
+                rc = up.issue(k + 1, &side);
+            } else {
+                rc = up.issue(k + 1);
+            }
+            if (rc) return rc;
+            ht.mark("gather+scat");
+        } else if (k > 0) {
             scatter(k - 1);
             ht.mark("scat");
         }
