@@ -5,7 +5,7 @@ Run in the BUILD container only (needs /root/reference and oracle/_ref, i.e.
 `make -C oracle ref`):
 
     python tests/golden/make_golden.py            # golden_ref_strict.npz, ubq_ws_fixture.npz
-    python tests/golden/make_golden.py --full     # golden_ref_strict_full.npz (configs 2 and 5 at full size, ~3 min)
+    python tests/golden/make_golden.py --full     # golden_ref_strict_full.npz (configs 2-5 at or near full size, ~15 min)
 
 What it writes
   ubq_ws_fixture.npz   inputs taken from the reference's own test trajectory
@@ -191,9 +191,10 @@ def bitmask_words(m, outSel):
 
 
 def main_full():
-    """golden_ref_strict_full.npz: the two BASELINE workloads whose full size the GPU suite can afford to pin --
-    config 2 at all 1000 frames (hits per frame + CRC of the bitmask) and config 5 at 69^3 = 328 509 atoms,
-    one frame (5.4e10 pairs: about a minute of the reference's OpenMP code here)."""
+    """golden_ref_strict_full.npz: the BASELINE workloads at (or near) full size --
+    config 2 at all 1000 frames (hits per frame + CRC of the bitmask), config 5 at 69^3 = 328 509 atoms, one frame
+    (5.4e10 pairs: about a minute of the reference's OpenMP code here), config 3 at 200 frames x 76 residues and
+    config 4 at all 10 000 frames."""
     from namdanalyzer_b200 import synth
     from oracle.ref import RefLib
     ref = RefLib("strict")
@@ -211,6 +212,23 @@ def main_full():
     c = synth.config5(n_side=69, n_frames=1)
     out["c5full_crc"] = crc(c["sel1"], c["cellDims"])
     out["c5full_counts"] = ref.rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, nb, 0.1, 15.0)
+    # config 3, 200 frames, all 76 residues, one reference call per residue (4.9e9 pairs)
+    c = synth.config3(n_frames=200)
+    out["c3big_crc"] = crc(c["waters"], c["protein"], c["cellDims"])
+    g = np.zeros((c["nGroups"], nb), np.int64)
+    for r in range(c["nGroups"]):
+        sel = np.ascontiguousarray(c["protein"][c["groupId"] == r])
+        g[r] = ref.rdf_counts(c["waters"], sel, c["cellDims"], 0, nb, 0.1, 15.0)
+    out["c3big_group_counts"] = g
+    # config 4 at its stated size: 10 000 frames; per-frame float32 distances, mean formed in float64
+    c = synth.config4(n_frames=10000)
+    out["c4full_crc"] = crc(c["sel1"], c["sel2"], c["cellDims"])
+    acc = np.zeros((7, 1231), np.float64)
+    for f0 in range(0, 10000, 500):
+        d = ref.distances_per_frame(np.ascontiguousarray(c["sel1"][:, f0:f0 + 500]), np.ascontiguousarray(c["sel2"][:, f0:f0 + 500]),
+                                    c["cellDims"][f0:f0 + 500], 0)
+        acc += d.astype(np.float64).sum(0)
+    out["c4full_mean64"] = acc / 10000.0
     np.savez_compressed(os.path.join(HERE, "golden_ref_strict_full.npz"), **out)
     for k, v in out.items():
         print("%-24s %-12s %s" % (k, v.dtype, v.shape))

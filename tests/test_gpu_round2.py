@@ -370,3 +370,23 @@ def test_repeated_calls_are_bit_identical():
     """tools/repeat_check.py: the same 300-frame config-2 call 60 times -- every bitmask identical to the first"""
     out = _run_tool("repeat_check.py", {"NF": "300", "REPS": "60"})
     assert "calls with differences: 0" in out, out[-500:]
+
+
+def test_config3_200_frames_and_config4_10000_frames_against_the_reference(golden_full):
+    """configs[2] (residue-wise water RDF, one grouped launch against 76 reference calls per frame set) on 200 frames, and
+    configs[3] (getDistances 7 x 1231) at its stated 10 000 frames, against the reference's own code"""
+    c = synth.config3(n_frames=200)
+    assert _crc(c["waters"], c["protein"], c["cellDims"]) == int(golden_full["c3big_crc"])
+    got = plf.py_getRadialNbrCounts(c["waters"], c["protein"], c["cellDims"], 0, NB, 0.1, groupId=c["groupId"], nGroups=c["nGroups"])
+    assert _capi.load().nda_last_filter() == 100
+    assert np.array_equal(got.astype(np.int64), golden_full["c3big_group_counts"])
+    c = synth.config4(n_frames=10000)
+    assert _crc(c["sel1"], c["sel2"], c["cellDims"]) == int(golden_full["c4full_crc"])
+    out = np.zeros((7, 1231), np.float32)
+    plf.py_getDistances(c["sel1"], c["sel2"], out, c["cellDims"], 0)
+    want = golden_full["c4full_mean64"]
+    assert np.max(np.abs(out.astype(np.float64) - want) / np.maximum(want, 1e-30)) <= 1e-6      # north_star tolerance, float32 result
+    s = plf.py_getDistancesSum(c["sel1"], c["sel2"], c["cellDims"], 0) / 10000.0
+    nz = want > 0
+    assert np.max(np.abs(s[nz] - want[nz]) / want[nz]) <= 1e-12                                  # the float64 sums themselves
+    assert np.all(s[~nz] == 0.0)                                                                 # an atom against itself

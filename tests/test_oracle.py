@@ -242,3 +242,19 @@ def test_port_against_full_size_config2_golden():
     bits = np.packbits(pad, axis=1, bitorder="little")
     got = np.array([zlib.crc32(bits[i].tobytes()) for i in range(frames.size)], np.uint32)
     assert np.array_equal(got, g["c2full_bits_frame_crc"][frames])
+
+
+def test_port_against_config3_200_frames_and_config4_full_golden():
+    """the C port against the reference's own output for config 3 (76 groups, 200 frames, ONE grouped pass against the
+    reference's one call per residue) and config 4 at its stated 10 000 frames"""
+    import os
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_ref_strict_full.npz")))
+    c = synth.config3(n_frames=200)
+    assert crc(c["waters"], c["protein"], c["cellDims"]) == g["c3big_crc"]
+    got = port.rdf_counts(c["waters"], c["protein"], c["cellDims"], 0, NB, 0.1, groupId=c["groupId"], nGroups=c["nGroups"])
+    assert np.array_equal(got.astype(np.int64), g["c3big_group_counts"])
+    c = synth.config4(n_frames=10000)
+    assert crc(c["sel1"], c["sel2"], c["cellDims"]) == g["c4full_crc"]
+    s = port.distances_sum(c["sel1"], c["sel2"], c["cellDims"], 0) / 10000.0
+    want = g["c4full_mean64"]
+    assert np.max(np.abs(s - want) / np.maximum(want, 1e-30)) <= 1e-12
