@@ -18,7 +18,9 @@ what = sys.argv[1] if len(sys.argv) > 1 else "all"
 WITHIN_FRAMES = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 lib = _capi.load()
 dev = torch.device("cuda", 0)
-st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+stream = torch.cuda.Stream(device=dev)            # explicit: the library treats a NULL stream as "use my own"
+torch.cuda.set_stream(stream)
+st = ctypes.c_void_p(stream.cuda_stream)
 
 
 def ms():
@@ -39,7 +41,14 @@ if what in ("within", "all"):
                                        os_.numel(), bits.data_ptr(), None, cell.data_ptr(), 3.0, 0, nF, st))
         t = ms()
     pairs = 1231.0 * 7923.0 * nF
-    print("within: %.3f ms, %.3e pairs/s" % (t, pairs / t * 1e3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(40):                                   # whole resident step: pack + prep + pair kernel
+        _capi.check(lib.nda_dev_within(xyz.data_ptr(), xyz.shape[0], nF, rs.data_ptr(), rs.numel(), os_.data_ptr(),
+                                       os_.numel(), bits.data_ptr(), None, cell.data_ptr(), 3.0, 0, nF, st))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    print("within: %.3f ms, %.3e pairs/s; whole step %.4f ms" % (t, pairs / t * 1e3, e0.elapsed_time(e1) / 40))
 
 if what in ("rdf", "all"):
     n_side, nF = 48, 2
