@@ -100,3 +100,18 @@ def test_product_does_not_import_the_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "minimage_port" not in src and "libref_" not in src, f
+
+
+def test_options_and_device_list_without_a_gpu():
+    """nda_set_option needs no GPU (the switches are plain host state, the environment is read once); an unknown name is
+    an error; the device-list calls fail cleanly when there is no device instead of falling back to anything"""
+    lib = _capi.load()
+    assert lib.nda_set_option(b"NDA_FILTER", b"fold2") == 0
+    assert lib.nda_set_option(b"NDA_FILTER", None) == 0
+    assert lib.nda_set_option(b"NDA_NO_SUCH_SWITCH", b"1") != 0
+    assert b"unknown option" in lib.nda_last_error()
+    if lib.nda_device_count() == 0:
+        arr = (ctypes.c_int * 2)(0, 1)
+        assert lib.nda_set_devices(arr, 2) != 0
+        with pytest.raises(RuntimeError):
+            _capi.set_devices([0])
