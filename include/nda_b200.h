@@ -71,7 +71,7 @@ int  nda_last_collective(void);
  * NDA_TC_RANGE_FACTOR, NDA_TC_MAX_FRACTION, NDA_TC_ALLOW_PADDING, NDA_NO_CELL_CACHE, NDA_STRICT_SLOW,
  * NDA_TC_NO_SURE, NDA_CTAS_PER_SM, NDA_DEBUG, NDA_HOST_THREADS, NDA_UPLOAD_CHUNKS, NDA_WITHIN_CHUNKS,
  * NDA_NO_TAPER, NDA_TAPER_LEVELS, NDA_COPY_STREAMS, NDA_D2H_COPY_ENGINE, NDA_COLLECTIVE=nccl|host,
- * NDA_SUBPASS_FRAMES, NDA_COMPAT_CUDA, NDA_NVTX, NDA_HEAD_TAPER, NDA_SIDE_TEAM) are read ONCE, when the library is first used; afterwards
+ * NDA_SUBPASS_FRAMES, NDA_COMPAT_CUDA, NDA_NVTX, NDA_HEAD_TAPER, NDA_SIDE_TEAM, NDA_DENSE_FRACTION) are read ONCE, when the library is first used; afterwards
  * only this call changes a value.  value NULL or "" restores the default.  No switch changes a result,
  * except NDA_COMPAT_CUDA=1: nda_get_within then also marks every refSel atom in every frame, as the
  * reference's legacy CUDA build does (lib/cuda/src/getWithin.cu:27-28). */

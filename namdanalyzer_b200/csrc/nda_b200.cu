@@ -67,6 +67,7 @@ struct Config {
     int    compatCuda = 0;          // NDA_COMPAT_CUDA: getWithin also flags every refSel atom (legacy CUDA build, SURVEY B-1)
     int    nvtx = 1;                // NDA_NVTX=0 switches the NVTX ranges off
     int    sideTeam = 0;            // NDA_SIDE_TEAM=1: the mask scatter runs beside the row gather on a quarter of the team (measured: no gain)
+    double denseFraction = 0.25;    // NDA_DENSE_FRACTION: RDF frames whose cut-off sphere exceeds this share of the cell run all-exact (0 = never)
     int    headTaper = 0;           // NDA_HEAD_TAPER=1: small head chunks for pageable inputs (measured SLOWER, see Uploader::begin)
 };
 static Config g_cfg;
@@ -77,7 +78,7 @@ static const char *const kOptionNames[] = {
     "NDA_FILTER", "NDA_TC_RANGE_FACTOR", "NDA_TC_MAX_FRACTION", "NDA_TC_ALLOW_PADDING", "NDA_NO_CELL_CACHE",
     "NDA_STRICT_SLOW", "NDA_TC_NO_SURE", "NDA_TC_TRACE", "NDA_CTAS_PER_SM", "NDA_DEBUG", "NDA_HOST_THREADS",
     "NDA_UPLOAD_CHUNKS", "NDA_WITHIN_CHUNKS", "NDA_NO_TAPER", "NDA_TAPER_LEVELS", "NDA_COPY_STREAMS",
-    "NDA_D2H_COPY_ENGINE", "NDA_COLLECTIVE", "NDA_SUBPASS_FRAMES", "NDA_COMPAT_CUDA", "NDA_NVTX", "NDA_HEAD_TAPER", "NDA_SIDE_TEAM"};
+    "NDA_D2H_COPY_ENGINE", "NDA_COLLECTIVE", "NDA_SUBPASS_FRAMES", "NDA_COMPAT_CUDA", "NDA_NVTX", "NDA_HEAD_TAPER", "NDA_SIDE_TEAM", "NDA_DENSE_FRACTION"};
 
 // value == nullptr or "": back to the default
 static bool apply_option(Config &c, const char *name, const char *v)
@@ -118,6 +119,7 @@ static bool apply_option(Config &c, const char *name, const char *v)
     else if (!strcmp(name, "NDA_NVTX")) num(c.nvtx, 1, 0, 1);
     else if (!strcmp(name, "NDA_HEAD_TAPER")) num(c.headTaper, 0, 0, 1);
     else if (!strcmp(name, "NDA_SIDE_TEAM")) num(c.sideTeam, 0, 0, 1);
+    else if (!strcmp(name, "NDA_DENSE_FRACTION")) { c.denseFraction = d.denseFraction; if (has && atof(v) >= 0.0) c.denseFraction = atof(v); }
     else return false;
     return true;
 }
@@ -688,7 +690,12 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
     }
     // shared memory: as many warp-private histogram copies as still allow PAIR_MIN_CTAS CTAs per SM
     const size_t perCta = ((size_t)227 * 1024) / PAIR_MIN_CTAS - 1024;
-    const int bTile = grouped ? PAIR_BTILE_GROUPED : PAIR_BTILE;
+    // The kernel with 256-atom B tiles (the grouped one; an absent group array means group 0 for every atom) also
+    // serves SMALL ungrouped calls: with 1024-atom tiles a call like BASELINE config 1 (1000 atoms x 100 frames) has 200
+    // work items for ~590 resident CTAs and runs on a third of the GPU.
+    const long long items1024 = (long long)(fe - fb) * ((n1 + PAIR_ATILE - 1) / PAIR_ATILE) * ((n2 + PAIR_BTILE - 1) / PAIR_BTILE);
+    const bool smallB = grouped || items1024 < 16LL * c.numSMs;
+    const int bTile = smallB ? PAIR_BTILE_GROUPED : PAIR_BTILE;
     const size_t base = pair_smem_base(bTile);
     size_t histBudget = (perCta > base) ? perCta - base : 0;
     // groups in batches that fit the shared histogram (see dev_rdf_tc)
@@ -737,7 +744,7 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
     int ctasPerSM = 0;
     const void *kfn = nullptr;
 #define NDA_RDF_CASE(G, F) case F: kfn = (const void *)rdf_kernel<G, F>; break;
-    if (grouped) switch (filter) { NDA_RDF_CASE(true, 0) NDA_RDF_CASE(true, 1) NDA_RDF_CASE(true, 2) NDA_RDF_CASE(true, 3) NDA_RDF_CASE(true, 4) NDA_RDF_CASE(true, 5) }
+    if (smallB)  switch (filter) { NDA_RDF_CASE(true, 0) NDA_RDF_CASE(true, 1) NDA_RDF_CASE(true, 2) NDA_RDF_CASE(true, 3) NDA_RDF_CASE(true, 4) NDA_RDF_CASE(true, 5) }
     else         switch (filter) { NDA_RDF_CASE(false, 0) NDA_RDF_CASE(false, 1) NDA_RDF_CASE(false, 2) NDA_RDF_CASE(false, 3) NDA_RDF_CASE(false, 4) NDA_RDF_CASE(false, 5) }
 #undef NDA_RDF_CASE
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -750,7 +757,7 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
         const long long rows = (long long)pass * a.nATiles;
         const long long chunksWanted = std::max<long long>(1, (target + rows - 1) / rows);
         long long ct = (a.nBTiles + chunksWanted - 1) / chunksWanted;
-        ct = std::max<long long>(2, std::min<long long>(32, ct));
+        ct = std::max<long long>((smallB && !grouped) ? 1 : 2, std::min<long long>(32, ct));
         a.chunkTiles = (int)std::min<long long>(ct, a.nBTiles);
         a.nBChunks = (a.nBTiles + a.chunkTiles - 1) / a.chunkTiles;
     }
@@ -768,7 +775,7 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
             if (rc) return rc;
         }
         prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
-                                                             L.fp.as<FrameParams>(), stats);
+                                                             L.fp.as<FrameParams>(), stats, c.cfg.denseFraction);
         LAUNCHED();
         a.A = L.packA.as<float4>();
         a.B = sameSel ? a.A : L.packB.as<float4>();
@@ -787,7 +794,7 @@ static int dev_rdf(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_sel1, i
             if (g0 > 0) CK(cudaMemsetAsync(work, 0, 8, st));
             NvtxRange nv("nda:rdf_kernel", c.cfg.nvtx);
             CK(c.kev_record(st));
-            if (grouped) switch (filter) { NDA_RDF_LAUNCH(true, 0) NDA_RDF_LAUNCH(true, 1) NDA_RDF_LAUNCH(true, 2) NDA_RDF_LAUNCH(true, 3) NDA_RDF_LAUNCH(true, 4) NDA_RDF_LAUNCH(true, 5) }
+            if (smallB)  switch (filter) { NDA_RDF_LAUNCH(true, 0) NDA_RDF_LAUNCH(true, 1) NDA_RDF_LAUNCH(true, 2) NDA_RDF_LAUNCH(true, 3) NDA_RDF_LAUNCH(true, 4) NDA_RDF_LAUNCH(true, 5) }
             else         switch (filter) { NDA_RDF_LAUNCH(false, 0) NDA_RDF_LAUNCH(false, 1) NDA_RDF_LAUNCH(false, 2) NDA_RDF_LAUNCH(false, 3) NDA_RDF_LAUNCH(false, 4) NDA_RDF_LAUNCH(false, 5) }
             LAUNCHED();
             CK(c.kev_record(st));
@@ -879,7 +886,7 @@ static int dev_within(Ctx &c, Ctx::Lane &L, cudaStream_t st, const float *d_all,
                              L.packB.as<float4>(), L.maxAbs.as<unsigned>(), d_cell, fold ? L.packBw.as<float4>() : nullptr, pairLayout);
             if (rc) return rc;
             prep_frames_kernel<<<(nFc + 127) / 128, 128, 0, st>>>(d_cell, f0, nFc, L.maxAbs.as<unsigned>(), T,
-                                                                 L.fp.as<FrameParams>(), stats);
+                                                                 L.fp.as<FrameParams>(), stats, 0.0);
             LAUNCHED();
             a.A = L.packA.as<float4>();
             a.B = L.packB.as<float4>();
