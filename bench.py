@@ -481,6 +481,11 @@ def configs_leg(E, headline):
     sync = torch.cuda.synchronize
     rows = []
 
+    def exact_frames():
+        st4 = (ctypes.c_double * 4)()
+        capi.check(lib.nda_last_stats(st4))
+        return int(st4[2])
+
     def row(i, workload, pairs, fn, calls, h2d, extra=None):
         fn()
         dt = timed_calls(fn, calls, sync)
@@ -502,9 +507,11 @@ def configs_leg(E, headline):
     def f1():
         o1[:] = 0
         plf.py_getRadialNbrDensity(c["sel1"], c["sel1"], o1, c["cellDims"], 1, c["maxR"], c["dr"])
-    row(1, "RDF O-O, 1000 O atoms x 100 frames, dr 0.1 maxR 15 (15 A in a 31 A cell: packed-FP32 filter)",
+    row(1, "RDF O-O, 1000 O atoms x 100 frames, dr 0.1 maxR 15 (15 A in a 31 A cell, 46 % of the pairs in range)",
         0.5 * 1000 * 999 * 100, f1, 5, c["sel1"].nbytes + c["cellDims"].nbytes,
-        lambda filt, k: {"filter": "tensor-core" if filt == 100 else "fp32 %d" % filt})
+        lambda filt, k: {"filter": ("tensor-core" if filt == 100 else "fp32 %d" % filt) +
+                                   (", all %d frames all-exact (dense range: every pair through the strict arithmetic)" % exact_frames()
+                                    if exact_frames() else "")})
     rows.append(headline)
     # 3: ResidueWiseWaterDensity('protein', dr 0.1, maxR 15): 76 residues, 20 000 water O, 5000 frames -- ONE grouped call
     c3 = synth.config3(n_frames=5000)
