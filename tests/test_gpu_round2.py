@@ -390,3 +390,28 @@ def test_config3_200_frames_and_config4_10000_frames_against_the_reference(golde
     nz = want > 0
     assert np.max(np.abs(s[nz] - want[nz]) / want[nz]) <= 1e-12                                  # the float64 sums themselves
     assert np.all(s[~nz] == 0.0)                                                                 # an atom against itself
+
+
+def test_dense_ranges_run_all_exact_with_identical_counts():
+    """Round 2: RDF frames whose cut-off sphere exceeds a quarter of the cell skip the filter (NDA_DENSE_FRACTION); small
+    ungrouped calls use the 256-atom-tile kernel.  Same counts either way, also when dense and sparse frames mix in a call"""
+    lib = _capi.load()
+    c = synth.config1(n_frames=6)
+    nb = synth.n_bins(c["dr"], c["maxR"])
+    want = port.rdf_counts(c["sel1"], c["sel1"], c["cellDims"], 1, nb, c["dr"])
+    st = (ctypes.c_double * 4)()
+    got = plf.py_getRadialNbrCounts(c["sel1"], c["sel1"], c["cellDims"], 1, nb, c["dr"])
+    _capi.check(lib.nda_last_stats(st))
+    assert np.array_equal(got, want) and int(st[2]) == 6            # all six frames all-exact
+    with _capi.options(NDA_DENSE_FRACTION="0"):
+        got = plf.py_getRadialNbrCounts(c["sel1"], c["sel1"], c["cellDims"], 1, nb, c["dr"])
+        _capi.check(lib.nda_last_stats(st))
+        assert np.array_equal(got, want) and int(st[2]) == 0        # the packed-FP32 filter + candidate ring
+    # frames 0-2 in the 31 A cell (dense for 15 A), frames 3-5 the same atoms in a 120 A cell (sparse): one call
+    cell = c["cellDims"].copy()
+    cell[3:] = 120.0
+    a, b = np.ascontiguousarray(c["sel1"][:600]), np.ascontiguousarray(c["sel1"][600:])
+    with _capi.options(NDA_FILTER="fold2"):
+        got = plf.py_getRadialNbrCounts(a, b, cell, 0, nb, c["dr"])
+        _capi.check(lib.nda_last_stats(st))
+    assert np.array_equal(got, port.rdf_counts(a, b, cell, 0, nb, c["dr"])) and int(st[2]) == 3
